@@ -1,0 +1,362 @@
+r"""Graph -> fused kernel plan.
+
+The reference executes one TF op per Keras layer (conv, BN, ReLU, add, pool, upsample,
+concat, ... -- roughly 10 launches and 10 HBM round trips per residual unit).  Here every
+convolution absorbs the layers around it:
+
+  [BatchNormalization] -> [ReLU] -> conv/sepconv -> [BatchNormalization] -> [ReLU] -> [add]
+   \__ prologue in the A-tile producer __/          \________ epilogue _______________/
+
+(the prologue is legal because the reference is pre-activated: layers.py:258-301,
+models/common.py:25-67; padding is applied after it, as Keras pads the activated tensor),
+`concatenate` and channel slices become views (`ld` / channel offset of dh_view), and
+UpSampling2D followed by add becomes one kernel.  Buffers are planned with liveness so a
+whole forward fits comfortably in HBM and micro-batches stay L2-resident.
+"""
+from collections import defaultdict
+
+CONV_OPS = ('conv', 'sepconv')
+DENSE_OUT_OPS = ('pose_regression_2d_context', 'pose_regression_2d', 'pose_regression_3d',
+                 'sam2d', 'kron', 'global_maxmin_softmax')
+
+
+class KOp(object):
+    """One kernel launch (or a short fixed sequence) of the C ABI."""
+    __slots__ = ('kind', 'ins', 'outs', 'attrs', 'pos')
+
+    def __init__(self, kind, ins, outs, attrs, pos):
+        self.kind = kind
+        self.ins = ins
+        self.outs = outs
+        self.attrs = attrs
+        self.pos = pos
+
+    def __repr__(self):
+        return 'K[%s %s -> %s]' % (self.kind, self.ins, self.outs)
+
+
+class Storage(object):
+    __slots__ = ('buf', 'c_off', 'ld')
+
+    def __init__(self, buf, c_off, ld):
+        self.buf = buf
+        self.c_off = c_off
+        self.ld = ld
+
+
+class Buffer(object):
+    __slots__ = ('id', 'kind', 'hw', 'ld', 'first', 'last', 'phys', 'is_output', 'is_input')
+
+    def __init__(self, id, kind, hw, ld):
+        self.id = id
+        self.kind = kind
+        self.hw = hw
+        self.ld = ld
+        self.first = None
+        self.last = -1
+        self.phys = None
+        self.is_output = False
+        self.is_input = False
+
+    @property
+    def floats_per_item(self):
+        return self.hw * self.ld
+
+
+class Plan(object):
+    def __init__(self):
+        self.kops = []
+        self.storage = {}      # tensor id -> Storage
+        self.buffers = []
+        self.phys = []         # physical slots: (kind, floats_per_item)
+        self.bn_folds = []     # bn node attrs whose (scale, shift) must be uploaded
+        self.stats = {}
+
+
+def _consumers(g):
+    cons = defaultdict(list)
+    for n in g.nodes:
+        for i, t in enumerate(n.inputs):
+            cons[t.id].append(n)
+    return cons
+
+
+def compile_graph(g):
+    cons = _consumers(g)
+    out_ids = set(t.id for t in g.outputs)
+
+    def sole_consumer(t, op):
+        if t.id in out_ids:
+            return None
+        c = cons[t.id]
+        if len(c) == 1 and c[0].op == op:
+            return c[0]
+        return None
+
+    # ---- phase 1: producer-side (epilogue) fusion for conv chains ----------------
+    chains = {}            # conv node id -> dict
+    fused_into = {}        # node id (bn/relu/add) -> conv node id that absorbed it as epilogue
+    add_claim = {}         # add node id -> conv node id
+    for n in g.nodes:
+        if n.op not in CONV_OPS:
+            continue
+        ch = {'conv': n, 'post_bn': None, 'post_relu': False, 'add': None, 'end': n.out, 'pos': n.id}
+        cur = n.out
+        b = sole_consumer(cur, 'bn')
+        if b is not None:
+            ch['post_bn'] = b
+            cur = b.out
+        r = sole_consumer(cur, 'relu')
+        if r is not None:
+            ch['post_relu'] = r
+            cur = r.out
+        ch['end_pre_add'] = cur
+        chains[n.id] = ch
+    # adds: absorbed by the last-created conv chain that ends exactly at one of its inputs
+    for n in g.nodes:
+        if n.op != 'add' or len(n.inputs) > 3:
+            continue
+        best = None
+        for t in n.inputs:
+            if t.id in out_ids or len(cons[t.id]) != 1:
+                continue
+            for cid, ch in chains.items():
+                if ch['end_pre_add'] is t:
+                    if best is None or cid > best:
+                        best = cid
+        # every residual must have the output resolution (true for keras add)
+        if best is not None:
+            chains[best]['add'] = n
+            add_claim[n.id] = best
+    for cid, ch in chains.items():
+        for key in ('post_bn', 'post_relu', 'add'):
+            nd = ch[key]
+            if nd:
+                fused_into[nd.id] = cid
+                ch['pos'] = max(ch['pos'], nd.id)
+                ch['end'] = nd.out
+
+    # ---- phase 2: consumer-side (prologue) fusion ---------------------------------
+    absorbed_edges = set()   # (producer node id, consumer node id) edges that need no materialisation
+    for cid, ch in chains.items():
+        n = ch['conv']
+        t = n.inputs[0]
+        pre_relu, pre_bn = False, None
+        if t.node.op == 'relu' and t.node.id not in fused_into:
+            pre_relu = True
+            absorbed_edges.add((t.node.id, n.id))
+            rnode = t.node
+            t = rnode.inputs[0]
+            if t.node.op == 'bn' and t.node.id not in fused_into:
+                pre_bn = t.node
+                absorbed_edges.add((t.node.id, rnode.id))   # provisional: valid if relu not materialised
+                t = t.node.inputs[0]
+        elif t.node.op == 'bn' and t.node.id not in fused_into:
+            pre_bn = t.node
+            absorbed_edges.add((t.node.id, n.id))
+            t = t.node.inputs[0]
+        ch['pre_relu'], ch['pre_bn'], ch['src'] = pre_relu, pre_bn, t
+
+    # which bn / relu nodes still need their own kernel?
+    def needs_materialise(nd):
+        if nd.id in fused_into:
+            return False
+        if nd.out.id in out_ids:
+            return True
+        for c in cons[nd.out.id]:
+            if (nd.id, c.id) in absorbed_edges:
+                # edge bn->relu only counts if that relu itself is not materialised
+                if c.op == 'relu' and nd.op == 'bn' and needs_materialise(c):
+                    return True
+                continue
+            return True
+        return False
+
+    # ---- phase 3: emit kernel ops in schedule order --------------------------------
+    plan = Plan()
+    emitted = []           # (pos, seq, KOp)
+    seq = [0]
+
+    def emit(kind, ins, outs, attrs, pos):
+        k = KOp(kind, list(ins), list(outs), attrs, pos)
+        emitted.append((pos, seq[0], k))
+        seq[0] += 1
+        return k
+
+    up_fused = set()
+    for n in g.nodes:
+        op = n.op
+        if op == 'input':
+            continue
+        if op in CONV_OPS:
+            ch = chains[n.id]
+            res = []
+            if ch['add']:
+                res = [t for t in ch['add'].inputs if t is not ch['end_pre_add']]
+            attrs = dict(n.attrs)
+            attrs.update({'pre_relu': ch['pre_relu'], 'pre_bn': ch['pre_bn'].attrs if ch['pre_bn'] else None,
+                          'post_bn': ch['post_bn'].attrs if ch['post_bn'] else None,
+                          'post_relu': bool(ch['post_relu']), 'n_res': len(res)})
+            emit(op, [ch['src']] + res, [ch['end']], attrs, ch['pos'])
+            continue
+        if op in ('bn', 'relu'):
+            if needs_materialise(n):
+                src = n.inputs[0]
+                attrs = {'bn': n.attrs if op == 'bn' else None, 'relu': op == 'relu'}
+                # bn -> relu pair where only the relu is materialised: fold the bn in
+                if op == 'relu' and src.node.op == 'bn' and src.node.id not in fused_into \
+                        and not needs_materialise(src.node):
+                    attrs['bn'] = src.node.attrs
+                    src = src.node.inputs[0]
+                emit('affine', [src], [n.out], attrs, n.id)
+            continue
+        if op == 'add':
+            if n.id in add_claim:
+                continue
+            ups = [t for t in n.inputs if t.node.op == 'upsample' and t.id not in out_ids
+                   and len(cons[t.id]) == 1]
+            if len(n.inputs) == 2 and len(ups) >= 1:
+                u = ups[-1]
+                other = n.inputs[0] if n.inputs[1] is u else n.inputs[1]
+                up_fused.add(u.node.id)
+                emit('upsample_add', [other, u.node.inputs[0]], [n.out], {}, n.id)
+            else:
+                emit('add', n.inputs, [n.out], {}, n.id)
+            continue
+        if op == 'upsample':
+            # decided when its consumer add is visited; emit lazily below if not fused
+            emit('upsample?', [n.inputs[0]], [n.out], {'node': n.id}, n.id)
+            continue
+        if op in ('slice', 'concat'):
+            emit(op, n.inputs, [n.out], dict(n.attrs), n.id)
+            continue
+        # everything else maps 1:1 onto a kernel op
+        emit(op, n.inputs, n.outs, dict(n.attrs), n.id)
+
+    emitted.sort(key=lambda e: (e[0], e[1]))
+    kops = []
+    for _, _, k in emitted:
+        if k.kind == 'upsample?':
+            if k.attrs['node'] in up_fused:
+                continue
+            k.kind = 'upsample'
+        kops.append(k)
+
+    # ---- phase 4: storage ----------------------------------------------------------
+    tensors = {t.id: t for t in g.tensors}
+
+    def new_buffer(kind, hw, ld):
+        b = Buffer(len(plan.buffers), kind, hw, ld)
+        plan.buffers.append(b)
+        return b
+
+    def hw_of(t):
+        return t.shape[0] * t.shape[1]
+
+    written_by = {}
+    for k in kops:
+        for t in k.outs:
+            written_by[t.id] = k
+
+    # concat placement: claim inputs that are plain kernel outputs
+    placed = {}     # tensor id -> (concat out tensor, offset)
+    for k in kops:
+        if k.kind != 'concat':
+            continue
+        off = 0
+        copies = []
+        for t in k.ins:
+            w = written_by.get(t.id)
+            ok = (w is not None and w.kind not in ('slice', 'concat') and w.kind not in DENSE_OUT_OPS
+                  and t.id not in placed and t.id not in out_ids)
+            if ok:
+                placed[t.id] = (k.outs[0], off)
+            else:
+                copies.append((t, off))
+            off += t.channels
+        k.attrs['copies'] = copies
+
+    def storage_of(t):
+        s = plan.storage.get(t.id)
+        if s is not None:
+            return s
+        if t.id in placed:
+            parent, off = placed[t.id]
+            ps = storage_of(parent)
+            s = Storage(ps.buf, ps.c_off + off, ps.ld)
+        else:
+            w = written_by.get(t.id)
+            if w is not None and w.kind == 'slice':
+                ps = storage_of(w.ins[0])
+                s = Storage(ps.buf, ps.c_off + w.attrs['c0'], ps.ld)
+            else:
+                b = new_buffer(t.kind, hw_of(t), t.channels)
+                s = Storage(b, 0, t.channels)
+                if w is None:
+                    b.is_input = True
+        plan.storage[t.id] = s
+        return s
+
+    for t in g.inputs:
+        storage_of(t)
+    final_kops = []
+    for k in kops:
+        for t in k.ins:
+            storage_of(t)
+        for t in k.outs:
+            storage_of(t)
+        if k.kind == 'slice':
+            continue
+        if k.kind == 'concat':
+            for (t, off) in k.attrs['copies']:
+                final_kops.append(KOp('copy', [t], [k.outs[0]], {'c_off': off, 'channels': t.channels}, k.pos))
+            continue
+        final_kops.append(k)
+    plan.kops = final_kops
+
+    # ---- phase 5: liveness + physical slots -----------------------------------------
+    for i, k in enumerate(plan.kops):
+        for t in k.outs:
+            b = plan.storage[t.id].buf
+            if b.first is None:
+                b.first = i
+            b.last = max(b.last, i)
+        for t in k.ins:
+            b = plan.storage[t.id].buf
+            b.last = max(b.last, i)
+    for t in g.outputs:
+        plan.storage[t.id].buf.is_output = True
+    for b in plan.buffers:
+        if b.is_input:
+            b.first = -1
+        if b.first is None:
+            b.first = 0
+    free = defaultdict(list)
+    events = sorted(plan.buffers, key=lambda b: b.first)
+    active = []
+    for b in events:
+        # release finished buffers
+        still = []
+        for a in active:
+            if a.last < b.first and not a.is_output and not a.is_input:
+                free[(a.kind, a.floats_per_item)].append(a.phys)
+            else:
+                still.append(a)
+        active = still
+        key = (b.kind, b.floats_per_item)
+        if b.is_output or b.is_input or not free[key]:
+            b.phys = len(plan.phys)
+            plan.phys.append(key)
+        else:
+            b.phys = free[key].pop()
+        active.append(b)
+
+    plan.stats = {
+        'graph_nodes': len(g.nodes),
+        'kernel_ops': len(plan.kops),
+        'buffers': len(plan.buffers),
+        'phys_slots': len(plan.phys),
+        'floats_per_item_frame': sum(f for (kd, f) in plan.phys if kd == 'frame'),
+        'floats_per_item_clip': sum(f for (kd, f) in plan.phys if kd == 'clip'),
+    }
+    return plan

@@ -1,0 +1,67 @@
+// Context, error reporting and version of the C ABI (include/deephar_b200.h).
+#include <stdarg.h>
+#include <string.h>
+#include "common.cuh"
+
+static thread_local char g_last_error[512] = "";
+
+void dh_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char* dh_last_error(void) { return g_last_error; }
+
+extern "C" int dh_version(void) { return 100; }
+
+extern "C" int dh_ctx_create(dh_ctx** out, int device) {
+    DH_CHECK_ARG(out != nullptr, "dh_ctx_create: out is NULL");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        dh_set_error("dh_ctx_create: no CUDA device (%s) -- this library has no CPU fallback",
+                     cudaGetErrorString(e));
+        return e == cudaSuccess ? (int)cudaErrorNoDevice : (int)e;
+    }
+    DH_CHECK_ARG(device >= 0 && device < count, "dh_ctx_create: device %d out of range", device);
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) {
+        dh_set_error("cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+        return (int)e;
+    }
+    if (prop.major != 10) {
+        dh_set_error("dh_ctx_create: device %d is sm_%d%d; this build targets sm_100a (B200) only",
+                     device, prop.major, prop.minor);
+        return -2;
+    }
+    dh_ctx* c = new dh_ctx();
+    c->device = device;
+    c->num_sms = prop.multiProcessorCount;
+    c->launches = 0;
+    c->workspace = nullptr;
+    c->workspace_bytes = 0;
+    *out = c;
+    return 0;
+}
+
+extern "C" int dh_ctx_destroy(dh_ctx* ctx) {
+    delete ctx;
+    return 0;
+}
+
+extern "C" int64_t dh_launch_count(dh_ctx* ctx, int reset) {
+    if (!ctx) return -1;
+    int64_t v = ctx->launches;
+    if (reset) ctx->launches = 0;
+    return v;
+}
+
+extern "C" int dh_set_workspace(dh_ctx* ctx, void* ptr, int64_t bytes) {
+    DH_CHECK_ARG(ctx != nullptr, "dh_set_workspace: ctx is NULL");
+    ctx->workspace = ptr;
+    ctx->workspace_bytes = bytes;
+    return 0;
+}

@@ -1,0 +1,70 @@
+// Shared helpers for the deephar_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/deephar_b200.h"
+
+struct dh_ctx {
+    int device;
+    int num_sms;
+    int64_t launches;
+    void* workspace;
+    int64_t workspace_bytes;
+};
+
+void dh_set_error(const char* fmt, ...);
+
+#define DH_CHECK_ARG(cond, ...)            \
+    do {                                   \
+        if (!(cond)) {                     \
+            dh_set_error(__VA_ARGS__);     \
+            return -1;                     \
+        }                                  \
+    } while (0)
+
+// After a launch: count it and surface launch-configuration errors.
+#define DH_LAUNCH_EPILOGUE(ctx, nlaunch)                     \
+    do {                                                     \
+        (ctx)->launches += (nlaunch);                        \
+        cudaError_t e__ = cudaGetLastError();                \
+        if (e__ != cudaSuccess) {                            \
+            dh_set_error("CUDA launch failed: %s (%s:%d)",   \
+                         cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return (int)e__;                                 \
+        }                                                    \
+        return 0;                                            \
+    } while (0)
+
+// TF 'SAME' padding: out = ceil(in/s), extra pad goes bottom/right.
+static inline void dh_same_pad(int in, int k, int s, int* out, int* before) {
+    int o = (in + s - 1) / s;
+    int total = (o - 1) * s + k - in;
+    if (total < 0) total = 0;
+    *out = o;
+    *before = total / 2;
+}
+
+static inline int dh_out_size(int in, int k, int s, int pad_same, int* before) {
+    int o;
+    if (pad_same) {
+        dh_same_pad(in, k, s, &o, before);
+    } else {
+        o = (in - k) / s + 1;
+        *before = 0;
+    }
+    return o;
+}
+
+static inline bool dh_aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}

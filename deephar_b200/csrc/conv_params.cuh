@@ -1,0 +1,28 @@
+#pragma once
+#include "common.cuh"
+
+struct ConvParams {
+    const float* x;
+    int N, H, W, Cin, ldx;
+    const float* w;      // dense conv: HWIO flattened [K][Cout]; separable: pointwise [Cin][Cout]
+    const float* w_dw;   // separable only: (kh,kw,Cin) depthwise taps
+    float* out;
+    int Ho, Wo, Cout, ldo;
+    int kh, kw, sh, sw, pt, pl;
+    const float *pre_scale, *pre_shift, *post_scale, *post_shift;
+    int pre_relu, post_relu;
+    const float* res0; int ldr0;
+    const float* res1; int ldr1;
+    int M;  // N*Ho*Wo
+    int K;  // kh*kw*Cin (dense) ; Cin (pointwise stage)
+};
+
+int dh_fill_conv_params(ConvParams* p, const dh_view* x, const dh_conv_desc* d, const dh_view* out,
+                        int cout, const char* who);
+void dh_launch_conv_simt(const ConvParams& p, cudaStream_t s);
+void dh_launch_depthwise_simt(const ConvParams& p, float* tmp, int num_sms, cudaStream_t s);
+
+// tensor-core path (conv_tc.cu). Returns true if it took the op.
+bool dh_tc_supported(const ConvParams& p, const dh_packed_w* packed, bool separable);
+int dh_launch_conv_tc(dh_ctx* ctx, const ConvParams& p, const dh_packed_w* packed, bool separable,
+                      int precision, cudaStream_t s);

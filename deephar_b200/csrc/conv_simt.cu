@@ -1,0 +1,234 @@
+// CUDA-core (fp32 FFMA) convolution kernels: the general implicit-GEMM Conv2D used
+// for shapes the tensor-core path does not take (Cin = 3 stem conv, the tiny action
+// head convs, ragged channel counts), and the stand-alone depthwise stage.
+//
+// replaces: keras Conv2D / SeparableConv2D lowered by TF-1.6 to cuDNN
+// (deephar/layers.py:66-80), with the BatchNormalization / ReLU / add layers
+// around them fused in (layers.py:202-325, models/common.py:25-67).
+#include "common.cuh"
+#include "conv_params.cuh"
+
+// ---------------------------------------------------------------------------
+// Implicit GEMM:  out[m, co] = sum_k A[m, k] * W[k, co],  m = (n, oy, ox),
+// k = (ky, kx, ci)  -- exactly the HWIO weight layout flattened to [K][Cout].
+// Tile 128 x 64 x 16, 256 threads, 8x4 accumulators per thread.
+// ---------------------------------------------------------------------------
+namespace {
+
+constexpr int BM = 128, BN = 64, BK = 16, NT = 256;
+constexpr int A_ROWS_PER_PASS = NT / BK;       // 16
+constexpr int A_PASSES = BM / A_ROWS_PER_PASS; // 8
+
+__global__ void __launch_bounds__(NT) conv_simt_kernel(ConvParams p) {
+    __shared__ __align__(16) float As[BK][BM + 4];
+    __shared__ __align__(16) float Bs[BK][BN];
+
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.x * BM;
+    const int n0 = blockIdx.y * BN;
+    const int HoWo = p.Ho * p.Wo;
+
+    // A-load assignment: fixed k-lane, 8 pixel rows.
+    const int a_kk = tid % BK;
+    const int a_r0 = tid / BK;
+    int a_base[A_PASSES], a_iy[A_PASSES], a_ix[A_PASSES];
+#pragma unroll
+    for (int i = 0; i < A_PASSES; ++i) {
+        int m = m0 + a_r0 + i * A_ROWS_PER_PASS;
+        if (m < p.M) {
+            int n = m / HoWo;
+            int r = m - n * HoWo;
+            int oy = r / p.Wo;
+            int ox = r - oy * p.Wo;
+            a_base[i] = n * p.H * p.W;
+            a_iy[i] = oy * p.sh - p.pt;
+            a_ix[i] = ox * p.sw - p.pl;
+        } else {
+            a_base[i] = 0;
+            a_iy[i] = -(1 << 28);
+            a_ix[i] = 0;
+        }
+    }
+    // B-load assignment: one float4 per thread.
+    const int b_row = tid / (BN / 4);
+    const int b_col = (tid % (BN / 4)) * 4;
+    const bool b_vec = (p.Cout % 4) == 0;
+
+    const int tx = tid % 16;  // cout group (4 wide)
+    const int ty = tid / 16;  // pixel group (8 tall)
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int k0 = 0; k0 < p.K; k0 += BK) {
+        // ---- A tile (gather + fused pre-ops) ----
+        {
+            int k = k0 + a_kk;
+            bool kval = k < p.K;
+            int tap = kval ? k / p.Cin : 0;
+            int ci = k - tap * p.Cin;
+            int ky = tap / p.kw;
+            int kx = tap - ky * p.kw;
+            float ps = 1.f, pb = 0.f;
+            if (kval && p.pre_scale) {
+                ps = __ldg(p.pre_scale + ci);
+                pb = __ldg(p.pre_shift + ci);
+            }
+#pragma unroll
+            for (int i = 0; i < A_PASSES; ++i) {
+                int iy = a_iy[i] + ky, ix = a_ix[i] + kx;
+                float v = 0.f;
+                if (kval && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
+                    v = __ldg(p.x + (size_t)(a_base[i] + iy * p.W + ix) * p.ldx + ci);
+                    v = fmaf(v, ps, pb);
+                    if (p.pre_relu) v = fmaxf(v, 0.f);
+                }
+                As[a_kk][a_r0 + i * A_ROWS_PER_PASS] = v;
+            }
+        }
+        // ---- B tile ----
+        {
+            int k = k0 + b_row;
+            int co = n0 + b_col;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k < p.K) {
+                const float* wp = p.w + (size_t)k * p.Cout + co;
+                if (b_vec && co + 3 < p.Cout) {
+                    v = __ldg(reinterpret_cast<const float4*>(wp));
+                } else {
+                    if (co + 0 < p.Cout) v.x = __ldg(wp + 0);
+                    if (co + 1 < p.Cout) v.y = __ldg(wp + 1);
+                    if (co + 2 < p.Cout) v.z = __ldg(wp + 2);
+                    if (co + 3 < p.Cout) v.w = __ldg(wp + 3);
+                }
+            }
+            *reinterpret_cast<float4*>(&Bs[b_row][b_col]) = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 8]);
+            float4 a1 = *reinterpret_cast<const float4*>(&As[kk][ty * 8 + 4]);
+            float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+            float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+
+    // ---- epilogue: BN affine, ReLU, residual adds, store ----
+    const int co0 = n0 + tx * 4;
+    float sc[4], sf[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        int co = co0 + j;
+        sc[j] = (p.post_scale && co < p.Cout) ? __ldg(p.post_scale + co) : 1.f;
+        sf[j] = (p.post_shift && co < p.Cout) ? __ldg(p.post_shift + co) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        int m = m0 + ty * 8 + i;
+        if (m >= p.M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int co = co0 + j;
+            if (co >= p.Cout) continue;
+            float v = fmaf(acc[i][j], sc[j], sf[j]);
+            if (p.post_relu) v = fmaxf(v, 0.f);
+            if (p.res0) v += __ldg(p.res0 + (size_t)m * p.ldr0 + co);
+            if (p.res1) v += __ldg(p.res1 + (size_t)m * p.ldr1 + co);
+            p.out[(size_t)m * p.ldo + co] = v;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Stand-alone depthwise stage (only used when the fused tensor-core separable
+// kernel does not apply).  One thread per (output pixel, channel).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) depthwise_simt_kernel(ConvParams p, float* __restrict__ tmp) {
+    const int64_t total = (int64_t)p.M * p.Cin;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        int c = (int)(idx % p.Cin);
+        int m = (int)(idx / p.Cin);
+        int n = m / (p.Ho * p.Wo);
+        int r = m - n * p.Ho * p.Wo;
+        int oy = r / p.Wo, ox = r - oy * p.Wo;
+        float ps = 1.f, pb = 0.f;
+        if (p.pre_scale) {
+            ps = __ldg(p.pre_scale + c);
+            pb = __ldg(p.pre_shift + c);
+        }
+        float acc = 0.f;
+        for (int ky = 0; ky < p.kh; ++ky) {
+            int iy = oy * p.sh - p.pt + ky;
+            if (iy < 0 || iy >= p.H) continue;
+            for (int kx = 0; kx < p.kw; ++kx) {
+                int ix = ox * p.sw - p.pl + kx;
+                if (ix < 0 || ix >= p.W) continue;
+                float v = __ldg(p.x + ((size_t)(n * p.H + iy) * p.W + ix) * p.ldx + c);
+                v = fmaf(v, ps, pb);
+                if (p.pre_relu) v = fmaxf(v, 0.f);
+                acc = fmaf(v, __ldg(p.w_dw + (ky * p.kw + kx) * p.Cin + c), acc);
+            }
+        }
+        tmp[idx] = acc;
+    }
+}
+
+}  // namespace
+
+int dh_fill_conv_params(ConvParams* p, const dh_view* x, const dh_conv_desc* d, const dh_view* out,
+                        int cout, const char* who) {
+    DH_CHECK_ARG(x && d && out && x->p && out->p, "%s: NULL argument", who);
+    DH_CHECK_ARG(d->kh >= 1 && d->kw >= 1 && d->sh >= 1 && d->sw >= 1, "%s: bad kernel/stride", who);
+    DH_CHECK_ARG(d->n_res >= 0 && d->n_res <= 2, "%s: n_res must be 0..2", who);
+    DH_CHECK_ARG((d->pre_scale == nullptr) == (d->pre_shift == nullptr), "%s: pre_scale/pre_shift must come together", who);
+    int pt, pl;
+    int ho = dh_out_size(x->h, d->kh, d->sh, d->pad_same, &pt);
+    int wo = dh_out_size(x->w, d->kw, d->sw, d->pad_same, &pl);
+    DH_CHECK_ARG(ho >= 1 && wo >= 1, "%s: empty output (%dx%d input, %dx%d kernel)", who, x->h, x->w, d->kh, d->kw);
+    DH_CHECK_ARG(out->n == x->n && out->h == ho && out->w == wo && out->c == cout,
+                 "%s: output view is (%d,%d,%d,%d), expected (%d,%d,%d,%d)", who, out->n, out->h, out->w,
+                 out->c, x->n, ho, wo, cout);
+    DH_CHECK_ARG(x->ld >= x->c && out->ld >= out->c, "%s: ld smaller than c", who);
+    for (int i = 0; i < d->n_res; ++i) {
+        DH_CHECK_ARG(d->res[i].p && d->res[i].n == out->n && d->res[i].h == ho && d->res[i].w == wo &&
+                         d->res[i].c == cout,
+                     "%s: residual %d shape mismatch", who, i);
+    }
+    p->x = x->p; p->N = x->n; p->H = x->h; p->W = x->w; p->Cin = x->c; p->ldx = x->ld;
+    p->w = nullptr; p->w_dw = nullptr;
+    p->out = out->p; p->Ho = ho; p->Wo = wo; p->Cout = cout; p->ldo = out->ld;
+    p->kh = d->kh; p->kw = d->kw; p->sh = d->sh; p->sw = d->sw; p->pt = pt; p->pl = pl;
+    p->pre_scale = d->pre_scale; p->pre_shift = d->pre_shift;
+    p->post_scale = d->post_scale; p->post_shift = d->post_shift;
+    p->pre_relu = d->pre_relu; p->post_relu = d->post_relu;
+    p->res0 = d->n_res > 0 ? d->res[0].p : nullptr; p->ldr0 = d->n_res > 0 ? d->res[0].ld : 0;
+    p->res1 = d->n_res > 1 ? d->res[1].p : nullptr; p->ldr1 = d->n_res > 1 ? d->res[1].ld : 0;
+    int64_t m = (int64_t)x->n * ho * wo;
+    DH_CHECK_ARG(m < (1ll << 31) && (int64_t)x->n * x->h * x->w < (1ll << 31), "%s: too many pixels for int32 indexing", who);
+    p->M = (int)m;
+    p->K = d->kh * d->kw * x->c;
+    return 0;
+}
+
+void dh_launch_conv_simt(const ConvParams& p, cudaStream_t s) {
+    dim3 grid((p.M + BM - 1) / BM, (p.Cout + BN - 1) / BN);
+    conv_simt_kernel<<<grid, NT, 0, s>>>(p);
+}
+
+void dh_launch_depthwise_simt(const ConvParams& p, float* tmp, int num_sms, cudaStream_t s) {
+    int64_t total = (int64_t)p.M * p.Cin;
+    int64_t blocks = (total + 255) / 256;
+    int64_t cap = (int64_t)num_sms * 16;
+    if (blocks > cap) blocks = cap;
+    depthwise_simt_kernel<<<(int)blocks, 256, 0, s>>>(p, tmp);
+}

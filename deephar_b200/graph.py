@@ -1,0 +1,134 @@
+"""Symbolic layer graph recorded by the model builders (deephar_b200/reception.py,
+spnet.py).  It plays the role of the Keras functional graph in the reference: the
+builders call Keras-like layer helpers (deephar_b200/layers.py) on `Tensor`s; nothing is
+computed here.  compiler.py turns the graph into fused sm_100a kernel launches.
+
+Tensor shapes are per-item NHWC without the batch axis: (H, W, C).  `kind` says which
+batch axis the tensor lives on: 'frame' (N = B*T frames; TimeDistributed in the reference
+folds T into the batch, layers.py:66-104) or 'clip' (B clips; the action head treats
+(T, joints) as an image, spnet.py:109-146).
+"""
+
+
+class Tensor(object):
+    __slots__ = ('g', 'id', 'shape', 'kind', 'node', 'out_index')
+
+    def __init__(self, g, shape, kind, node, out_index=0):
+        self.g = g
+        self.id = len(g.tensors)
+        self.shape = tuple(int(s) for s in shape)
+        self.kind = kind
+        self.node = node
+        self.out_index = out_index
+        g.tensors.append(self)
+
+    @property
+    def channels(self):
+        return self.shape[-1]
+
+    def __repr__(self):
+        return 'T%d%s<%s>' % (self.id, self.shape, self.node.op if self.node else 'input')
+
+
+class Node(object):
+    __slots__ = ('id', 'op', 'inputs', 'outs', 'attrs')
+
+    def __init__(self, g, op, inputs, attrs):
+        self.id = len(g.nodes)
+        self.op = op
+        self.inputs = list(inputs)
+        self.outs = []
+        self.attrs = attrs
+        g.nodes.append(self)
+
+    @property
+    def out(self):
+        return self.outs[0]
+
+    def __repr__(self):
+        return 'N%d:%s' % (self.id, self.op)
+
+
+class Graph(object):
+    def __init__(self, name='model'):
+        self.name = name
+        self.nodes = []
+        self.tensors = []
+        self.inputs = []
+        self.outputs = []
+        self.output_names = []
+        self.weight_specs = []      # ordered [(name, shape)] in layer-creation order
+        self._weight_names = set()
+        self._counters = {}
+        self._scope = []
+        self.frames_per_clip = 1    # T (TimeDistributed fold); 1 for single-frame models
+
+    # --- naming (Keras auto names: one global counter per class prefix) --------
+    def auto_name(self, prefix):
+        n = self._counters.get(prefix, 0) + 1
+        self._counters[prefix] = n
+        return '%s_%d' % (prefix, n)
+
+    def scope(self, name):
+        g = self
+
+        class _Scope(object):
+            def __enter__(self_):
+                g._scope.append(name)
+
+            def __exit__(self_, *a):
+                g._scope.pop()
+
+        return _Scope()
+
+    def qualify(self, layer):
+        return '/'.join(self._scope + [layer])
+
+    def add_weight(self, layer_qualified, leaf, shape):
+        name = layer_qualified + '/' + leaf
+        if name in self._weight_names:
+            raise ValueError('duplicate weight name %s' % name)
+        self._weight_names.add(name)
+        self.weight_specs.append((name, tuple(int(s) for s in shape)))
+        return name
+
+    # --- graph construction --------------------------------------------------
+    def input(self, shape, kind='frame'):
+        node = Node(self, 'input', [], {})
+        t = Tensor(self, shape, kind, node)
+        node.outs.append(t)
+        self.inputs.append(t)
+        return t
+
+    def op(self, op, inputs, out_shapes, attrs=None, kind=None):
+        node = Node(self, op, inputs, attrs or {})
+        kind = kind or inputs[0].kind
+        if out_shapes and not isinstance(out_shapes[0], (tuple, list)):
+            out_shapes = [out_shapes]
+        for i, s in enumerate(out_shapes):
+            node.outs.append(Tensor(self, s, kind, node, i))
+        return node.outs[0] if len(node.outs) == 1 else tuple(node.outs)
+
+    def num_params(self):
+        n = 0
+        for _, s in self.weight_specs:
+            k = 1
+            for d in s:
+                k *= d
+            n += k
+        return n
+
+
+def same_pad(in_size, k, s):
+    """TF 'SAME': out = ceil(in/s); extra pad on bottom/right."""
+    out = -(-in_size // s)
+    total = max((out - 1) * s + k - in_size, 0)
+    return out, total // 2, total - total // 2
+
+
+def conv_out_hw(h, w, size, strides, padding):
+    if padding == 'same':
+        return same_pad(h, size[0], strides[0])[0], same_pad(w, size[1], strides[1])[0]
+    if padding == 'valid':
+        return (h - size[0]) // strides[0] + 1, (w - size[1]) // strides[1] + 1
+    raise ValueError('padding must be "same" or "valid", got %r' % (padding,))

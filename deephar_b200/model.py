@@ -1,0 +1,410 @@
+"""keras.Model-like object over a compiled deephar_b200 graph.
+
+Protocol kept for the reference's evaluators (exp/common/mpii_tools.py:63-90,
+h36m_tools.py:12-50, penn_tools.py:13-60): `.predict(x, batch_size, verbose)` returning a
+list of numpy arrays (a single array if the model has one output), `.outputs`,
+`.input_shape`, `.get_input_shape_at(0)`, `.name`, `.load_weights`, `.set_weights`.
+
+PyTorch is used only as the device-memory / stream container; every FLOP runs in
+libdeephar_b200.so.  There is no CPU path: constructing the engine without a CUDA device
+raises.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _ffi
+from .compiler import compile_graph
+from .weights import fold_batchnorm, load_calibration, synthetic_weights
+
+
+def _align(n, a=4):
+    return (n + a - 1) // a * a
+
+
+class _Bound(object):
+    """Plan bound to a batch size: device buffers + prebuilt ctypes argument lists."""
+
+    def __init__(self):
+        self.calls = []
+        self.keep = []
+        self.slots = []
+        self.n_items = 0
+
+
+class Model(object):
+    def __init__(self, graph, calib_key=None, name=None):
+        self.graph = graph
+        self.name = name or graph.name
+        self.plan = compile_graph(graph)
+        self.calib_key = calib_key
+        self.weight_specs = list(graph.weight_specs)
+        self._host_weights = None
+        self._dev = None            # device-side weight arena (torch tensor) + pointer table
+        self._ptr = {}
+        self._ctx = None
+        self._bound = {}
+        self.precision = 3          # tensor-core split precision (bf16 x3 ~ fp32); 1 = plain bf16
+        self.use_tensor_cores = True
+
+    # ---- keras.Model protocol ------------------------------------------------------
+    @property
+    def outputs(self):
+        return list(self.graph.outputs)
+
+    @property
+    def input_shape(self):
+        t = self.graph.inputs[0]
+        if self.graph.frames_per_clip > 1:
+            return (None, self.graph.frames_per_clip) + t.shape
+        return (None,) + t.shape
+
+    def get_input_shape_at(self, i):
+        assert i == 0
+        return self.input_shape
+
+    @property
+    def output_shape(self):
+        return [self._keras_shape(t, None) for t in self.graph.outputs]
+
+    def count_params(self):
+        return self.graph.num_params()
+
+    def conv_flops_per_frame(self):
+        """2 x MAC of every Conv2D / SeparableConv2D per input frame; clip-level
+        (action head) convs are divided by the frames per clip."""
+        total = 0.0
+        for k in self.plan.kops:
+            if k.kind not in ('conv', 'sepconv'):
+                continue
+            ho, wo, cout = k.outs[0].shape
+            cin = k.ins[0].shape[2]
+            kh, kw = k.attrs['size']
+            mac = ho * wo * (kh * kw * cin * cout if k.kind == 'conv' else kh * kw * cin + cin * cout)
+            if k.outs[0].kind == 'clip':
+                mac /= float(self.graph.frames_per_clip)
+            total += 2.0 * mac
+        return total
+
+    # ---- weights -----------------------------------------------------------------
+    def set_weights(self, table):
+        """table: {name: array} in the Keras layouts listed by `weight_specs`."""
+        host = {}
+        for name, shape in self.weight_specs:
+            if name not in table:
+                raise KeyError('missing weight %s %s' % (name, shape))
+            a = np.asarray(table[name], dtype=np.float32)
+            if tuple(a.shape) != tuple(shape):
+                raise ValueError('weight %s has shape %s, expected %s' % (name, a.shape, shape))
+            host[name] = a
+        self._host_weights = host
+        self._dev = None
+        self._bound = {}
+
+    def get_weights(self):
+        return dict(self._host_weights)
+
+    def init_synthetic_weights(self, seed=1234):
+        calib = load_calibration(self.calib_key) if self.calib_key else {}
+        self.set_weights(synthetic_weights(self.weight_specs, seed, calib))
+        return self
+
+    def load_weights(self, path, by_name=False):
+        """.npz written by save_weights (names = weight_specs).  Importing the released Keras
+        .h5 files is SURVEY.md 8(f) rank 1 (needs an HDF5 reader that is not in this image)."""
+        if str(path).endswith(('.h5', '.hdf5')):
+            raise NotImplementedError('Keras HDF5 import is not available (no h5py in the image); '
+                                      'convert to .npz with names from Model.weight_specs')
+        with np.load(path) as z:
+            self.set_weights({k: z[k] for k in z.files})
+
+    def save_weights(self, path):
+        np.savez(path, **self._host_weights)
+
+    # ---- engine --------------------------------------------------------------------
+    def _torch(self):
+        import torch
+        if not torch.cuda.is_available():
+            raise _ffi.DeepharB200Error('deephar_b200 needs a CUDA device (B200, sm_100a); '
+                                        'there is no CPU fallback')
+        return torch
+
+    def _ensure_device_weights(self):
+        if self._dev is not None:
+            return
+        torch = self._torch()
+        if self._host_weights is None:
+            raise RuntimeError('weights not set: call load_weights / set_weights / init_synthetic_weights')
+        if self._ctx is None:
+            self._ctx = _ffi.Context(torch.cuda.current_device())
+        hw = self._host_weights
+        chunks, offsets, off = [], {}, 0
+
+        def put(key, arr):
+            nonlocal off
+            arr = np.ascontiguousarray(arr, dtype=np.float32).ravel()
+            offsets[key] = off
+            chunks.append(arr)
+            pad = _align(arr.size) - arr.size
+            if pad:
+                chunks.append(np.zeros(pad, np.float32))
+            off += _align(arr.size)
+
+        for name, _ in self.weight_specs:
+            put(name, hw[name])
+        for k in self.plan.kops:
+            for key in ('pre_bn', 'post_bn', 'bn'):
+                bn = k.attrs.get(key) if isinstance(k.attrs, dict) else None
+                if bn and ('fold:' + bn['name']) not in offsets:
+                    w = bn['weights']
+                    scale, shift = fold_batchnorm(hw[w['gamma']] if 'gamma' in w else None,
+                                                  hw[w['beta']], hw[w['mean']], hw[w['var']])
+                    put('fold:' + bn['name'], scale)
+                    put('shift:' + bn['name'], shift)
+        flat = np.concatenate(chunks) if chunks else np.zeros(4, np.float32)
+        self._dev = torch.from_numpy(flat).cuda()
+        base = self._dev.data_ptr()
+        self._ptr = {k: base + 4 * o for k, o in offsets.items()}
+
+    def _keras_shape(self, t, n):
+        h, w, c = t.shape
+        lead = (n,)
+        if t.kind == 'frame' and self.graph.frames_per_clip > 1 and n is not None:
+            lead = (n // self.graph.frames_per_clip, self.graph.frames_per_clip)
+        elif t.kind == 'frame' and self.graph.frames_per_clip > 1:
+            lead = (None, self.graph.frames_per_clip)
+        if h == 1:
+            return lead + ((w, c) if w > 1 or c > 1 else (c,))
+        return lead + (h, w, c)
+
+    def _items(self, kind, n_frames):
+        return n_frames if kind == 'frame' else n_frames // self.graph.frames_per_clip
+
+    def _bind(self, n_frames):
+        if n_frames in self._bound:
+            return self._bound[n_frames]
+        torch = self._torch()
+        self._ensure_device_weights()
+        lib = _ffi.lib()
+        plan = self.plan
+        b = _Bound()
+        b.n_items = n_frames
+        for (kind, fl) in plan.phys:
+            b.slots.append(torch.empty(self._items(kind, n_frames) * fl, dtype=torch.float32, device='cuda'))
+        ws_floats = 0
+        for k in plan.kops:
+            if k.kind == 'sepconv':
+                t = k.outs[0]
+                ws_floats = max(ws_floats, self._items(t.kind, n_frames) * t.shape[0] * t.shape[1] * k.ins[0].channels)
+        b.workspace = torch.empty(max(ws_floats, 4), dtype=torch.float32, device='cuda')
+        ctxh = self._ctx.handle
+        P = self._ptr
+
+        def view(t):
+            s = plan.storage[t.id]
+            ptr = b.slots[s.buf.phys].data_ptr() + 4 * s.c_off
+            v = _ffi.dh_view(ptr, self._items(t.kind, n_frames), t.shape[0], t.shape[1], t.shape[2], s.ld)
+            b.keep.append(v)
+            return v
+
+        def dense_ptr(t):
+            s = plan.storage[t.id]
+            assert s.c_off == 0 and s.ld == t.shape[2], 'dense output expected'
+            return b.slots[s.buf.phys].data_ptr()
+
+        def conv_desc(k):
+            a = k.attrs
+            d = _ffi.dh_conv_desc()
+            d.kh, d.kw = a['size']
+            d.sh, d.sw = a['strides']
+            d.pad_same = 1 if a['padding'] == 'same' else 0
+            d.pre_relu = 1 if a['pre_relu'] else 0
+            d.post_relu = 1 if a['post_relu'] else 0
+            if a['pre_bn']:
+                d.pre_scale = P['fold:' + a['pre_bn']['name']]
+                d.pre_shift = P['shift:' + a['pre_bn']['name']]
+            if a['post_bn']:
+                d.post_scale = P['fold:' + a['post_bn']['name']]
+                d.post_shift = P['shift:' + a['post_bn']['name']]
+            d.n_res = a['n_res']
+            for i in range(a['n_res']):
+                d.res[i] = view(k.ins[1 + i])
+            d.precision = self.precision
+            b.keep.append(d)
+            return d
+
+        nullv = C.cast(None, C.POINTER(_ffi.dh_view))
+        nullp = C.cast(None, C.POINTER(_ffi.dh_packed_w))
+        for k in plan.kops:
+            kd = k.kind
+            if kd == 'conv':
+                args = (lib.dh_conv2d_f32, ctxh, C.byref(view(k.ins[0])), P[k.attrs['kernel']],
+                        self._packed(k, b) or nullp, C.byref(conv_desc(k)), C.byref(view(k.outs[0])))
+            elif kd == 'sepconv':
+                args = (lib.dh_sepconv2d_f32, ctxh, C.byref(view(k.ins[0])), P[k.attrs['depthwise']],
+                        P[k.attrs['pointwise']], self._packed(k, b) or nullp, C.byref(conv_desc(k)),
+                        C.byref(view(k.outs[0])))
+            elif kd == 'maxpool':
+                a = k.attrs
+                args = (lib.dh_maxpool2d_f32, ctxh, C.byref(view(k.ins[0])), a['pool'][0], a['pool'][1],
+                        a['strides'][0], a['strides'][1], 1 if a['padding'] == 'same' else 0,
+                        C.byref(view(k.outs[0])))
+            elif kd == 'upsample_add':
+                args = (lib.dh_upsample2x_add_f32, ctxh, C.byref(view(k.ins[0])), C.byref(view(k.ins[1])),
+                        C.byref(view(k.outs[0])))
+            elif kd == 'upsample':
+                args = (lib.dh_upsample2x_add_f32, ctxh, nullv, C.byref(view(k.ins[0])),
+                        C.byref(view(k.outs[0])))
+            elif kd in ('add', 'affine', 'copy'):
+                arr = (_ffi.dh_view * len(k.ins))(*[view(t) for t in k.ins])
+                b.keep.append(arr)
+                scale = shift = None
+                relu = 0
+                if kd == 'affine':
+                    if k.attrs['bn']:
+                        scale = P['fold:' + k.attrs['bn']['name']]
+                        shift = P['shift:' + k.attrs['bn']['name']]
+                    relu = 1 if k.attrs['relu'] else 0
+                ov = view(k.outs[0])
+                if kd == 'copy':
+                    ov.p = ov.p + 4 * k.attrs['c_off']
+                    ov.c = k.attrs['channels']
+                args = (lib.dh_add_n_f32, ctxh, arr, len(k.ins), scale, shift, relu, C.byref(ov))
+            elif kd == 'pose_regression_2d_context':
+                a = k.attrs
+                args = (lib.dh_softargmax2d_ctx_f32, ctxh, C.byref(view(k.ins[0])), a['num_joints'],
+                        a['num_context'], C.c_float(a['alpha']), dense_ptr(k.outs[0]), dense_ptr(k.outs[1]))
+            elif kd == 'pose_regression_2d':
+                args = (lib.dh_softargmax2d_f32, ctxh, C.byref(view(k.ins[0])), nullv, C.c_float(1.0), 0,
+                        dense_ptr(k.outs[0]), dense_ptr(k.outs[1]), nullv)
+            elif kd == 'pose_regression_3d':
+                a = k.attrs
+                args = (lib.dh_softargmax3d_f32, ctxh, C.byref(view(k.ins[0])), a['num_joints'],
+                        a['depth_maps'], dense_ptr(k.outs[0]), dense_ptr(k.outs[1]))
+            else:
+                raise NotImplementedError('kernel op %s' % kd)
+            b.calls.append((kd,) + args)
+        self._bound[n_frames] = b
+        return b
+
+    def _packed(self, k, b):
+        return None     # tensor-core weight packing is attached by tc.py when enabled
+
+    def _run(self, b, stream_ptr):
+        self._ctx.set_workspace(b.workspace.data_ptr(), b.workspace.numel() * 4)
+        for call in b.calls:
+            rc = call[1](*call[2:], stream_ptr)
+            if rc != 0:
+                _ffi.check(rc, call[0])
+
+    def _output_tensor(self, b, t, n_frames):
+        s = self.plan.storage[t.id]
+        items = self._items(t.kind, n_frames)
+        base = b.slots[s.buf.phys].view(items, s.buf.hw, s.ld)
+        return base[:, :, s.c_off:s.c_off + t.shape[2]]
+
+    def forward_device(self, x_dev):
+        """x_dev: float32 CUDA tensor (N,H,W,3) (or (B,T,H,W,3)); returns device tensors (views into
+        the plan's buffers, valid until the next call)."""
+        torch = self._torch()
+        n_frames = int(np.prod(x_dev.shape[:-3]))
+        b = self._bind(n_frames)
+        t_in = self.graph.inputs[0]
+        s = self.plan.storage[t_in.id]
+        b.slots[s.buf.phys].copy_(x_dev.reshape(-1), non_blocking=True)
+        self._run(b, torch.cuda.current_stream().cuda_stream)
+        outs = []
+        for t in self.graph.outputs:
+            o = self._output_tensor(b, t, n_frames)
+            outs.append(o.reshape(self._keras_shape(t, self._items(t.kind, n_frames) if t.kind == 'clip' else n_frames)))
+        return outs
+
+    def predict(self, x, batch_size=32, verbose=0):
+        """keras.Model.predict: host numpy in, list of host numpy out.  `batch_size` counts items
+        of the leading axis (frames, or clips for clip models), as in Keras."""
+        torch = self._torch()
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        T = self.graph.frames_per_clip
+        lead = 2 if T > 1 else 1
+        exp = tuple(self.graph.inputs[0].shape)
+        if tuple(x.shape[lead:]) != exp or (T > 1 and x.shape[1] != T):
+            raise ValueError('input shape %s does not match model input %s' % (x.shape, self.input_shape))
+        n = x.shape[0]
+        xt = torch.from_numpy(x)
+        pinned = xt.is_pinned()
+        item = int(np.prod(x.shape[1:]))
+        if not pinned:
+            if getattr(self, '_stage', None) is None or self._stage.numel() < batch_size * item:
+                self._stage = torch.empty(batch_size * item, dtype=torch.float32).pin_memory()
+        # per-output pinned result buffers for the whole call (one D2H copy per output per batch)
+        res = []
+        for t in self.graph.outputs:
+            shp = self._keras_shape(t, n if t.kind == 'clip' or T == 1 else n * T)
+            res.append(torch.empty(shp, dtype=torch.float32).pin_memory())
+        for i in range(0, n, batch_size):
+            j = min(i + batch_size, n)
+            if pinned:
+                xb = xt[i:j].cuda(non_blocking=True)
+            else:
+                st = self._stage[:(j - i) * item].view((j - i,) + tuple(x.shape[1:]))
+                torch.cuda.current_stream().synchronize()     # staging buffer reuse
+                st.copy_(xt[i:j])
+                xb = st.cuda(non_blocking=True)
+            outs = self.forward_device(xb)
+            for r, o in zip(res, outs):
+                r[i:j].copy_(o, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        outs = [r.numpy() for r in res]
+        return outs[0] if len(outs) == 1 else outs
+
+    def math_mode(self):
+        """Arithmetic the convolutions run in (bench.py `dtype`)."""
+        if self.use_tensor_cores and self._uses_tc():
+            return 'bf16x%d split (fp32 accumulate, tcgen05)' % self.precision if self.precision != 1 else 'bf16'
+        return 'f32'
+
+    def _uses_tc(self):
+        return False
+
+    def profile(self, x_dev):
+        """One forward with CUDA events around every kernel op (launch stream = torch's current
+        stream).  Returns {label: {'label','ms','launches','flops'}} aggregated per op shape."""
+        torch = self._torch()
+        n_frames = int(np.prod(x_dev.shape[:-3]))
+        b = self._bind(n_frames)
+        s = self.plan.storage[self.graph.inputs[0].id]
+        b.slots[s.buf.phys].copy_(x_dev.reshape(-1))
+        stream = torch.cuda.current_stream().cuda_stream
+        self._ctx.set_workspace(b.workspace.data_ptr(), b.workspace.numel() * 4)
+        evs = []
+        for call in b.calls:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = call[1](*call[2:], stream)
+            e1.record()
+            if rc != 0:
+                _ffi.check(rc, call[0])
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        out = {}
+        for k, (e0, e1) in zip(self.plan.kops, evs):
+            label = '%s %s->%s' % (k.kind, 'x'.join(map(str, k.ins[0].shape)), 'x'.join(map(str, k.outs[0].shape)))
+            flops = 0.0
+            if k.kind in ('conv', 'sepconv'):
+                ho, wo, cout = k.outs[0].shape
+                cin = k.ins[0].shape[2]
+                kh, kw = k.attrs['size']
+                label += ' k%dx%d' % (kh, kw)
+                mac = ho * wo * (kh * kw * cin * cout if k.kind == 'conv' else kh * kw * cin + cin * cout)
+                flops = 2.0 * mac * self._items(k.outs[0].kind, n_frames)
+            r = out.setdefault(label, {'label': label, 'ms': 0.0, 'launches': 0, 'flops': flops})
+            r['ms'] += e0.elapsed_time(e1)
+            r['launches'] += 1
+        return out
+
+    def launches_per_forward(self, n_frames):
+        b = self._bind(n_frames)
+        n = 0
+        for call in b.calls:
+            n += 2 if (call[0] == 'sepconv' and not self.use_tensor_cores) else 1
+        return n

@@ -1,0 +1,148 @@
+/* deephar_b200 -- C ABI of the B200-native deephar forward hot path.
+ *
+ * The reference (dluvizon/deephar) has no FFI / plugin interface: its seam is
+ * Python (keras layers + keras.Model.predict).  This header is the boundary a
+ * ctypes binding uses (deephar_b200/_ffi.py; INTEGRATION.md shows the stub a
+ * maintainer of the reference would add).  Every entry point names the
+ * reference code it replaces (paths relative to the reference tree).
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no C++ / torch types.
+ *   - all tensors are fp32 NHWC device memory owned by the CALLER; a `dh_view`
+ *     is a (possibly channel-sliced) window: element (n,y,x,c) lives at
+ *     p[((n*h + y)*w + x)*ld + c], so `ld` is the channel count of the
+ *     underlying buffer (ld == c for a dense tensor) and a channel offset is
+ *     folded into `p`.  This is how `concatenate` / Lambda-slices cost nothing.
+ *   - every launch goes on the `stream` argument (a cudaStream_t passed as
+ *     void*); no hidden synchronisation, no global mutable state besides the
+ *     per-thread last-error string.
+ *   - return value: 0 = ok; <0 = argument error (text via dh_last_error());
+ *     >0 = cudaError_t.
+ */
+#ifndef DEEPHAR_B200_H
+#define DEEPHAR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dh_view {
+    float*  p;
+    int32_t n, h, w, c;
+    int32_t ld;
+} dh_view;
+
+/* Fused pre-/post-ops of a convolution.  Order of evaluation:
+ *   a   = x                                   (input tap, 0 outside the image)
+ *   a   = a * pre_scale[ci] + pre_shift[ci]   if pre_scale      (BatchNormalization before the conv)
+ *   a   = max(a, 0)                           if pre_relu       (Activation('relu') before the conv)
+ *   (zero padding is applied AFTER these, as keras pads the activated tensor)
+ *   y   = conv(a)
+ *   y   = y * post_scale[co] + post_shift[co] if post_scale     (BatchNormalization after the conv)
+ *   y   = max(y, 0)                           if post_relu
+ *   y  += res[0] (+ res[1])                   keras `add([...])`
+ * replaces: layers.py:202-325 (conv_bn, conv_bn_act, act_conv_bn, act_conv,
+ * separable_act_conv_bn, ...), models/common.py:25-67 residual_unit,
+ * models/reception.py:43-59 _sepconv_residual. */
+typedef struct dh_conv_desc {
+    int32_t kh, kw, sh, sw;
+    int32_t pad_same;            /* 1 = TF 'SAME' (extra pad bottom/right), 0 = 'VALID' */
+    int32_t pre_relu;
+    int32_t post_relu;
+    int32_t n_res;               /* 0..2 */
+    const float* pre_scale;      /* [Cin] or NULL */
+    const float* pre_shift;      /* [Cin] or NULL */
+    const float* post_scale;     /* [Cout] or NULL */
+    const float* post_shift;     /* [Cout] or NULL */
+    dh_view res[2];
+    int32_t precision;           /* tensor-core path: 1 = bf16 x1, 3 = bf16 x3 split (~fp32); 0 = library default */
+    int32_t reserved;
+} dh_conv_desc;
+
+/* Packed weights for the tensor-core path (built once at load time). */
+typedef struct dh_packed_w {
+    const void* hi;              /* bf16 [Cout_pad][K]  K-major, K = kh*kw*Cin */
+    const void* lo;              /* bf16 residual (w - hi), same layout */
+    int32_t cout_pad, k;
+} dh_packed_w;
+
+typedef struct dh_ctx dh_ctx;
+
+/* --- context ------------------------------------------------------------- */
+int         dh_ctx_create(dh_ctx** out, int device);
+int         dh_ctx_destroy(dh_ctx* ctx);
+const char* dh_last_error(void);
+int         dh_version(void);
+/* number of kernel launches issued through this context since creation / reset */
+int64_t     dh_launch_count(dh_ctx* ctx, int reset);
+/* scratch for two-kernel ops (owned by the caller): set before use */
+int         dh_set_workspace(dh_ctx* ctx, void* ptr, int64_t bytes);
+
+/* --- convolutions -------------------------------------------------------- */
+/* keras Conv2D(use_bias=False) (layers.py:66-71) with fused pre/post ops.
+ * w: HWIO (kh,kw,Cin,Cout) fp32 -- the keras kernel layout, unchanged.
+ * packed may be NULL (CUDA-core path only). */
+int dh_conv2d_f32(dh_ctx* ctx, const dh_view* x, const float* w_hwio, const dh_packed_w* packed,
+                  const dh_conv_desc* d, const dh_view* out, void* stream);
+
+/* keras SeparableConv2D(use_bias=False) (layers.py:74-80): depthwise kxk
+ * (w_dw: (kh,kw,Cin,1)) then 1x1 pointwise (w_pw: (1,1,Cin,Cout)), nothing in between. */
+int dh_sepconv2d_f32(dh_ctx* ctx, const dh_view* x, const float* w_dw, const float* w_pw,
+                     const dh_packed_w* packed_pw, const dh_conv_desc* d, const dh_view* out,
+                     void* stream);
+
+/* --- pooling / resampling / elementwise ---------------------------------- */
+/* keras MaxPooling2D (reception.py:74,86,108,115; layers.py:92-97); 'same' pads with -inf. */
+int dh_maxpool2d_f32(dh_ctx* ctx, const dh_view* x, int kh, int kw, int sh, int sw, int pad_same,
+                     const dh_view* out, void* stream);
+/* out = a + UpSampling2D((2,2))(b)  (reception.py:122-127); a may be NULL-p (plain upsample). */
+int dh_upsample2x_add_f32(dh_ctx* ctx, const dh_view* a, const dh_view* b, const dh_view* out,
+                          void* stream);
+/* out = sum of n_in (1..4) views, optional per-channel affine + relu on the sum
+ * (keras add([...]) followed by BatchNormalization / Activation). */
+int dh_add_n_f32(dh_ctx* ctx, const dh_view* in, int n_in, const float* scale, const float* shift,
+                 int relu, const dh_view* out, void* stream);
+
+/* --- soft-argmax heads ---------------------------------------------------- */
+/* One pass over h (N,H,W,C): per (frame, channel)
+ *   p = channel_softmax_2d(alpha)(h)                    activations.py:3-16
+ *   xy = softargmax2d(p)  grid linspace(0,1) inclusive  layers.py:122-129,160-200; utils/math.py:6-19
+ *   conf = max over 2x2 windows (stride 1, valid) of the window SUM of
+ *          p   if conf_on_prob = 1   (keypoint_confidence, layers.py:107-119)
+ *          h   if conf_on_prob = 0   (build_joints_probability on raw maps, blocks.py:328-343)
+ *   z = sum_hw sigmoid(d) * p  if d != NULL             spnet.py:201-205
+ * out_pose: (N, C, 2 or 3) dense; out_conf: (N, C, 1) dense; prob_out (optional,
+ * may be NULL-p) receives p for the kronecker product.                        */
+int dh_softargmax2d_f32(dh_ctx* ctx, const dh_view* h, const dh_view* d, float alpha,
+                        int conf_on_prob, float* out_pose, float* out_conf,
+                        const dh_view* prob_out, void* stream);
+
+/* reception.py:167-182 pose_regression_2d_context: h = [hs (nj) | hc (nj*n_ctx)];
+ * pose = a*sSAM(hs) + (1-a)*sum_ctx(pc*cSAM(hc))/sum_ctx(pc) (blocks.py:217-285),
+ * visible = sjProb(hs) (raw maps).  out_pose (N,nj,2), out_vis (N,nj,1). */
+int dh_softargmax2d_ctx_f32(dh_ctx* ctx, const dh_view* h, int nj, int n_ctx, float alpha_mix,
+                            float* out_pose, float* out_vis, void* stream);
+
+/* reception.py:193-222 pose_regression_3d: h (N,H,W,D*nj), channel = d*nj + j.
+ * out_pose (N,nj,3), out_vis (N,nj,1) = sigmoid(max hxy + max hz). */
+int dh_softargmax3d_f32(dh_ctx* ctx, const dh_view* h, int nj, int depth_maps,
+                        float* out_pose, float* out_vis, void* stream);
+
+/* layers.py:478-508 kronecker_prod for clips: out[n,j,f] = sum_hw P[n,h,w,j] * Z[n,h,w,f]. */
+int dh_kron_pool_f32(dh_ctx* ctx, const dh_view* p, const dh_view* z, float* out, void* stream);
+
+/* --- small action-head ops (spnet.py:51-148) ------------------------------ */
+/* layers.py:411-425 max_min_pooling 2x2 stride 2 'same' */
+int dh_maxmin_pool2d_f32(dh_ctx* ctx, const dh_view* x, const dh_view* out, void* stream);
+/* layers.py:428-442 + Activation('softmax'): out (B, C) */
+int dh_global_maxmin_softmax_f32(dh_ctx* ctx, const dh_view* x, float* out, void* stream);
+/* out[b,t,j,:] = p[b,t,j,:] * c[b,t,j,0]   (spnet.py:110-111) */
+int dh_mask_mul_f32(dh_ctx* ctx, const float* p, const float* c, int64_t rows, int dim, float* out,
+                    void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEEPHAR_B200_H */

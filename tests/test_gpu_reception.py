@@ -1,0 +1,75 @@
+"""End-to-end parity of the ReceptionNet forward (reception.build) against the fp64 oracle on
+identical seeded weights + inputs.  north_star tolerance: joint coordinates <= 1e-3 relative,
+confidences <= 1e-3 relative."""
+import numpy as np
+import pytest
+
+from deephar_b200 import reception
+from deephar_b200.weights import load_calibration
+from oracle import ops_np
+from oracle import reception as oracle_reception
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+def _check(outs, refs, tol=TOL):
+    assert len(outs) == len(refs)
+    for o, r in zip(outs, refs):
+        assert o.shape == r.shape
+        scale = np.maximum(np.abs(r), 1.0) if r.shape[-1] == 1 else 1.0   # coordinates live in [0,1]
+        err = np.abs(o.astype(np.float64) - r) / scale
+        assert err.max() <= tol, 'max err %g' % err.max()
+
+
+@pytest.mark.parametrize('res,blocks,n', [(64, 2, 3), (128, 3, 2)])
+def test_reception_2d_context(cuda, res, blocks, n):
+    kw = dict(num_joints=16, dim=2, num_context_per_joint=2, num_blocks=blocks, ksize=(5, 5),
+              concat_pose_confidence=False)
+    m = reception.build((res, res, 3), **kw).init_synthetic_weights(1234)
+    x = synth.synth_frames(n, res, res, seed=21)
+    refs = oracle_reception.forward(ops_np, m.get_weights(), x, **kw)
+    outs = m.predict(x, batch_size=2)
+    _check(outs, refs)
+    # batch-size independence (keras predict semantics)
+    outs1 = m.predict(x, batch_size=1)
+    for a, b in zip(outs, outs1):
+        assert np.abs(a - b).max() < 1e-5
+
+
+def test_reception_2d_concat_and_heatmaps(cuda):
+    kw = dict(num_joints=16, dim=2, num_blocks=2, ksize=(3, 3), export_heatmaps=True)
+    m = reception.build((64, 64, 3), **kw).init_synthetic_weights(7)
+    x = synth.synth_frames(2, 64, 64, seed=22)
+    refs = oracle_reception.forward(ops_np, m.get_weights(), x, **kw)
+    outs = m.predict(x)
+    assert [o.shape for o in outs] == [(2, 16, 3), (2, 8, 8, 16)] * 2
+    for o, r in zip(outs, refs):
+        if o.ndim == 4:
+            assert np.abs(o - r).max() <= 1e-3 * max(1.0, np.abs(r).max())
+            assert np.array_equal(o.reshape(2, -1, 16).argmax(1), r.reshape(2, -1, 16).argmax(1))
+        else:
+            _check([o], [r])
+
+
+def test_reception_3d(cuda):
+    kw = dict(num_joints=17, dim=3, num_blocks=2, ksize=(5, 5), concat_pose_confidence=False)
+    m = reception.build((64, 64, 3), **kw).init_synthetic_weights(1234)
+    x = synth.synth_frames(2, 64, 64, seed=23)
+    refs = oracle_reception.forward(ops_np, m.get_weights(), x, **kw)
+    outs = m.predict(x)
+    _check(outs, refs)
+
+
+def test_full_size_single_frame(cuda):
+    """C1 (BASELINE.json configs[0]): 256x256, 8 blocks, batch 1 -- vs the torch-CPU oracle
+    (fp32; the fp64 numpy oracle takes > 1 min at this size)."""
+    from oracle import ops_torch
+    kw = dict(num_joints=16, dim=2, num_context_per_joint=2, num_blocks=8, ksize=(5, 5),
+              concat_pose_confidence=False)
+    m = reception.build((256, 256, 3), **kw).init_synthetic_weights(1234)
+    x = synth.synth_frames(1, seed=24)
+    refs = oracle_reception.forward(ops_torch, m.get_weights(), x, **kw)
+    outs = m.predict(x)
+    _check(outs, [r.astype(np.float64) for r in refs])

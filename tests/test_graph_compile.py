@@ -1,0 +1,83 @@
+"""Host-side logic (no GPU): the product's layer graph must expose exactly the weight list
+(names, Keras layouts, creation order) that the oracle's independent restatement consumes;
+synthetic weight generators agree; fusion plan sanity; FLOP counts of SURVEY.md 8(d)."""
+import numpy as np
+
+from deephar_b200 import reception
+from deephar_b200.weights import load_calibration, split_bf16, synthetic_weight
+from oracle import ops_torch
+from oracle import reception as oracle_reception
+from oracle import synth
+
+
+def _oracle_used(res, **kw):
+    tab = synth.SyntheticTable(1234)
+    x = synth.synth_frames(1, res, res)
+    _, used = oracle_reception.forward(ops_torch, tab, x, return_weights_used=True, **kw)
+    return used
+
+
+def test_weight_specs_match_oracle_2d():
+    kw = dict(num_joints=16, dim=2, num_context_per_joint=2, num_blocks=3, ksize=(5, 5))
+    m = reception.build((64, 64, 3), **kw)
+    assert m.weight_specs == _oracle_used(64, **kw)
+
+
+def test_weight_specs_match_oracle_3d():
+    kw = dict(num_joints=17, dim=3, num_blocks=2, ksize=(3, 3))
+    m = reception.build((64, 64, 3), **kw)
+    assert m.weight_specs == _oracle_used(64, **kw)
+
+
+def test_synthetic_generators_agree():
+    calib = load_calibration('reception_j16_d2_c2_k5')
+    assert len(calib) > 50
+    m = reception.build((64, 64, 3), 16, 2, num_blocks=1, ksize=(5, 5))
+    for name, shape in m.weight_specs[:40] + m.weight_specs[-10:]:
+        a = synthetic_weight(1234, name, shape, calib)
+        b = synth.synth_weight(1234, name, shape, calib)
+        assert np.array_equal(a, b), name
+
+
+def test_param_count_and_plan():
+    m = reception.build((256, 256, 3), 16, 2, num_context_per_joint=2, num_blocks=8, ksize=(5, 5),
+                        concat_pose_confidence=False)
+    assert m.count_params() == 14746560          # 14.75 M
+    assert len(m.outputs) == 16
+    assert m.input_shape == (None, 256, 256, 3)
+    st = m.plan.stats
+    assert st['kernel_ops'] < st['graph_nodes'] / 2.5     # BN/ReLU/add/concat fused away
+    kinds = [k.kind for k in m.plan.kops]
+    assert 'affine' not in kinds and 'add' not in kinds and 'copy' not in kinds
+    assert kinds.count('pose_regression_2d_context') == 8
+    flops = m.conv_flops_per_frame()
+    assert abs(flops - 19.67e9) / 19.67e9 < 0.005
+
+
+def test_flops_3d():
+    m = reception.build((256, 256, 3), 17, 3, num_blocks=8, ksize=(5, 5), concat_pose_confidence=False)
+    assert abs(m.conv_flops_per_frame() - 23.63e9) / 23.63e9 < 0.005
+    assert m.count_params() == 16683712 or abs(m.count_params() - 16.68e6) < 0.01e6
+
+
+def test_output_order_and_shapes():
+    m = reception.build((64, 64, 3), 16, 2, num_blocks=2, ksize=(3, 3))
+    assert m.output_shape == [(None, 16, 3), (None, 16, 3)]
+    m = reception.build((64, 64, 3), 17, 3, num_blocks=2, concat_pose_confidence=False)
+    assert m.output_shape == [(None, 17, 3), (None, 17, 1)] * 2
+
+
+def test_argument_errors_match_reference():
+    import pytest
+    with pytest.raises(ValueError):
+        reception.build((64, 64, 3), 16, 4)
+    with pytest.raises(AssertionError):
+        reception.build((64, 64, 3), 17, 3, num_context_per_joint=2)
+
+
+def test_split_bf16_reconstructs():
+    rng = np.random.default_rng(0)
+    w = rng.standard_normal(4096).astype(np.float32)
+    hi, lo = split_bf16(w)
+    rec = (hi.astype(np.uint32) << 16).view(np.float32) + (lo.astype(np.uint32) << 16).view(np.float32)
+    assert np.abs(rec - w).max() <= np.abs(w).max() * 2.0 ** -16
