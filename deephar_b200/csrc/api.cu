@@ -43,6 +43,7 @@ extern "C" int dh_ctx_create(dh_ctx** out, int device) {
     c->launches = 0;
     c->workspace = nullptr;
     c->workspace_bytes = 0;
+    c->last_conv_path = 0;
     *out = c;
     return 0;
 }
@@ -58,6 +59,8 @@ extern "C" int64_t dh_launch_count(dh_ctx* ctx, int reset) {
     if (reset) ctx->launches = 0;
     return v;
 }
+
+extern "C" int dh_last_conv_path(dh_ctx* ctx) { return ctx ? ctx->last_conv_path : -1; }
 
 extern "C" int dh_set_workspace(dh_ctx* ctx, void* ptr, int64_t bytes) {
     DH_CHECK_ARG(ctx != nullptr, "dh_set_workspace: ctx is NULL");

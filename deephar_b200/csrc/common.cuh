@@ -11,6 +11,7 @@ struct dh_ctx {
     int64_t launches;
     void* workspace;
     int64_t workspace_bytes;
+    int last_conv_path;   // 0 = CUDA-core kernels, 1 = tcgen05 kernel (test / bench introspection)
 };
 
 void dh_set_error(const char* fmt, ...);

@@ -1,13 +1,663 @@
-// tcgen05 tensor-core convolution path (placeholder: not taking any op yet).
+// tcgen05 tensor-core convolutions for sm_100a: Conv2D (1x1 and dense kxk) and the fused
+// SeparableConv2D (depthwise kxk + pointwise 1x1 in ONE kernel; the depthwise result never
+// leaves the SM), with BatchNorm / ReLU prologue, BatchNorm / ReLU / residual-add epilogue.
+//
+// replaces: keras SeparableConv2D / Conv2D lowered by TF-1.6 to cuDNN (deephar/layers.py:66-80)
+// and the BN / Activation / add layers around them (layers.py:202-325, models/common.py:25-67,
+// models/reception.py:43-59).
+//
+// Shape of the computation (per CTA):  D[128 px, BN couts] = A[128 px, K] * W[K, BN]
+//   A  : produced by 8 CUDA-core warps straight into the 128B-swizzled K-major UMMA layout in
+//        shared memory.  dense / 1x1: im2col gather (+prologue).  separable: the depthwise kxk
+//        (register-tiled: each thread owns 2 channels x 4x4 output pixels, 25 taps in registers).
+//   W  : weights, pre-packed on the host as bf16 [Cout_pad][K_pad] K-major, loaded by TMA
+//        (cp.async.bulk.tensor, 128B swizzle) into the same UMMA layout.
+//   D  : fp32 accumulators in TMEM; one elected thread issues tcgen05.mma (kind::f16, bf16).
+//   precision = 3: both operands are split x = hi + lo (bf16 each) and three MMAs
+//        (hi*hi + lo*hi + hi*lo) accumulate in fp32 -> ~2^-16 relative operand error, which keeps
+//        the <=1e-3 parity bar through 8 stacked blocks; precision = 1 issues hi*hi only.
+//   epilogue: tcgen05.ld -> registers -> BN affine, ReLU, residual adds -> global stores.
+//
+// Pipeline: `stages` x {A_hi, A_lo, W_hi, W_lo} ring; mbarriers full[s] (256 producer arrivals
+// + TMA transaction bytes) / empty[s] (tcgen05.commit) / tmem_full.
+#include <cuda.h>
+#include <cuda_bf16.h>
 #include "common.cuh"
 #include "conv_params.cuh"
-bool dh_tc_supported(const ConvParams& p, const dh_packed_w* packed, bool separable) {
-    (void)p; (void)packed; (void)separable;
-    return false;
+
+namespace tc {
+
+constexpr int BM = 128;
+constexpr int BK = 64;                 // bf16 per K-block = one 128-byte swizzle row
+constexpr int NPROD = 256;             // producer / epilogue threads (warps 0..7)
+constexpr int WARP_TMA = 8, WARP_MMA = 9;
+constexpr int NTHREADS = NPROD + 64;
+constexpr int A_TILE_BYTES = BM * 128; // 16 KB per (hi | lo)
+constexpr int MAX_STAGES = 4;
+constexpr int MAX_BN_CTA = 288;
+
+struct TcParams {
+    ConvParams c;
+    int n_kblocks;
+    int bn_cta, nsub, nw;   // bn_cta = nsub * nw, nw = MMA N (multiple of 16, <= 256)
+    int stages;
+    int precision;          // 1 | 3
+    int tmem_cols;          // power of two >= bn_cta
+    uint32_t idesc;
+    int ks;                 // separable: depthwise kernel size (3 | 5); 0 = dense
+    int k_pad;
+};
+
+// ---------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
-int dh_launch_conv_tc(dh_ctx* ctx, const ConvParams& p, const dh_packed_w* packed, bool separable,
-                      int precision, cudaStream_t s) {
-    (void)ctx; (void)p; (void)packed; (void)separable; (void)precision; (void)s;
-    dh_set_error("dh_launch_conv_tc: not built");
-    return -1;
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"(bar), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], bf16 x bf16 -> fp32
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
+        " tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, 128-byte swizzle UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor):
+// start>>4 [0,14) | LBO>>4 [16,30) (unused for swizzled K-major, 1) | SBO>>4 [32,46) = 1024 B
+// (8 rows x 128 B per swizzle atom) | version 1 [46,48) | layout SWIZZLE_128B = 2 [61,64).
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+           (2ull << 61);
+}
+
+// fp32 -> (hi, lo) bf16 split, round-to-nearest-even: x ~= hi + lo to ~16 mantissa bits.
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    float ra = a - __low2float(h), rb = b - __high2float(h);
+    __nv_bfloat162 l = __floats2bfloat162_rn(ra, rb);
+    hi = *reinterpret_cast<uint32_t*>(&h);
+    lo = *reinterpret_cast<uint32_t*>(&l);
+}
+
+// byte offset of element (row, k) inside a [rows][64 bf16] 128B-swizzled K-major tile
+__device__ __forceinline__ uint32_t swz(int row, int k) {
+    return (uint32_t)(row * 128 + ((((k >> 3) ^ (row & 7)) << 4) | ((k & 7) << 1)));
+}
+
+// ---------------------------------------------------------------------------
+// A-tile producers
+// ---------------------------------------------------------------------------
+// dense / 1x1: item = (pixel row, 4 consecutive k); 16 items per row, 8 rows per thread.
+// The per-row pixel coordinates do not depend on the K-block: they are decoded once per CTA
+// (DenseRows) so the K loop is 8 independent 16-byte loads issued back to back.
+struct DenseRows {
+    int base[8];   // (n*H)*W  -- pixel index of the frame origin, -1 = row outside M
+    int yx[8];     // (oy*sh - pt) << 16 | ((ox*sw - pl) & 0xffff)
+};
+
+__device__ __forceinline__ void dense_rows_init(const ConvParams& c, int m0, int tid, DenseRows& R) {
+    const int HoWo = c.Ho * c.Wo;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int m = m0 + (tid >> 4) + i * 16;
+        if (m < c.M) {
+            int n = m / HoWo;
+            int rem = m - n * HoWo;
+            int oy = rem / c.Wo;
+            int ox = rem - oy * c.Wo;
+            R.base[i] = n * c.H * c.W;
+            R.yx[i] = ((oy * c.sh - c.pt) << 16) | ((ox * c.sw - c.pl) & 0xffff);
+        } else {
+            R.base[i] = -1;
+            R.yx[i] = 0;
+        }
+    }
+}
+
+__device__ __forceinline__ void produce_dense(const TcParams& P, const DenseRows& R, int kb, uint8_t* a_hi,
+                                              uint8_t* a_lo, int tid, bool want_lo) {
+    const ConvParams& c = P.c;
+    const int j = tid & 15;
+    const int k = kb * BK + j * 4;          // k = tap*Cin + ci, groups of 4 never straddle a tap (Cin % 4 == 0)
+    const bool kval = k < c.K;
+    int ci = 0, ky = 0, kx = 0;
+    if (kval) {
+        int tap = k / c.Cin;
+        ci = k - tap * c.Cin;
+        ky = tap / c.kw;
+        kx = tap - ky * c.kw;
+    }
+    float4 ps = make_float4(1.f, 1.f, 1.f, 1.f), pb = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (kval && c.pre_scale) {
+        ps = __ldg(reinterpret_cast<const float4*>(c.pre_scale + ci));
+        pb = __ldg(reinterpret_cast<const float4*>(c.pre_shift + ci));
+    }
+    float4 v[8];
+    bool ok[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int iy = (R.yx[i] >> 16) + ky, ix = (int)(short)(R.yx[i] & 0xffff) + kx;
+        ok[i] = kval && R.base[i] >= 0 && iy >= 0 && iy < c.H && ix >= 0 && ix < c.W;
+        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok[i]) v[i] = __ldg(reinterpret_cast<const float4*>(c.x + (size_t)(R.base[i] + iy * c.W + ix) * c.ldx + ci));
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        float4 t = v[i];
+        if (ok[i]) {
+            t.x = fmaf(t.x, ps.x, pb.x); t.y = fmaf(t.y, ps.y, pb.y);
+            t.z = fmaf(t.z, ps.z, pb.z); t.w = fmaf(t.w, ps.w, pb.w);
+            if (c.pre_relu) {
+                t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f);
+            }
+        }
+        uint32_t h0, l0, h1, l1;
+        split2(t.x, t.y, h0, l0);
+        split2(t.z, t.w, h1, l1);
+        const uint32_t off = swz((tid >> 4) + i * 16, j * 4);
+        *reinterpret_cast<uint2*>(a_hi + off) = make_uint2(h0, h1);
+        if (want_lo) *reinterpret_cast<uint2*>(a_lo + off) = make_uint2(l0, l1);
+    }
+}
+
+// separable: thread = (2 channels, 4 columns, 4-row strip).  32 channel pairs x (128/16) pixel
+// blocks = 256 threads per 64-channel K-block; the KSxKS taps of the thread's 2 channels live in
+// registers; input rows slide through a 3-row rotating register buffer that is loaded two rows
+// ahead of the FMAs (16-24 loads in flight per thread; every input value is loaded once per
+// thread).  Stride 1, TF SAME padding (symmetric for odd KS).
+template <int KS>
+__device__ __forceinline__ void produce_sep(const TcParams& P, int kb, uint8_t* a_hi, uint8_t* a_lo, int m0,
+                                            int tid, bool want_lo) {
+    const ConvParams& c = P.c;
+    constexpr int PAD = KS / 2;
+    constexpr int NR = 4 + KS - 1;        // input rows (and columns) per thread
+    const int cg = tid & 31;              // channel pair inside the K-block
+    const int blk = tid >> 5;             // pixel block: 4 rows x 4 cols
+    const int ch = kb * BK + cg * 2;
+    const int W = c.W, H = c.H;
+    const int cols4 = W >> 2;             // column groups per row
+    const int strip = blk / cols4;        // 4-row strip inside the tile
+    const int x0 = (blk - strip * cols4) * 4;
+    const int mrow = m0 / W + strip * 4;  // global row index (n*H + y) of the strip's first row
+    const int n = mrow / H;
+    const int y0 = mrow - n * H;
+    const bool cval = ch < c.Cin;
+    const bool tile_valid = (m0 + strip * 4 * W) < c.M;   // whole strips are valid or not (M % (4W) == 0)
+
+    float acc[4][4][2];
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[o][q][0] = acc[o][q][1] = 0.f;
+
+    if (cval && tile_valid) {
+        const float* xb = c.x + (size_t)n * H * W * c.ldx + ch;
+        unsigned colmask = 0;
+#pragma unroll
+        for (int q = 0; q < NR; ++q) {
+            const int ix = x0 - PAD + q;
+            if (ix >= 0 && ix < W) colmask |= 1u << q;
+        }
+        float2 buf[3][NR];
+        auto load_row = [&](int r, float2* dst) {
+            const int iy = y0 - PAD + r;
+            const bool rowok = iy >= 0 && iy < H;
+            const float* rp = xb + (size_t)(iy * W + x0 - PAD) * c.ldx;
+#pragma unroll
+            for (int q = 0; q < NR; ++q) {
+                dst[q] = make_float2(0.f, 0.f);
+                if (rowok && ((colmask >> q) & 1u)) dst[q] = __ldg(reinterpret_cast<const float2*>(rp + (size_t)q * c.ldx));
+            }
+        };
+        load_row(0, buf[0]);
+        load_row(1, buf[1]);
+        float2 wt[KS][KS];
+#pragma unroll
+        for (int a = 0; a < KS; ++a)
+#pragma unroll
+            for (int b = 0; b < KS; ++b)
+                wt[a][b] = __ldg(reinterpret_cast<const float2*>(c.w_dw + (size_t)(a * KS + b) * c.Cin + ch));
+        float2 ps = make_float2(1.f, 1.f), pb = make_float2(0.f, 0.f);
+        if (c.pre_scale) {
+            ps = __ldg(reinterpret_cast<const float2*>(c.pre_scale + ch));
+            pb = __ldg(reinterpret_cast<const float2*>(c.pre_shift + ch));
+        }
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            if (r + 2 < NR) load_row(r + 2, buf[(r + 2) % 3]);
+            const int iy = y0 - PAD + r;
+            const bool rowok = iy >= 0 && iy < H;
+            float2 in[NR];
+#pragma unroll
+            for (int q = 0; q < NR; ++q) {
+                float2 v = buf[r % 3][q];
+                if (rowok && ((colmask >> q) & 1u)) {      // zero padding is applied AFTER BN/ReLU
+                    v.x = fmaf(v.x, ps.x, pb.x);
+                    v.y = fmaf(v.y, ps.y, pb.y);
+                    if (c.pre_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); }
+                }
+                in[q] = v;
+            }
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+                const int ky = r - o;          // compile-time after unrolling
+                if (ky >= 0 && ky < KS) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+#pragma unroll
+                        for (int kx = 0; kx < KS; ++kx) {
+                            acc[o][q][0] = fmaf(wt[ky][kx].x, in[q + kx].x, acc[o][q][0]);
+                            acc[o][q][1] = fmaf(wt[ky][kx].y, in[q + kx].y, acc[o][q][1]);
+                        }
+                }
+            }
+        }
+    }
+    // write the 16 pixels x 2 channels into the swizzled A tile
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int row = (strip * 4 + o) * W + x0 + q;   // row inside the 128-pixel tile
+            uint32_t hi, lo;
+            split2(acc[o][q][0], acc[o][q][1], hi, lo);
+            const uint32_t off = swz(row, cg * 2);
+            *reinterpret_cast<uint32_t*>(a_hi + off) = hi;
+            if (want_lo) *reinterpret_cast<uint32_t*>(a_lo + off) = lo;
+        }
+}
+
+// ---------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------
+template <int MODE>   // 0 dense/1x1, 3 separable 3x3, 5 separable 5x5
+__global__ void __launch_bounds__(NTHREADS, 1)
+conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUtensorMap map_hi,
+               const __grid_constant__ CUtensorMap map_lo) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const bool want_lo = P.precision == 3;
+    const int b_tile_bytes = P.bn_cta * 128;
+    const int stage_bytes = 2 * A_TILE_BYTES + 2 * b_tile_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)P.stages * stage_bytes);
+    // bars[0..S) full, [S..2S) empty, [2S] tmem_full ; then the TMEM base address word
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 1);
+    const uint32_t bar_full0 = smem_u32(bars), bar_empty0 = smem_u32(bars + P.stages),
+                   bar_tmem = smem_u32(bars + 2 * P.stages);
+    const int m0 = blockIdx.x * BM;
+    const int n0 = blockIdx.y * P.bn_cta;
+
+    if (warp == WARP_TMA && lane == 0) {
+        tma_prefetch_desc(&map_hi);
+        if (want_lo) tma_prefetch_desc(&map_lo);
+        for (int s = 0; s < P.stages; ++s) {
+            mbar_init(bar_full0 + 8 * s, NPROD + 1);
+            mbar_init(bar_empty0 + 8 * s, 1);
+        }
+        mbar_init(bar_tmem, 1);
+        fence_barrier_init();
+    }
+    if (warp == WARP_MMA) tmem_alloc(smem_u32(tmem_slot), (uint32_t)P.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 8) {
+        // ======================= A producers =======================
+        DenseRows rows;
+        if (MODE == 0) dense_rows_init(P.c, m0, tid, rows);
+        for (int kb = 0; kb < P.n_kblocks; ++kb) {
+            const int s = kb % P.stages;
+            const uint32_t it = (uint32_t)(kb / P.stages);
+            mbar_wait(bar_empty0 + 8 * s, (it & 1) ^ 1);
+            uint8_t* a_hi = smem + (size_t)s * stage_bytes;
+            uint8_t* a_lo = a_hi + A_TILE_BYTES;
+            if (MODE == 0) produce_dense(P, rows, kb, a_hi, a_lo, tid, want_lo);
+            else if (MODE == 3) produce_sep<3>(P, kb, a_hi, a_lo, m0, tid, want_lo);
+            else produce_sep<5>(P, kb, a_hi, a_lo, m0, tid, want_lo);
+            fence_proxy_async();           // generic-proxy smem writes -> visible to the tensor core
+            mbar_arrive(bar_full0 + 8 * s);
+        }
+        // ======================= epilogue =======================
+        // TMEM -> registers (lane = pixel row) -> per-warp smem transpose (the drained stage-0
+        // buffers are reused) -> lane = output channel: every global access below is a fully
+        // coalesced 128-byte row segment; BN affine / ReLU / residual adds are fused here.
+        mbar_wait(bar_tmem, 0);
+        tc_fence_after();
+        const ConvParams& c = P.c;
+        const int q = warp & 3, half = warp >> 2;
+        constexpr int TS = 36;                                 // tile row stride (floats): 16B-aligned rows
+        float* tile = reinterpret_cast<float*>(smem) + warp * (32 * TS);
+        const int mbase = m0 + q * 32;
+        const int nch32 = (P.bn_cta + 31) >> 5;               // 32-column chunks (last may be 16 wide)
+        const int c_begin = half == 0 ? 0 : (nch32 + 1) / 2;
+        const int c_end = half == 0 ? (nch32 + 1) / 2 : nch32;
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+        const bool vec_ok = ((c.ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(c.out) & 15) == 0) &&
+                            (!c.res0 || (((c.ldr0 & 3) == 0) && ((reinterpret_cast<uintptr_t>(c.res0) & 15) == 0))) &&
+                            (!c.res1 || (((c.ldr1 & 3) == 0) && ((reinterpret_cast<uintptr_t>(c.res1) & 15) == 0))) &&
+                            ((c.Cout & 3) == 0) &&
+                            (!c.post_scale || (((reinterpret_cast<uintptr_t>(c.post_scale) & 15) == 0) &&
+                                               ((reinterpret_cast<uintptr_t>(c.post_shift) & 15) == 0)));
+        for (int ck = c_begin; ck < c_end; ++ck) {
+            const int col0 = ck * 32;
+            const int width = min(32, P.bn_cta - col0);        // 32 or 16
+            {
+                float v[32];
+                tmem_ld16(trow + (uint32_t)col0, v);
+                if (width == 32) tmem_ld16(trow + (uint32_t)(col0 + 16), v + 16);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (j * 4 < width)
+                        *reinterpret_cast<float4*>(tile + lane * TS + j * 4) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+            __syncwarp();
+            if (vec_ok) {
+                // lane = (row r4 = lane/8 + 4*i, 4 columns c4 = lane%8): 4 rows x 128 B per instruction
+                const int c4 = (lane & 7) * 4;
+                const int co = n0 + col0 + c4;
+                const bool cok = c4 < width && co < c.Cout;
+                float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (cok && c.post_scale) {
+                    sc = __ldg(reinterpret_cast<const float4*>(c.post_scale + co));
+                    sh = __ldg(reinterpret_cast<const float4*>(c.post_shift + co));
+                }
+                float4 ra[8], rb[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int m = mbase + (lane >> 3) + 4 * i;
+                    ra[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    rb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (cok && m < c.M) {
+                        if (c.res0) ra[i] = __ldg(reinterpret_cast<const float4*>(c.res0 + (size_t)m * c.ldr0 + co));
+                        if (c.res1) rb[i] = __ldg(reinterpret_cast<const float4*>(c.res1 + (size_t)m * c.ldr1 + co));
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int r = (lane >> 3) + 4 * i;
+                    const int m = mbase + r;
+                    if (cok && m < c.M) {
+                        float4 t = *reinterpret_cast<const float4*>(tile + r * TS + c4);
+                        t.x = fmaf(t.x, sc.x, sh.x); t.y = fmaf(t.y, sc.y, sh.y);
+                        t.z = fmaf(t.z, sc.z, sh.z); t.w = fmaf(t.w, sc.w, sh.w);
+                        if (c.post_relu) {
+                            t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f);
+                        }
+                        t.x += ra[i].x + rb[i].x; t.y += ra[i].y + rb[i].y;
+                        t.z += ra[i].z + rb[i].z; t.w += ra[i].w + rb[i].w;
+                        *reinterpret_cast<float4*>(c.out + (size_t)m * c.ldo + co) = t;
+                    }
+                }
+            } else {
+                const int co = n0 + col0 + lane;
+                const bool cok = lane < width && co < c.Cout;
+                float sc = 1.f, sh = 0.f;
+                if (cok && c.post_scale) {
+                    sc = __ldg(c.post_scale + co);
+                    sh = __ldg(c.post_shift + co);
+                }
+#pragma unroll 8
+                for (int r = 0; r < 32; ++r) {
+                    const int m = mbase + r;
+                    if (cok && m < c.M) {
+                        float t = fmaf(tile[r * TS + lane], sc, sh);
+                        if (c.post_relu) t = fmaxf(t, 0.f);
+                        if (c.res0) t += __ldg(c.res0 + (size_t)m * c.ldr0 + co);
+                        if (c.res1) t += __ldg(c.res1 + (size_t)m * c.ldr1 + co);
+                        c.out[(size_t)m * c.ldo + co] = t;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    } else if (warp == WARP_TMA) {
+        // ======================= weight tiles via TMA =======================
+        if (lane == 0) {
+            const uint32_t tx = (uint32_t)(want_lo ? 2 : 1) * (uint32_t)b_tile_bytes;
+            for (int kb = 0; kb < P.n_kblocks; ++kb) {
+                const int s = kb % P.stages;
+                const uint32_t it = (uint32_t)(kb / P.stages);
+                mbar_wait(bar_empty0 + 8 * s, (it & 1) ^ 1);
+                const uint32_t full = bar_full0 + 8 * s;
+                mbar_arrive_expect_tx(full, tx);
+                const uint32_t b_hi = smem_u32(smem + (size_t)s * stage_bytes + 2 * A_TILE_BYTES);
+                const uint32_t b_lo = b_hi + (uint32_t)b_tile_bytes;
+                for (int sub = 0; sub < P.nsub; ++sub) {
+                    tma_load_2d(b_hi + (uint32_t)(sub * P.nw * 128), &map_hi, kb * BK, n0 + sub * P.nw, full);
+                    if (want_lo)
+                        tma_load_2d(b_lo + (uint32_t)(sub * P.nw * 128), &map_lo, kb * BK, n0 + sub * P.nw, full);
+                }
+            }
+        }
+    } else {
+        // ======================= MMA issue (one thread) =======================
+        if (lane == 0) {
+            for (int kb = 0; kb < P.n_kblocks; ++kb) {
+                const int s = kb % P.stages;
+                const uint32_t it = (uint32_t)(kb / P.stages);
+                mbar_wait(bar_full0 + 8 * s, it & 1);
+                tc_fence_after();
+                const uint32_t a_hi = smem_u32(smem + (size_t)s * stage_bytes);
+                const uint32_t a_lo = a_hi + A_TILE_BYTES;
+                const uint32_t b_hi = a_hi + 2 * A_TILE_BYTES;
+                const uint32_t b_lo = b_hi + (uint32_t)b_tile_bytes;
+                for (int sub = 0; sub < P.nsub; ++sub) {
+                    const uint32_t d = tmem_base + (uint32_t)(sub * P.nw);
+                    const uint32_t bo = (uint32_t)(sub * P.nw * 128);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        const uint32_t ko = (uint32_t)(k * 32);      // 16 bf16 = 32 B along the swizzle row
+                        const uint32_t acc0 = (kb > 0 || k > 0) ? 1u : 0u;
+                        umma_bf16(d, make_desc(a_hi + ko), make_desc(b_hi + bo + ko), P.idesc, acc0);
+                        if (want_lo) {
+                            umma_bf16(d, make_desc(a_lo + ko), make_desc(b_hi + bo + ko), P.idesc, 1u);
+                            umma_bf16(d, make_desc(a_hi + ko), make_desc(b_lo + bo + ko), P.idesc, 1u);
+                        }
+                    }
+                }
+                umma_commit(bar_empty0 + 8 * s);      // frees this smem stage when the MMAs retire
+            }
+            umma_commit(bar_tmem);                    // accumulators complete -> epilogue
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == WARP_MMA) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+static bool make_map(CUtensorMap* map, const void* base, int k_pad, int rows, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)k_pad, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)k_pad * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+// N tiling rule shared with the host-side weight packer (dh_tc_cout_pad).
+static void tile_n(int cout, int* bn_cta, int* gy, int* nsub, int* nw) {
+    int cp = (cout + 15) / 16 * 16;
+    int g = (cp + MAX_BN_CTA - 1) / MAX_BN_CTA;
+    int bn = ((cp + g - 1) / g + 15) / 16 * 16;
+    int ns = 1;
+    if (bn > 256) {
+        bn = (bn + 31) / 32 * 32;
+        ns = 2;
+    }
+    *bn_cta = bn; *gy = g; *nsub = ns; *nw = bn / ns;
+}
+
+}  // namespace tc
+
+extern "C" int dh_tc_cout_pad(int cout) {
+    int bn, gy, ns, nw;
+    tc::tile_n(cout, &bn, &gy, &ns, &nw);
+    return bn * gy;
+}
+
+extern "C" int dh_tc_k_pad(int k) { return (k + tc::BK - 1) / tc::BK * tc::BK; }
+
+bool dh_tc_supported(const ConvParams& p, const dh_packed_w* packed, bool separable) {
+    if (!packed || !packed->hi) return false;
+    if (p.M < 1) return false;
+    if ((reinterpret_cast<uintptr_t>(p.x) & 15) != 0) return false;
+    const int K = separable ? p.Cin : p.kh * p.kw * p.Cin;
+    if (packed->k != dh_tc_k_pad(K) || packed->cout_pad != dh_tc_cout_pad(p.Cout)) return false;
+    if (p.pre_scale && ((reinterpret_cast<uintptr_t>(p.pre_scale) & 15) || (reinterpret_cast<uintptr_t>(p.pre_shift) & 15)))
+        return false;
+    if (separable) {
+        if (!(p.kh == p.kw && (p.kh == 3 || p.kh == 5))) return false;
+        if (p.sh != 1 || p.sw != 1) return false;
+        if (p.Ho != p.H || p.Wo != p.W) return false;                 // SAME, stride 1
+        if (p.W < 4 || (tc::BM % p.W) != 0 || (p.W & 3) || (p.H & 3)) return false;
+        if ((p.Cin & 1) || (p.ldx & 1)) return false;
+        if ((reinterpret_cast<uintptr_t>(p.w_dw) & 7) != 0) return false;
+        if (p.M % (4 * p.W) != 0) return false;
+        return true;
+    }
+    if ((p.Cin & 3) || (p.ldx & 3)) return false;
+    return true;
+}
+
+int dh_launch_conv_tc(dh_ctx* ctx, const ConvParams& p, const dh_packed_w* packed, bool separable, int precision,
+                      cudaStream_t s) {
+    using namespace tc;
+    (void)ctx;
+    TcParams P;
+    P.c = p;
+    const int K = separable ? p.Cin : p.kh * p.kw * p.Cin;
+    P.c.K = K;
+    P.k_pad = packed->k;
+    P.n_kblocks = packed->k / BK;
+    int gy;
+    tile_n(p.Cout, &P.bn_cta, &gy, &P.nsub, &P.nw);
+    P.precision = (precision == 1) ? 1 : 3;
+    P.ks = separable ? p.kh : 0;
+    int tm = 32;
+    while (tm < P.bn_cta) tm <<= 1;
+    P.tmem_cols = tm;
+    // cute::UMMA::InstrDescriptor: c_format F32 [4,6)=1, a/b_format BF16 [7,10)/[10,13)=1, K-major A and B,
+    // n_dim = N>>3 at [17,23), m_dim = M>>4 at [24,29)
+    P.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.nw >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    const int stage_bytes = 2 * A_TILE_BYTES + 2 * P.bn_cta * 128;
+    const int budget = 227 * 1024 - 1024 /*alignment*/ - 256 /*barriers*/;
+    int stages = budget / stage_bytes;
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    if (stages > P.n_kblocks) stages = P.n_kblocks;
+    if (stages < 1) {
+        dh_set_error("dh_launch_conv_tc: tile does not fit shared memory");
+        return -1;
+    }
+    P.stages = stages;
+    const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
+
+    CUtensorMap map_hi, map_lo;
+    if (!make_map(&map_hi, packed->hi, packed->k, packed->cout_pad, P.nw) ||
+        !make_map(&map_lo, packed->lo ? packed->lo : packed->hi, packed->k, packed->cout_pad, P.nw)) {
+        dh_set_error("dh_launch_conv_tc: cuTensorMapEncodeTiled failed");
+        return -1;
+    }
+    dim3 grid((p.M + BM - 1) / BM, gy);
+    cudaError_t e;
+#define DH_TC_LAUNCH(MODE)                                                                                   \
+    do {                                                                                                     \
+        e = cudaFuncSetAttribute(conv_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e == cudaSuccess) conv_tc_kernel<MODE><<<grid, NTHREADS, smem, s>>>(P, map_hi, map_lo);           \
+    } while (0)
+    if (!separable) DH_TC_LAUNCH(0);
+    else if (p.kh == 3) DH_TC_LAUNCH(3);
+    else DH_TC_LAUNCH(5);
+#undef DH_TC_LAUNCH
+    if (e != cudaSuccess) {
+        dh_set_error("dh_launch_conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        return (int)e;
+    }
+    return 0;
 }

@@ -165,6 +165,35 @@ class Model(object):
         self._dev = torch.from_numpy(flat).cuda()
         base = self._dev.data_ptr()
         self._ptr = {k: base + 4 * o for k, o in offsets.items()}
+        # bf16 hi/lo operand copies for the tcgen05 path (tc.py / conv_tc.cu)
+        self._packed_info = {}
+        if self.use_tensor_cores:
+            from . import tc
+            parts, poff = [], 0
+            for k in self.plan.kops:
+                if k.kind not in ('conv', 'sepconv') or not tc.conv_eligible(k):
+                    continue
+                key = k.attrs['kernel'] if k.kind == 'conv' else k.attrs['pointwise']
+                if key in self._packed_info:
+                    continue
+                w = hw[key]
+                hi, lo, cp, kp = tc.pack_conv_kernel(w)
+                rec = {'cout_pad': cp, 'k_pad': kp}
+                for nm, arr in (('hi', hi), ('lo', lo)):
+                    rec[nm] = poff
+                    parts.append(arr.ravel())
+                    pad = (-arr.size) % 128
+                    if pad:
+                        parts.append(np.zeros(pad, np.uint16))
+                    poff += arr.size + pad
+                self._packed_info[key] = rec
+            if parts:
+                arena = np.concatenate(parts).view(np.int16)
+                self._dev_packed = torch.from_numpy(arena).cuda()
+                pbase = self._dev_packed.data_ptr()
+                for rec in self._packed_info.values():
+                    rec['hi'] = pbase + 2 * rec['hi']
+                    rec['lo'] = pbase + 2 * rec['lo']
 
     def _keras_shape(self, t, n):
         h, w, c = t.shape
@@ -288,7 +317,13 @@ class Model(object):
         return b
 
     def _packed(self, k, b):
-        return None     # tensor-core weight packing is attached by tc.py when enabled
+        key = k.attrs['kernel'] if k.kind == 'conv' else k.attrs['pointwise']
+        rec = getattr(self, '_packed_info', {}).get(key)
+        if rec is None:
+            return None
+        pw = _ffi.dh_packed_w(rec['hi'], rec['lo'], rec['cout_pad'], rec['k_pad'])
+        b.keep.append(pw)
+        return C.pointer(pw)
 
     def _run(self, b, stream_ptr):
         self._ctx.set_workspace(b.workspace.data_ptr(), b.workspace.numel() * 4)
@@ -364,7 +399,7 @@ class Model(object):
         return 'f32'
 
     def _uses_tc(self):
-        return False
+        return bool(getattr(self, '_packed_info', None))
 
     def profile(self, x_dev):
         """One forward with CUDA events around every kernel op (launch stream = torch's current

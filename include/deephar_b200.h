@@ -81,6 +81,14 @@ int64_t     dh_launch_count(dh_ctx* ctx, int reset);
 int         dh_set_workspace(dh_ctx* ctx, void* ptr, int64_t bytes);
 
 /* --- convolutions -------------------------------------------------------- */
+/* Tensor-core weight packing geometry: dh_packed_w.hi/lo are bf16 [dh_tc_cout_pad(Cout)][dh_tc_k_pad(K)]
+ * (zero padded), K = kh*kw*Cin ordered (ky,kx,ci) for Conv2D, K = Cin for the pointwise stage. */
+int dh_tc_cout_pad(int cout);
+int dh_tc_k_pad(int k);
+/* which kernel family served the last dh_conv2d_f32 / dh_sepconv2d_f32 on this context:
+ * 0 = CUDA-core (fp32 FFMA), 1 = tcgen05 tensor-core kernel. */
+int dh_last_conv_path(dh_ctx* ctx);
+
 /* keras Conv2D(use_bias=False) (layers.py:66-71) with fused pre/post ops.
  * w: HWIO (kh,kw,Cin,Cout) fp32 -- the keras kernel layout, unchanged.
  * packed may be NULL (CUDA-core path only). */

@@ -204,13 +204,18 @@ def context_aggregation_model(ops, ys, yc, pc, num_joints, num_context, alpha):
     return alpha * ys + (1 - alpha) * yc_div
 
 
-def pose_regression_2d_context(ops, h, num_joints, num_context, alpha):
-    """reception.py:167-182."""
+def pose_regression_2d_context(ops, h, num_joints, num_context, alpha, debug=None):
+    """reception.py:167-182.  `debug` (dict) receives the conditioning of the context division:
+    the reference divides by sum_ctx(pc) where pc are RAW (possibly negative) confidences
+    (blocks.py:264-267), so |sum pc| << sum |pc| makes that joint ill-conditioned in ANY precision."""
     hs = h[..., :num_joints]
     hc = h[..., num_joints:]
     ps = softargmax_2d_model(ops, hs)
     pc = softargmax_2d_model(ops, hc)
     vc = joints_probability_model(ops, hc)
+    if debug is not None:
+        v = np.asarray(ops.to_numpy(vc), dtype=np.float64).reshape(-1, num_joints, num_context)
+        debug.setdefault('ctx_cond', []).append(np.abs(v).sum(-1) / np.maximum(np.abs(v.sum(-1)), 1e-300))
     pose = context_aggregation_model(ops, ps, pc, vc, num_joints, num_context, alpha)
     visible = joints_probability_model(ops, hs)
     return pose, visible, hs
@@ -239,7 +244,7 @@ def pose_regression_3d(ops, h, num_joints, depth_maps):
 
 def forward(ops, weight_table, x, num_joints, dim, num_context_per_joint=None, alpha=0.8,
             num_blocks=4, depth_maps=16, ksize=(3, 3), export_heatmaps=False,
-            concat_pose_confidence=True, return_weights_used=False):
+            concat_pose_confidence=True, return_weights_used=False, debug=None):
     """reception.py:225-319 `build(...)` applied to batch x (N,256,256,3)."""
     if dim == 2:
         if num_context_per_joint is None:
@@ -268,7 +273,7 @@ def forward(ops, weight_table, x, num_joints, dim, num_context_per_joint=None, a
         if dim == 2:
             if num_context_per_joint is not None:
                 pose, visible, hm = pose_regression_2d_context(
-                    ops, h, num_joints, num_context_per_joint, alpha)
+                    ops, h, num_joints, num_context_per_joint, alpha, debug)
             else:
                 pose, visible, hm = pose_regression_2d(ops, h)
         else:

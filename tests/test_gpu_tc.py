@@ -1,0 +1,152 @@
+"""tcgen05 path parity (conv_tc.cu): the tensor-core kernels vs the fp64 oracle, at the layer
+shapes of the models and at ragged / tail shapes.  Each test asserts through
+dh_last_conv_path() that the tensor-core kernel really served the call."""
+import ctypes as C
+import zlib
+
+import numpy as np
+import pytest
+
+from deephar_b200 import _ffi, tc
+from oracle import ops_np
+
+from gpu_util import Dev, conv_desc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def dev(cuda):
+    return Dev(cuda)
+
+
+def _packed(dev, w_k_by_cout):
+    hi, lo, cp, kp = tc.pack_matrix(np.asarray(w_k_by_cout, np.float32))
+    th = dev.torch.from_numpy(hi.view(np.int16).copy()).cuda()
+    tl = dev.torch.from_numpy(lo.view(np.int16).copy()).cuda()
+    dev.keep += [th, tl]
+    return _ffi.dh_packed_w(th.data_ptr(), tl.data_ptr(), cp, kp)
+
+
+def _err(got, ref):
+    return float(np.abs(got.astype(np.float64) - ref).max()) / max(1.0, float(np.abs(ref).max()))
+
+
+TOL3 = 3e-5      # bf16x3 split: operand error ~2^-16, fp32 accumulate
+TOL1 = 3e-2      # plain bf16 (precision = 1)
+
+CONV_CASES = [
+    # N, H, W, Cin, Cout, size, strides, fused(pre_relu+post_bn+res)
+    (2, 12, 12, 32, 64, (1, 1), (1, 1), False),
+    (1, 13, 11, 8, 20, (3, 3), (1, 1), True),
+    (1, 9, 9, 16, 24, (5, 1), (1, 1), False),
+    (1, 9, 9, 16, 24, (1, 5), (1, 1), True),
+    (2, 32, 32, 576, 48, (1, 1), (1, 1), True),      # RegMap
+    (2, 32, 32, 48, 576, (1, 1), (1, 1), True),      # fReMap (+2 residuals)
+    (3, 16, 16, 576, 288, (1, 1), (1, 1), True),     # rBlock reduce (two MMA sub-tiles)
+    (2, 32, 32, 384, 576, (1, 1), (1, 1), True),     # stem shortcut (two N CTAs)
+    (1, 64, 64, 192, 192, (3, 3), (2, 2), True),     # stem 3x3 stride 2
+    (1, 32, 32, 32, 64, (3, 3), (1, 1), False),      # K-block straddles taps (Cin = 32)
+    (1, 7, 5, 12, 272, (1, 1), (1, 1), False),       # M tail, ragged Cout (3-D RegMap width)
+    (1, 16, 16, 64, 17, (1, 1), (1, 1), False),      # Cout = 17 (SPNet heat-maps): scalar epilogue
+]
+
+
+@pytest.mark.parametrize('case', CONV_CASES)
+@pytest.mark.parametrize('precision', [3, 1])
+def test_conv_tc(dev, case, precision):
+    n, h, w, cin, cout, size, strides, fused = case
+    rng = np.random.default_rng(zlib.crc32(repr(case).encode()))
+    x = rng.standard_normal((n, h, w, cin))
+    wt = rng.standard_normal(size + (cin, cout)) / np.sqrt(size[0] * size[1] * cin)
+    pre = post = None
+    res = []
+    xin = x
+    if fused:
+        pre = (rng.uniform(0.5, 1.5, cin), rng.standard_normal(cin) * 0.3)
+        post = (rng.uniform(0.5, 1.5, cout), rng.standard_normal(cout) * 0.3)
+        xin = np.maximum(x * pre[0] + pre[1], 0)
+    ref = ops_np.conv2d(xin, wt, strides, 'same')
+    if fused:
+        ref = ref * post[0] + post[1]
+        r0, r1 = rng.standard_normal(ref.shape), rng.standard_normal(ref.shape)
+        ref = ref + r0 + r1
+        res = [dev.view(dev.put(r0)), dev.view(dev.put(r1))]
+    out = dev.empty(*ref.shape)
+    d = conv_desc(dev, size, strides, 'same', pre_relu=fused, pre=pre, post=post, res=res, precision=precision)
+    pk = _packed(dev, wt.reshape(-1, cout))
+    xv, ov = dev.view(dev.put(x)), dev.view(out)
+    dev.call('dh_conv2d_f32', C.byref(xv), dev.put(wt).data_ptr(), C.byref(pk), C.byref(d), C.byref(ov))
+    assert dev.lib.dh_last_conv_path(dev.ctx.handle) == 1, 'tensor-core path was not taken'
+    e = _err(out.cpu().numpy(), ref)
+    assert e <= (TOL3 if precision == 3 else TOL1), e
+
+
+SEP_CASES = [
+    # N, H, W, Cin, Cout, k, mode
+    (2, 16, 16, 32, 48, 5, 'act_bn_res'),
+    (1, 8, 8, 24, 24, 3, 'plain'),                  # half-empty tile (M = 64)
+    (3, 4, 4, 64, 64, 5, 'bn_act'),                 # 4x4 maps: 8 frames per tile, tail tile
+    (2, 32, 32, 576, 576, 5, 'act_bn_res'),         # the hot layer (reception l1 / SepConv)
+    (2, 16, 16, 288, 288, 5, 'act_bn_res'),
+    (3, 8, 8, 288, 288, 5, 'act_bn_res'),
+    (2, 16, 16, 288, 576, 5, 'act_bn_res'),
+    (1, 32, 32, 384, 576, 3, 'act_bn_res'),         # stem sepconv1
+    (2, 32, 32, 288, 288, 5, 'bn_act'),             # SPNet level 0
+    (2, 16, 16, 384, 384, 5, 'bn_act'),
+    (2, 8, 8, 480, 480, 5, 'bn_act'),
+    (8, 4, 4, 576, 576, 5, 'bn_act'),
+]
+
+
+@pytest.mark.parametrize('case', SEP_CASES)
+@pytest.mark.parametrize('precision', [3, 1])
+def test_sepconv_tc(dev, case, precision):
+    n, h, w, cin, cout, k, mode = case
+    rng = np.random.default_rng(zlib.crc32(repr(case).encode()))
+    x = rng.standard_normal((n, h, w, cin))
+    dw = rng.standard_normal((k, k, cin, 1)) / k
+    pw = rng.standard_normal((1, 1, cin, cout)) / np.sqrt(cin)
+    pre = post = None
+    res = []
+    xin = x
+    if mode == 'act_bn_res':
+        xin = np.maximum(x, 0)
+        post = (rng.uniform(0.5, 1.5, cout), rng.standard_normal(cout) * 0.3)
+    elif mode == 'bn_act':
+        pre = (rng.uniform(0.5, 1.5, cin), rng.standard_normal(cin) * 0.3)
+        xin = np.maximum(x * pre[0] + pre[1], 0)
+    ref = ops_np.separable_conv2d(xin, dw, pw, (1, 1), 'same')
+    if mode == 'act_bn_res':
+        ref = ref * post[0] + post[1]
+        r0 = rng.standard_normal(ref.shape)
+        ref = ref + r0
+        res = [dev.view(dev.put(r0))]
+    out = dev.empty(*ref.shape)
+    d = conv_desc(dev, (k, k), (1, 1), 'same', pre_relu=(mode != 'plain'), pre=pre, post=post, res=res,
+                  precision=precision)
+    pk = _packed(dev, pw.reshape(cin, cout))
+    xv, ov = dev.view(dev.put(x)), dev.view(out)
+    dev.call('dh_sepconv2d_f32', C.byref(xv), dev.put(dw).data_ptr(), dev.put(pw).data_ptr(), C.byref(pk),
+             C.byref(d), C.byref(ov))
+    assert dev.lib.dh_last_conv_path(dev.ctx.handle) == 1, 'tensor-core path was not taken'
+    e = _err(out.cpu().numpy(), ref)
+    assert e <= (TOL3 if precision == 3 else TOL1), e
+
+
+def test_tc_channel_views(dev):
+    """concat / slice views through the tensor-core kernel (ld != c, channel offsets)."""
+    rng = np.random.default_rng(3)
+    big = rng.standard_normal((2, 16, 16, 96))
+    wt = rng.standard_normal((1, 1, 64, 32)) / 8.0
+    ref = ops_np.conv2d(big[..., 16:80], wt)
+    cat = dev.empty(2, 16, 16, 40)
+    cat.fill_(7.0)
+    d = conv_desc(dev, (1, 1))
+    pk = _packed(dev, wt.reshape(64, 32))
+    xv, ov = dev.view(dev.put(big), 16, 80), dev.view(cat, 4, 36)
+    dev.call('dh_conv2d_f32', C.byref(xv), dev.put(wt).data_ptr(), C.byref(pk), C.byref(d), C.byref(ov))
+    assert dev.lib.dh_last_conv_path(dev.ctx.handle) == 1
+    got = cat.cpu().numpy()
+    assert _err(got[..., 4:36], ref) <= TOL3
+    assert np.all(got[..., :4] == 7.0) and np.all(got[..., 36:] == 7.0)
