@@ -17,7 +17,7 @@ from collections import defaultdict
 
 CONV_OPS = ('conv', 'sepconv')
 DENSE_OUT_OPS = ('pose_regression_2d_context', 'pose_regression_2d', 'pose_regression_3d',
-                 'sam2d', 'kron', 'global_maxmin_softmax')
+                 'sam2d', 'kron', 'global_maxmin_softmax', 'mask_mul')
 
 
 class KOp(object):
@@ -112,29 +112,43 @@ def compile_graph(g):
             cur = r.out
         ch['end_pre_add'] = cur
         chains[n.id] = ch
-    # adds: absorbed by the last-created conv chain that ends exactly at one of its inputs
-    for n in g.nodes:
-        if n.op != 'add' or len(n.inputs) > 3:
-            continue
-        best = None
-        for t in n.inputs:
-            if t.id in out_ids or len(cons[t.id]) != 1:
-                continue
-            for cid, ch in chains.items():
-                if ch['end_pre_add'] is t:
-                    if best is None or cid > best:
-                        best = cid
-        # every residual must have the output resolution (true for keras add)
-        if best is not None:
-            chains[best]['add'] = n
-            add_claim[n.id] = best
     for cid, ch in chains.items():
-        for key in ('post_bn', 'post_relu', 'add'):
+        for key in ('post_bn', 'post_relu'):
             nd = ch[key]
             if nd:
                 fused_into[nd.id] = cid
                 ch['pos'] = max(ch['pos'], nd.id)
-                ch['end'] = nd.out
+        ch['end'] = ch['end_pre_add']
+        ch['res'] = []
+    # adds (keras `add([...])`): absorbed into the epilogue of the latest conv chain whose current
+    # end tensor feeds it -- also chained adds (residual add followed by a lateral add), as long as
+    # the epilogue carries at most two residual operands.
+    chain_end = {ch['end'].id: cid for cid, ch in chains.items()}
+    for n in g.nodes:
+        if n.op != 'add':
+            continue
+        if len(n.inputs) == 2 and any(t.node.op == 'upsample' and len(cons[t.id]) == 1 and t.id not in out_ids
+                                      for t in n.inputs):
+            continue        # UpSampling2D + add is one kernel of its own (upsample_add)
+        best = None
+        for t in n.inputs:
+            cid = chain_end.get(t.id)
+            if cid is None or t.id in out_ids or len(cons[t.id]) != 1:
+                continue
+            if len(chains[cid]['res']) + len(n.inputs) - 1 > 2:
+                continue
+            if best is None or chains[cid]['pos'] > chains[best]['pos']:
+                best = cid
+        if best is not None:
+            ch = chains[best]
+            endt = ch['end']
+            ch['res'] += [t for t in n.inputs if t is not endt]
+            add_claim[n.id] = best
+            fused_into[n.id] = best
+            del chain_end[endt.id]
+            chain_end[n.out.id] = best
+            ch['pos'] = max(ch['pos'], n.id)
+            ch['end'] = n.out
 
     # ---- phase 2: consumer-side (prologue) fusion ---------------------------------
     absorbed_edges = set()   # (producer node id, consumer node id) edges that need no materialisation
@@ -184,15 +198,19 @@ def compile_graph(g):
         return k
 
     up_fused = set()
+    sam_skip = set()
+    for n in g.nodes:           # pre-scan: (x,y)+z concats that the fused soft-argmax kernel writes directly
+        if n.op == 'depth_expect':
+            cat = sole_consumer(n.out, 'concat')
+            if cat is not None:
+                sam_skip.add(cat.id)
     for n in g.nodes:
         op = n.op
         if op == 'input':
             continue
         if op in CONV_OPS:
             ch = chains[n.id]
-            res = []
-            if ch['add']:
-                res = [t for t in ch['add'].inputs if t is not ch['end_pre_add']]
+            res = ch['res']
             attrs = dict(n.attrs)
             attrs.update({'pre_relu': ch['pre_relu'], 'pre_bn': ch['pre_bn'].attrs if ch['pre_bn'] else None,
                           'post_bn': ch['post_bn'].attrs if ch['post_bn'] else None,
@@ -227,8 +245,47 @@ def compile_graph(g):
             # decided when its consumer add is visited; emit lazily below if not fused
             emit('upsample?', [n.inputs[0]], [n.out], {'node': n.id}, n.id)
             continue
-        if op in ('slice', 'concat'):
+        if op in ('slice', 'concat', 'to_clip'):
+            if op == 'concat' and n.id in sam_skip:
+                continue
             emit(op, n.inputs, [n.out], dict(n.attrs), n.id)
+            continue
+        if op == 'softmax2d':
+            # channel_softmax_2d -> {softargmax2d, keypoint_confidence, depth expectation, kronecker
+            # product} (spnet.py:178-235): ONE kernel; the probability map is only written if the
+            # kronecker product needs it.
+            users = cons[n.out.id]
+            sa = [u for u in users if u.op == 'softargmax2d']
+            kc = [u for u in users if u.op == 'keypoint_confidence']
+            de = [u for u in users if u.op == 'depth_expect']
+            kr = [u for u in users if u.op == 'kron']
+            if len(sa) != 1 or len(kc) != 1 or len(de) > 1 or len(sa) + len(kc) + len(de) + len(kr) != len(users) \
+                    or n.out.id in out_ids:
+                raise NotImplementedError('unsupported use of channel_softmax_2d output')
+            pose_t, pos, ins = sa[0].out, max(sa[0].id, kc[0].id), [n.inputs[0]]
+            sam_skip.update([sa[0].id, kc[0].id])
+            if de:
+                cat = sole_consumer(sa[0].out, 'concat')
+                if cat is None or sole_consumer(de[0].out, 'concat') is not cat or len(cat.inputs) != 2 \
+                        or cat.inputs[0] is not sa[0].out:
+                    raise NotImplementedError('depth expectation must be concatenated right after (x, y)')
+                pose_t, pos = cat.out, max(pos, cat.id)
+                ins.append(de[0].inputs[0])
+                sam_skip.update([de[0].id, cat.id])
+            outs = [pose_t, kc[0].out] + ([n.out] if kr else [])
+            emit('sam2d', ins, outs, {'alpha': n.attrs['alpha'], 'depth': bool(de), 'prob': bool(kr)}, pos)
+            continue
+        if op in ('softargmax2d', 'keypoint_confidence', 'depth_expect'):
+            if n.id not in sam_skip and not any(c_.op == 'softmax2d' for c_ in [n.inputs[-1].node]):
+                raise NotImplementedError('%s is only supported on channel_softmax_2d outputs' % op)
+            continue
+        if op == 'global_maxmin':
+            sm = sole_consumer(n.out, 'softmax')
+            if sm is None:
+                raise NotImplementedError('global_max_min_pooling must feed Activation(softmax)')
+            emit('global_maxmin_softmax', [n.inputs[0]], [sm.out], {}, sm.id)
+            continue
+        if op == 'softmax':
             continue
         # everything else maps 1:1 onto a kernel op
         emit(op, n.inputs, n.outs, dict(n.attrs), n.id)
@@ -267,7 +324,7 @@ def compile_graph(g):
         copies = []
         for t in k.ins:
             w = written_by.get(t.id)
-            ok = (w is not None and w.kind not in ('slice', 'concat') and w.kind not in DENSE_OUT_OPS
+            ok = (w is not None and w.kind not in ('slice', 'concat', 'to_clip') and w.kind not in DENSE_OUT_OPS
                   and t.id not in placed and t.id not in out_ids)
             if ok:
                 placed[t.id] = (k.outs[0], off)
@@ -289,6 +346,9 @@ def compile_graph(g):
             if w is not None and w.kind == 'slice':
                 ps = storage_of(w.ins[0])
                 s = Storage(ps.buf, ps.c_off + w.attrs['c0'], ps.ld)
+            elif w is not None and w.kind == 'to_clip':
+                ps = storage_of(w.ins[0])        # (B*T, 1, nj, C) frames == (B, T, nj, C) clips
+                s = Storage(ps.buf, ps.c_off, ps.ld)
             else:
                 b = new_buffer(t.kind, hw_of(t), t.channels)
                 s = Storage(b, 0, t.channels)
@@ -305,7 +365,7 @@ def compile_graph(g):
             storage_of(t)
         for t in k.outs:
             storage_of(t)
-        if k.kind == 'slice':
+        if k.kind in ('slice', 'to_clip'):
             continue
         if k.kind == 'concat':
             for (t, off) in k.attrs['copies']:

@@ -206,6 +206,39 @@ extern "C" int dh_global_maxmin_softmax_f32(dh_ctx* ctx, const dh_view* x, float
     DH_LAUNCH_EPILOGUE(ctx, 1);
 }
 
+namespace {
+__global__ void __launch_bounds__(256) zeropad_kernel(const float* x, int H, int W, int C, int ldx, int pt, int pl,
+                                                      float* out, int Ho, int Wo, int ldo, int64_t total) {
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        int c = (int)(idx % C);
+        int64_t m = idx / C;
+        int ox = (int)(m % Wo);
+        int64_t t = m / Wo;
+        int oy = (int)(t % Ho);
+        int n = (int)(t / Ho);
+        int iy = oy - pt, ix = ox - pl;
+        float v = 0.f;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(x + ((size_t)(n * H + iy) * W + ix) * ldx + c);
+        out[(size_t)m * ldo + c] = v;
+    }
+}
+}  // namespace
+
+// keras ZeroPadding2D(((top, bottom), (left, right))) (spnet.py:124-125,131-132)
+extern "C" int dh_zeropad2d_f32(dh_ctx* ctx, const dh_view* x, int top, int left, const dh_view* out,
+                                void* stream) {
+    DH_CHECK_ARG(ctx && x && out && x->p && out->p, "dh_zeropad2d_f32: NULL argument");
+    DH_CHECK_ARG(out->n == x->n && out->c == x->c && out->h >= x->h + top && out->w >= x->w + left && top >= 0 &&
+                     left >= 0,
+                 "dh_zeropad2d_f32: output (%d,%d) too small for input (%d,%d) + pad (%d,%d)", out->h, out->w, x->h,
+                 x->w, top, left);
+    int64_t total = (int64_t)out->n * out->h * out->w * out->c;
+    zeropad_kernel<<<grid_for(total, ctx->num_sms), 256, 0, (cudaStream_t)stream>>>(
+        x->p, x->h, x->w, x->c, x->ld, top, left, out->p, out->h, out->w, out->ld, total);
+    DH_LAUNCH_EPILOGUE(ctx, 1);
+}
+
 extern "C" int dh_mask_mul_f32(dh_ctx* ctx, const float* p, const float* c, int64_t rows, int dim,
                                float* out, void* stream) {
     DH_CHECK_ARG(ctx && p && c && out, "dh_mask_mul_f32: NULL argument");

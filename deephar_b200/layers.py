@@ -244,3 +244,32 @@ def kronecker_prod(h, f, name='Kronecker_prod'):
     """layers.py:478-508 for clip tensors: (..,H,W,nj) x (..,H,W,F) -> per frame (nj, F)."""
     assert h.shape[:2] == f.shape[:2]
     return h.g.op('kron', [h, f], (1, h.channels, f.channels), {'name': name})
+
+
+# ---------------------------------------------------------------------------
+# SPNet-only helpers (spnet.py:178-235, 98-111)
+# ---------------------------------------------------------------------------
+def depth_expectation(d_logits, h, name=None):
+    """spnet.py:201-205: d = sigmoid(d_logits); z = sum_{h,w}(d * h); expand_dims -> (nj, 1).
+    Four parameter-free reference layers (Activation, multiply, two Lambdas) as one graph op."""
+    assert d_logits.shape == h.shape
+    return h.g.op('depth_expect', [d_logits, h], (1, h.channels, 1), {'name': name})
+
+
+def frames_to_clip(x):
+    """(B*T frames, 1, nj, C) -> (B clips, T, nj, C).  The reference's tensors are (B,T,nj,C) once
+    TimeDistributed unfolds; with clip-major frame order this is a free reinterpretation."""
+    t = x.g.frames_per_clip
+    assert x.kind == 'frame' and x.shape[0] == 1
+    return x.g.op('to_clip', [x], (t, x.shape[1], x.shape[2]), {}, kind='clip')
+
+
+def mask_multiply(p, c):
+    """spnet.py:110-111: mask = tile(c, dim); x = p * mask."""
+    assert p.shape[:2] == c.shape[:2] and c.shape[2] == 1
+    return p.g.op('mask_mul', [p, c], p.shape, {})
+
+
+def softmax_lastaxis(x, name=None):
+    """Activation('softmax') on (B, n_act) logits (spnet.py:66-68)."""
+    return x.g.op('softmax', [x], x.shape, {'name': name})

@@ -202,8 +202,10 @@ class Model(object):
             lead = (n // self.graph.frames_per_clip, self.graph.frames_per_clip)
         elif t.kind == 'frame' and self.graph.frames_per_clip > 1:
             lead = (None, self.graph.frames_per_clip)
+        if h == 1 and w == 1:
+            return lead + (c,)
         if h == 1:
-            return lead + ((w, c) if w > 1 or c > 1 else (c,))
+            return lead + (w, c)
         return lead + (h, w, c)
 
     def _items(self, kind, n_frames):
@@ -310,6 +312,27 @@ class Model(object):
                 a = k.attrs
                 args = (lib.dh_softargmax3d_f32, ctxh, C.byref(view(k.ins[0])), a['num_joints'],
                         a['depth_maps'], dense_ptr(k.outs[0]), dense_ptr(k.outs[1]))
+            elif kd == 'sam2d':
+                a = k.attrs
+                dv = C.byref(view(k.ins[1])) if a['depth'] else nullv
+                pv = C.byref(view(k.outs[2])) if a['prob'] else nullv
+                args = (lib.dh_softargmax2d_f32, ctxh, C.byref(view(k.ins[0])), dv, C.c_float(a['alpha']), 1,
+                        dense_ptr(k.outs[0]), dense_ptr(k.outs[1]), pv)
+            elif kd == 'kron':
+                args = (lib.dh_kron_pool_f32, ctxh, C.byref(view(k.ins[0])), C.byref(view(k.ins[1])),
+                        dense_ptr(k.outs[0]))
+            elif kd == 'mask_mul':
+                t = k.ins[0]
+                rows = self._items(t.kind, n_frames) * t.shape[0] * t.shape[1]
+                args = (lib.dh_mask_mul_f32, ctxh, dense_ptr(k.ins[0]), dense_ptr(k.ins[1]), rows, t.shape[2],
+                        dense_ptr(k.outs[0]))
+            elif kd == 'zeropad':
+                (pt, pb), (pl, pr) = k.attrs['pads']
+                args = (lib.dh_zeropad2d_f32, ctxh, C.byref(view(k.ins[0])), pt, pl, C.byref(view(k.outs[0])))
+            elif kd == 'maxminpool':
+                args = (lib.dh_maxmin_pool2d_f32, ctxh, C.byref(view(k.ins[0])), C.byref(view(k.outs[0])))
+            elif kd == 'global_maxmin_softmax':
+                args = (lib.dh_global_maxmin_softmax_f32, ctxh, C.byref(view(k.ins[0])), dense_ptr(k.outs[0]))
             else:
                 raise NotImplementedError('kernel op %s' % kd)
             b.calls.append((kd,) + args)
@@ -392,6 +415,12 @@ class Model(object):
         outs = [r.numpy() for r in res]
         return outs[0] if len(outs) == 1 else outs
 
+    def output_subset(self, indices, name=None):
+        """A keras-`Model(full.input, full.outputs[a:b])`-like view (spnet.split_model): shares the
+        compiled network, weights and device buffers with this model and returns only the
+        selected outputs."""
+        return _OutputSubset(self, list(indices), name)
+
     def math_mode(self):
         """Arithmetic the convolutions run in (bench.py `dtype`)."""
         if self.use_tensor_cores and self._uses_tc():
@@ -443,3 +472,38 @@ class Model(object):
         for call in b.calls:
             n += 2 if (call[0] == 'sepconv' and not self.use_tensor_cores) else 1
         return n
+
+
+class _OutputSubset(object):
+    """Result of spnet.split_model: same network, subset of the outputs (spnet.py:443-446)."""
+
+    def __init__(self, full, indices, name):
+        self.full = full
+        self.indices = indices
+        self.name = name or full.name
+
+    @property
+    def outputs(self):
+        return [self.full.outputs[i] for i in self.indices]
+
+    @property
+    def input_shape(self):
+        return self.full.input_shape
+
+    def get_input_shape_at(self, i):
+        return self.full.get_input_shape_at(i)
+
+    @property
+    def output_shape(self):
+        shp = self.full.output_shape
+        return [shp[i] for i in self.indices]
+
+    def predict(self, x, batch_size=32, verbose=0):
+        outs = self.full.predict(x, batch_size=batch_size, verbose=verbose)
+        if not isinstance(outs, list):
+            outs = [outs]
+        sel = [outs[i] for i in self.indices]
+        return sel[0] if len(sel) == 1 else sel
+
+    def load_weights(self, path, by_name=False):
+        return self.full.load_weights(path, by_name=by_name)

@@ -142,6 +142,8 @@ int dh_softargmax3d_f32(dh_ctx* ctx, const dh_view* h, int nj, int depth_maps,
 int dh_kron_pool_f32(dh_ctx* ctx, const dh_view* p, const dh_view* z, float* out, void* stream);
 
 /* --- small action-head ops (spnet.py:51-148) ------------------------------ */
+/* keras ZeroPadding2D(((top,bottom),(left,right))) (spnet.py:124-125,131-132): out is the padded view */
+int dh_zeropad2d_f32(dh_ctx* ctx, const dh_view* x, int top, int left, const dh_view* out, void* stream);
 /* layers.py:411-425 max_min_pooling 2x2 stride 2 'same' */
 int dh_maxmin_pool2d_f32(dh_ctx* ctx, const dh_view* x, const dh_view* out, void* stream);
 /* layers.py:428-442 + Activation('softmax'): out (B, C) */

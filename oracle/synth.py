@@ -18,7 +18,7 @@ import zlib
 import numpy as np
 
 HEAD_STD = 3.0
-HEAD_MARKERS = ('RegMap', '_heatmaps_conv1', '_depthmaps_conv1')
+HEAD_MARKERS = ('RegMap', '_heatmaps_conv1', '_depthmaps_conv1', '_pred_conv2h')
 
 
 def is_head_kernel(name):
