@@ -182,7 +182,9 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--micro-batch', type=int, default=32, help='frames per forward (L2 residency knob)')
+    ap.add_argument('--micro-batch', type=int, default=128, help='frames per forward call')
+    ap.add_argument('--workload', default='reception2d', choices=['reception2d', 'spnet_penn', 'spnet_ntu'],
+                    help='reception2d = BASELINE configs[1] model (headline); spnet_* = configs[3]/[4] models')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--precision', type=int, default=3)
     args = ap.parse_args()
@@ -201,26 +203,42 @@ def main():
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
 
-    from deephar_b200 import reception
     peaks = measured_peaks()
-    model = reception.build((256, 256, 3), **MODEL_KW).init_synthetic_weights(1234)
-    model.precision = args.precision
     n_frames = CLIPS * FRAMES
     mb = args.micro_batch
     assert n_frames % mb == 0
+    if args.workload == 'reception2d':
+        from deephar_b200 import reception
+        model = reception.build((256, 256, 3), **MODEL_KW).init_synthetic_weights(1234)
+        in_shape, step_items, wl_name = (n_frames, 256, 256, 3), mb, \
+            'reception2d_8blk_k5_j16 (BASELINE configs[1] model) x 32 clips x 16 frames'
+    else:
+        from deephar_b200 import spnet
+        from deephar_b200.config import ModelConfig, pa16j2d, pa17j3d
+        if args.workload == 'spnet_penn':
+            cfg = ModelConfig((FRAMES, 256, 256, 3), pa16j2d, num_actions=[15], num_pyramids=6,
+                              action_pyramids=[5, 6], num_levels=4, pose_replica=True, num_pose_features=160,
+                              num_visual_features=160)
+            wl_name = 'spnet PennAction multitask (BASELINE configs[3] model) x 32 clips x 16 frames'
+        else:
+            cfg = ModelConfig((FRAMES, 256, 256, 3), pa17j3d, num_actions=[60], num_pyramids=2,
+                              action_pyramids=[1, 2], num_levels=4, num_pose_features=192, num_visual_features=192)
+            wl_name = 'spnet NTU 3D multitask (BASELINE configs[4] model) x 32 clips x 16 frames'
+        model = spnet.build(cfg).init_synthetic_weights(1234)
+        assert mb % FRAMES == 0
+        in_shape, step_items = (CLIPS, FRAMES, 256, 256, 3), mb // FRAMES
+    model.precision = args.precision
 
     # synthetic frames, uniform [-1,1], pinned host memory (e2e source) + a device copy (value)
     gen = torch.Generator().manual_seed(rank)
-    x_host = torch.empty(n_frames, 256, 256, 3, dtype=torch.float32).pin_memory()
+    x_host = torch.empty(*in_shape, dtype=torch.float32).pin_memory()
     x_host.uniform_(-1.0, 1.0, generator=gen)
     x_dev = x_host.cuda()
-    n_out = len(model.outputs)
-    gather = [torch.empty(world, n_frames, 16, 3, device='cuda')] if world > 1 else None
 
     def step_device():
         last = None
-        for i in range(0, n_frames, mb):
-            last = model.forward_device(x_dev[i:i + mb])
+        for i in range(0, in_shape[0], step_items):
+            last = model.forward_device(x_dev[i:i + step_items])
         return last
 
     def barrier():
@@ -229,13 +247,11 @@ def main():
         torch.cuda.synchronize()
 
     def gather_outputs(outs):
-        # final exchange of the data-parallel path: all-gather of the last block's (pose, vis)
-        if world > 1:
-            local_out = torch.cat([outs[-2], outs[-1]], dim=-1).contiguous()
-            buf = torch.empty(world, *local_out.shape, device='cuda')
-            dist.all_gather_into_tensor(buf, local_out)
-            return buf
-        return outs[-1]
+        # the one exchange step of the data-parallel path: all-gather of the final outputs
+        # -- reception: last block's (pose, vis); SPNet: last action probabilities (B_local, n_act)
+        from deephar_b200.dist import gather_outputs as dh_gather
+        local_out = (torch.cat([outs[-2], outs[-1]], dim=-1) if args.workload == 'reception2d' else outs[-1])
+        return dh_gather(local_out.contiguous(), world)
 
     for _ in range(args.warmup):
         gather_outputs(step_device())
@@ -262,11 +278,11 @@ def main():
     # ---- e2e: public API, pinned host input, H2D + D2H inside the timed region ----
     x_np = x_host.numpy()
     for _ in range(2):
-        model.predict(x_np[:2 * mb], batch_size=mb)
+        model.predict(x_np[:2 * step_items], batch_size=step_items)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        outs = model.predict(x_np, batch_size=mb)
+        outs = model.predict(x_np, batch_size=step_items)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     t = torch.tensor([dt], device='cuda')
@@ -276,7 +292,7 @@ def main():
     d2h = sum(int(np.prod(o.shape)) * 4 for o in outs)
 
     # ---- per-kernel profile (CUDA events around every launch of one extra step) ----
-    prof = model.profile(x_dev[:mb])
+    prof = model.profile(x_dev[:step_items])
     conv_flops = model.conv_flops_per_frame()
     top = max(prof.values(), key=lambda r: r['ms'])
     total_ms = sum(r['ms'] for r in prof.values())
@@ -292,7 +308,7 @@ def main():
         'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': model.math_mode(), 'data': 'synthetic',
-        'config': {'workload': 'reception2d_8blk_k5_j16 (BASELINE configs[1] model) x 32 clips x 16 frames',
+        'config': {'workload': wl_name,
                    'global_batch_frames': world * n_frames, 'frames_per_gpu': n_frames, 'micro_batch': mb,
                    'parallelism': 'dp%d' % world,
                    'l2': 'inputs 403 MB per step > 126 MB L2; no flush needed'},

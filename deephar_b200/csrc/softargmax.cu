@@ -380,6 +380,8 @@ extern "C" int dh_softargmax2d_f32(dh_ctx* ctx, const dh_view* h, const dh_view*
         p.prob = prob_out->p; p.ldp = prob_out->ld;
     }
     p.nj = 0; p.n_ctx = 0; p.alpha_mix = 0.f;
+    if (dh_sam_stream_supported(h, conf_on_prob, alpha, p.d != nullptr, p.prob != nullptr))
+        return dh_sam_stream_launch(ctx, h, 0, 0, 0.f, out_pose, out_conf, stream);
     return launch_sam(ctx, p, stream, "dh_softargmax2d_f32");
 }
 

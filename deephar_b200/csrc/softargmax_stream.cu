@@ -1,12 +1,261 @@
-// Streaming soft-argmax for large dense heat-maps (placeholder until the TMA-bulk pipeline lands).
+// Streaming soft-argmax for large dense heat-maps (the 32x32x48 ReceptionNet maps: 196 608 B per
+// frame per block) -- the kernel behind the "softargmax HBM GB/s" figure.
+//
+// replaces the same reference layers as softargmax.cu (channel_softmax_2d + the two grid
+// SeparableConv2D + joint probability on the raw maps + context aggregation:
+// activations.py:3-16, layers.py:160-200, blocks.py:217-343, reception.py:167-182).
+//
+// HBM-bound design (B200: ~23 B/clk/SM): persistent CTAs (one per SM) loop over frames; a
+// producer thread streams each frame through a ring of shared-memory stages with 1-D TMA bulk
+// copies (cp.async.bulk + mbarrier complete_tx: ~150 KB in flight per SM, no registers held);
+// 12 consumer warps own (column, channel-quad) pairs and keep ONLINE softmax statistics in
+// registers (running max, sum, sum*y; sum*x follows from the fixed column), plus the running
+// max of the 2x2 window sums of the raw map.  Nothing but 16 x 3 floats per frame is written.
+#include <float.h>
 #include "common.cuh"
-bool dh_sam_stream_supported(const dh_view* h, int conf_on_prob, float alpha, bool has_d, bool has_prob) {
-    (void)h; (void)conf_on_prob; (void)alpha; (void)has_d; (void)has_prob;
-    return false;
+
+namespace sstream {
+
+constexpr int STAGES = 6;
+constexpr int ROWS_PER_CHUNK = 4;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
-int dh_sam_stream_launch(dh_ctx* ctx, const dh_view* h, int nj, int n_ctx, float alpha_mix,
-                         float* out_pose, float* out_conf, void* stream) {
-    (void)ctx; (void)h; (void)nj; (void)n_ctx; (void)alpha_mix; (void)out_pose; (void)out_conf; (void)stream;
-    dh_set_error("dh_sam_stream_launch: not built");
-    return -1;
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"(bar), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+struct Params {
+    const float* h;
+    int N, H, W, C;
+    int nj, n_ctx;          // n_ctx > 0: context aggregation; else plain (pose (N,C,2), conf (N,C,1))
+    float alpha_mix;
+    float* out_pose;
+    float* out_conf;
+    int chunks_per_frame;
+    int chunk_floats;       // ROWS_PER_CHUNK * W * C
+};
+
+// consumer threads: NCONS = W * C/4, thread -> (column c = t / Q, channel quad q = t % Q)
+__global__ void __launch_bounds__(512, 1) sam_stream_kernel(Params p) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    const int Q = p.C >> 2;
+    const int NCONS = p.W * Q;
+    const int tid = threadIdx.x;
+    float* ring = reinterpret_cast<float*>(smem_raw);
+    float* s_red = ring + (size_t)STAGES * p.chunk_floats;           // [4][W][C] : m, s, sy, wmax
+    float* s_res = s_red + 4 * p.W * p.C;                            // [3][C]    : x, y, conf
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_res + 3 * p.C + ((3 * p.C) & 1));
+    const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + STAGES);
+    const int ncons_warps = (NCONS + 31) >> 5;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, ncons_warps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int frames_mine = (p.N - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int total_chunks = frames_mine * p.chunks_per_frame;
+    const uint32_t chunk_bytes = (uint32_t)p.chunk_floats * 4u;
+
+    if (tid >= NCONS) {
+        // ===================== producer (one thread of the last warp) =====================
+        if (tid == (ncons_warps << 5)) {
+            for (int i = 0; i < total_chunks; ++i) {
+                const int s = i % STAGES;
+                const uint32_t it = (uint32_t)(i / STAGES);
+                mbar_wait(bar_empty + 8 * s, (it & 1) ^ 1);
+                const int f = blockIdx.x + (i / p.chunks_per_frame) * gridDim.x;
+                const int ck = i % p.chunks_per_frame;
+                const float* src = p.h + ((size_t)f * p.chunks_per_frame + ck) * p.chunk_floats;
+                mbar_expect_tx(bar_full + 8 * s, chunk_bytes);
+                bulk_g2s(smem_u32(ring + (size_t)s * p.chunk_floats), src, chunk_bytes, bar_full + 8 * s);
+            }
+        }
+        return;
+    }
+
+    // ===================== consumers =====================
+    const int c = tid / Q, q = tid - c * Q;
+    const int lane = tid & 31;
+    const bool has_right = c + 1 < p.W;
+    const float gx = (p.W > 1) ? (c == p.W - 1 ? 1.0f : (float)(c * (1.0 / (double)(p.W - 1)))) : 0.f;
+    const double ystep = p.H > 1 ? 1.0 / (double)(p.H - 1) : 0.0;
+    int chunk_idx = 0;
+    for (int fi = 0; fi < frames_mine; ++fi) {
+        const int f = blockIdx.x + fi * gridDim.x;
+        float m[4] = {-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
+        float s[4] = {0.f, 0.f, 0.f, 0.f}, sy[4] = {0.f, 0.f, 0.f, 0.f};
+        float wm[4] = {-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
+        float4 pv = make_float4(0.f, 0.f, 0.f, 0.f), pr = make_float4(0.f, 0.f, 0.f, 0.f);   // previous row (own, right)
+        for (int ck = 0; ck < p.chunks_per_frame; ++ck, ++chunk_idx) {
+            const int st = chunk_idx % STAGES;
+            const uint32_t it = (uint32_t)(chunk_idx / STAGES);
+            mbar_wait(bar_full + 8 * st, it & 1);
+            const float* base = ring + (size_t)st * p.chunk_floats + (size_t)c * p.C + q * 4;
+            float4 v[ROWS_PER_CHUNK], vr[ROWS_PER_CHUNK];
+#pragma unroll
+            for (int r = 0; r < ROWS_PER_CHUNK; ++r) {
+                v[r] = *reinterpret_cast<const float4*>(base + (size_t)r * p.W * p.C);
+                vr[r] = has_right ? *reinterpret_cast<const float4*>(base + (size_t)r * p.W * p.C + p.C)
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_empty + 8 * st);      // this warp is done with the stage
+            // chunk maxima -> one rescale per chunk
+            float cm[4] = {v[0].x, v[0].y, v[0].z, v[0].w};
+#pragma unroll
+            for (int r = 1; r < ROWS_PER_CHUNK; ++r) {
+                cm[0] = fmaxf(cm[0], v[r].x); cm[1] = fmaxf(cm[1], v[r].y);
+                cm[2] = fmaxf(cm[2], v[r].z); cm[3] = fmaxf(cm[3], v[r].w);
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                if (cm[e] > m[e]) {
+                    const float sc = __expf(m[e] - cm[e]);
+                    s[e] *= sc;
+                    sy[e] *= sc;
+                    m[e] = cm[e];
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < ROWS_PER_CHUNK; ++r) {
+                const int row = ck * ROWS_PER_CHUNK + r;
+                const float gy = (p.H > 1 && row == p.H - 1) ? 1.0f : (float)(row * ystep);
+                const float e0 = __expf(v[r].x - m[0]), e1 = __expf(v[r].y - m[1]);
+                const float e2 = __expf(v[r].z - m[2]), e3 = __expf(v[r].w - m[3]);
+                s[0] += e0; s[1] += e1; s[2] += e2; s[3] += e3;
+                sy[0] = fmaf(e0, gy, sy[0]); sy[1] = fmaf(e1, gy, sy[1]);
+                sy[2] = fmaf(e2, gy, sy[2]); sy[3] = fmaf(e3, gy, sy[3]);
+                if (has_right && row > 0) {       // 2x2 window with top-left corner (row-1, c), raw values
+                    wm[0] = fmaxf(wm[0], (pv.x + pr.x) + (v[r].x + vr[r].x));
+                    wm[1] = fmaxf(wm[1], (pv.y + pr.y) + (v[r].y + vr[r].y));
+                    wm[2] = fmaxf(wm[2], (pv.z + pr.z) + (v[r].z + vr[r].z));
+                    wm[3] = fmaxf(wm[3], (pv.w + pr.w) + (v[r].w + vr[r].w));
+                }
+                pv = v[r];
+                pr = vr[r];
+            }
+        }
+        // ---- combine the W columns of every channel ----
+        const int WC = p.W * p.C;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int idx = c * p.C + q * 4 + e;
+            s_red[0 * WC + idx] = m[e];
+            s_red[1 * WC + idx] = s[e];
+            s_red[2 * WC + idx] = sy[e];
+            s_red[3 * WC + idx] = wm[e];
+        }
+        asm volatile("bar.sync 1, %0;" ::"r"(ncons_warps << 5) : "memory");
+        if (tid < p.C) {
+            float M = -FLT_MAX, Wm = -FLT_MAX;
+            for (int cc = 0; cc < p.W; ++cc) {
+                M = fmaxf(M, s_red[0 * WC + cc * p.C + tid]);
+                Wm = fmaxf(Wm, s_red[3 * WC + cc * p.C + tid]);
+            }
+            float S = 0.f, SX = 0.f, SY = 0.f;
+            const double xstep = p.W > 1 ? 1.0 / (double)(p.W - 1) : 0.0;
+            for (int cc = 0; cc < p.W; ++cc) {
+                const float sc = __expf(s_red[0 * WC + cc * p.C + tid] - M);
+                const float sv = s_red[1 * WC + cc * p.C + tid] * sc;
+                const float gxc = (p.W > 1 && cc == p.W - 1) ? 1.0f : (float)(cc * xstep);
+                S += sv;
+                SX = fmaf(sv, gxc, SX);
+                SY = fmaf(s_red[2 * WC + cc * p.C + tid], sc, SY);
+            }
+            const float den = fmaxf(S, 1e-7f);
+            s_res[0 * p.C + tid] = SX / den;
+            s_res[1 * p.C + tid] = SY / den;
+            s_res[2 * p.C + tid] = Wm;
+        }
+        asm volatile("bar.sync 1, %0;" ::"r"(ncons_warps << 5) : "memory");
+        if (p.n_ctx > 0) {
+            if (tid < p.nj) {
+                float pcs = 0.f, px = 0.f, py = 0.f;
+                for (int i = 0; i < p.n_ctx; ++i) {
+                    const int cc = p.nj + tid * p.n_ctx + i;
+                    const float pc = s_res[2 * p.C + cc];
+                    pcs += pc;
+                    px = fmaf(s_res[0 * p.C + cc], pc, px);
+                    py = fmaf(s_res[1 * p.C + cc], pc, py);
+                }
+                const float a = p.alpha_mix;
+                p.out_pose[((size_t)f * p.nj + tid) * 2 + 0] = a * s_res[0 * p.C + tid] + (1.f - a) * (px / pcs);
+                p.out_pose[((size_t)f * p.nj + tid) * 2 + 1] = a * s_res[1 * p.C + tid] + (1.f - a) * (py / pcs);
+                p.out_conf[(size_t)f * p.nj + tid] = s_res[2 * p.C + tid];
+            }
+        } else if (tid < p.C) {
+            p.out_pose[((size_t)f * p.C + tid) * 2 + 0] = s_res[0 * p.C + tid];
+            p.out_pose[((size_t)f * p.C + tid) * 2 + 1] = s_res[1 * p.C + tid];
+            p.out_conf[(size_t)f * p.C + tid] = s_res[2 * p.C + tid];
+        }
+        // s_red / s_res are rewritten only after the next frame's first bar.sync pair -> safe
+    }
+    (void)gx;
+}
+
+}  // namespace sstream
+
+bool dh_sam_stream_supported(const dh_view* h, int conf_on_prob, float alpha, bool has_d, bool has_prob) {
+    if (conf_on_prob != 0 || alpha != 1.0f || has_d || has_prob) return false;
+    if (h->ld != h->c || (h->c & 3)) return false;
+    if ((reinterpret_cast<uintptr_t>(h->p) & 15) != 0) return false;
+    if (h->h % sstream::ROWS_PER_CHUNK != 0 || h->h < 2 || h->w < 2) return false;
+    const int ncons = h->w * (h->c >> 2);
+    if (ncons > 480 || ncons < 64 || (ncons & 31)) return false;
+    const size_t chunk_bytes = (size_t)sstream::ROWS_PER_CHUNK * h->w * h->c * 4;
+    if (chunk_bytes % 16 != 0) return false;
+    const size_t smem = sstream::STAGES * chunk_bytes + (size_t)(4 * h->w * h->c + 3 * h->c + 2) * 4 + 2 * sstream::STAGES * 8 + 128;
+    if (smem > 227 * 1024) return false;
+    if ((size_t)h->h * h->w * h->c * 4 < 64 * 1024) return false;    // small maps: the staged kernel is fine
+    return true;
+}
+
+int dh_sam_stream_launch(dh_ctx* ctx, const dh_view* h, int nj, int n_ctx, float alpha_mix, float* out_pose,
+                         float* out_conf, void* stream) {
+    using namespace sstream;
+    Params p;
+    p.h = h->p; p.N = h->n; p.H = h->h; p.W = h->w; p.C = h->c;
+    p.nj = nj; p.n_ctx = n_ctx; p.alpha_mix = alpha_mix;
+    p.out_pose = out_pose; p.out_conf = out_conf;
+    p.chunks_per_frame = h->h / ROWS_PER_CHUNK;
+    p.chunk_floats = ROWS_PER_CHUNK * h->w * h->c;
+    const int ncons = h->w * (h->c >> 2);
+    const int threads = ((ncons + 31) / 32) * 32 + 32;
+    const size_t smem = (size_t)STAGES * p.chunk_floats * 4 + (size_t)(4 * h->w * h->c + 3 * h->c + 2) * 4 +
+                        2 * STAGES * 8 + 128;
+    cudaError_t e = cudaFuncSetAttribute(sam_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+        dh_set_error("dh_sam_stream_launch: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        return (int)e;
+    }
+    int grid = h->n < ctx->num_sms ? h->n : ctx->num_sms;
+    sam_stream_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(p);
+    DH_LAUNCH_EPILOGUE(ctx, 1);
 }
