@@ -241,11 +241,11 @@ __device__ __forceinline__ void produce_sep(const TcParams& P, int kb, uint8_t* 
     const bool cval = ch < c.Cin;
     const bool tile_valid = (m0 + strip * 4 * W) < c.M;   // whole strips are valid or not (M % (4W) == 0)
 
-    float acc[4][4][2];
+    float2 acc[4][4];          // (2 channels) x 4 rows x 4 cols -- updated with packed FFMA2
 #pragma unroll
     for (int o = 0; o < 4; ++o)
 #pragma unroll
-        for (int q = 0; q < 4; ++q) acc[o][q][0] = acc[o][q][1] = 0.f;
+        for (int q = 0; q < 4; ++q) acc[o][q] = make_float2(0.f, 0.f);
 
     if (cval && tile_valid) {
         const float* xb = c.x + (size_t)n * H * W * c.ldx + ch;
@@ -289,8 +289,7 @@ __device__ __forceinline__ void produce_sep(const TcParams& P, int kb, uint8_t* 
             for (int q = 0; q < NR; ++q) {
                 float2 v = buf[r % 3][q];
                 if (rowok && ((colmask >> q) & 1u)) {      // zero padding is applied AFTER BN/ReLU
-                    v.x = fmaf(v.x, ps.x, pb.x);
-                    v.y = fmaf(v.y, ps.y, pb.y);
+                    v = __ffma2_rn(v, ps, pb);
                     if (c.pre_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); }
                 }
                 in[q] = v;
@@ -302,10 +301,7 @@ __device__ __forceinline__ void produce_sep(const TcParams& P, int kb, uint8_t* 
 #pragma unroll
                     for (int q = 0; q < 4; ++q)
 #pragma unroll
-                        for (int kx = 0; kx < KS; ++kx) {
-                            acc[o][q][0] = fmaf(wt[ky][kx].x, in[q + kx].x, acc[o][q][0]);
-                            acc[o][q][1] = fmaf(wt[ky][kx].y, in[q + kx].y, acc[o][q][1]);
-                        }
+                        for (int kx = 0; kx < KS; ++kx) acc[o][q] = __ffma2_rn(wt[ky][kx], in[q + kx], acc[o][q]);
                 }
             }
         }
@@ -317,7 +313,7 @@ __device__ __forceinline__ void produce_sep(const TcParams& P, int kb, uint8_t* 
         for (int q = 0; q < 4; ++q) {
             const int row = (strip * 4 + o) * W + x0 + q;   // row inside the 128-pixel tile
             uint32_t hi, lo;
-            split2(acc[o][q][0], acc[o][q][1], hi, lo);
+            split2(acc[o][q].x, acc[o][q].y, hi, lo);
             const uint32_t off = swz(row, cg * 2);
             *reinterpret_cast<uint32_t*>(a_hi + off) = hi;
             if (want_lo) *reinterpret_cast<uint32_t*>(a_lo + off) = lo;
@@ -592,6 +588,7 @@ bool dh_tc_supported(const ConvParams& p, const dh_packed_w* packed, bool separa
     if (packed->k != dh_tc_k_pad(K) || packed->cout_pad != dh_tc_cout_pad(p.Cout)) return false;
     if (p.pre_scale && ((reinterpret_cast<uintptr_t>(p.pre_scale) & 15) || (reinterpret_cast<uintptr_t>(p.pre_shift) & 15)))
         return false;
+    if ((int64_t)p.N * p.H * p.W * p.ldx >= (1ll << 31)) return false;    // int32 pixel*ld products in the producers
     if (separable) {
         if (!(p.kh == p.kw && (p.kh == 3 || p.kh == 5))) return false;
         if (p.sh != 1 || p.sw != 1) return false;
