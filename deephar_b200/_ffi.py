@@ -44,6 +44,7 @@ SIGNATURES = {
     'dh_version': (C.c_int, []),
     'dh_launch_count': (C.c_int64, [C.c_void_p, C.c_int]),
     'dh_set_workspace': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
+    'dh_set_option': (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     'dh_tc_cout_pad': (C.c_int, [C.c_int]),
     'dh_tc_k_pad': (C.c_int, [C.c_int]),
     'dh_last_conv_path': (C.c_int, [C.c_void_p]),

@@ -12,6 +12,7 @@ struct dh_ctx {
     void* workspace;
     int64_t workspace_bytes;
     int last_conv_path;   // 0 = CUDA-core kernels, 1 = tcgen05 kernel (test / bench introspection)
+    int share_a;          // 1 = cluster pairs share the separable A tile (default), 0 = independent CTAs
 };
 
 void dh_set_error(const char* fmt, ...);

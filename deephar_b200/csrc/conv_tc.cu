@@ -107,6 +107,32 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// ---- 2-CTA cluster helpers (A-tile sharing between the two N-half CTAs of one pixel tile) ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t mapa_peer(uint32_t local_addr, uint32_t peer) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(peer));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// local shared memory -> peer CTA's shared memory, completion counted on the PEER's mbarrier
+__device__ __forceinline__ void bulk_s2peer(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t bar_cluster) {
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_cluster), "r"(src_cta), "r"(bytes), "r"(bar_cluster)
+                 : "memory");
+}
+// tcgen05.commit arriving on the same mbarrier offset in both CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3)
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
     uint32_t r[16];
     asm volatile(
@@ -323,7 +349,11 @@ __device__ __forceinline__ void produce_sep(const TcParams& P, int kb, uint8_t* 
 // ---------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------
-template <int MODE>   // 0 dense/1x1, 3 separable 3x3, 5 separable 5x5
+// SHARE: the two CTAs (N halves) of one 128-pixel tile form a cluster (1,2,1) and split the A
+// production: CTA r produces the K-blocks with kb % 2 == r (stages == 2, so stage r is "its"
+// stage), pushes the finished tile to the peer with a DSMEM bulk copy that completes on the
+// peer's full[r] barrier, and every MMA commit is multicast to both CTAs' empty barriers.
+template <int MODE, bool SHARE>   // MODE: 0 dense/1x1, 3 separable 3x3, 5 separable 5x5
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUtensorMap map_hi,
                const __grid_constant__ CUtensorMap map_lo) {
@@ -346,23 +376,31 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
         tma_prefetch_desc(&map_hi);
         if (want_lo) tma_prefetch_desc(&map_lo);
         for (int s = 0; s < P.stages; ++s) {
-            mbar_init(bar_full0 + 8 * s, NPROD + 1);
-            mbar_init(bar_empty0 + 8 * s, 1);
+            if (SHARE) {
+                // own stage: TMA-thread arrive + elected producer arrive; peer stage: TMA-thread arrive
+                // (the A tile arrives as transaction bytes of the peer's bulk copy)
+                mbar_init(bar_full0 + 8 * s, (uint32_t)s == cluster_ctarank() ? 2u : 1u);
+                mbar_init(bar_empty0 + 8 * s, 2);
+            } else {
+                mbar_init(bar_full0 + 8 * s, NPROD + 1);
+                mbar_init(bar_empty0 + 8 * s, 1);
+            }
         }
         mbar_init(bar_tmem, 1);
         fence_barrier_init();
     }
     if (warp == WARP_MMA) tmem_alloc(smem_u32(tmem_slot), (uint32_t)P.tmem_cols);
     tc_fence_before();
-    __syncthreads();
+    if (SHARE) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
+    const uint32_t my_rank = SHARE ? cluster_ctarank() : 0u;
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp < 8) {
         // ======================= A producers =======================
         DenseRows rows;
         if (MODE == 0) dense_rows_init(P.c, m0, tid, rows);
-        for (int kb = 0; kb < P.n_kblocks; ++kb) {
+        for (int kb = SHARE ? (int)my_rank : 0; kb < P.n_kblocks; kb += SHARE ? 2 : 1) {
             const int s = kb % P.stages;
             const uint32_t it = (uint32_t)(kb / P.stages);
             mbar_wait(bar_empty0 + 8 * s, (it & 1) ^ 1);
@@ -371,8 +409,19 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
             if (MODE == 0) produce_dense(P, rows, kb, a_hi, a_lo, tid, want_lo);
             else if (MODE == 3) produce_sep<3>(P, kb, a_hi, a_lo, m0, tid, want_lo);
             else produce_sep<5>(P, kb, a_hi, a_lo, m0, tid, want_lo);
-            fence_proxy_async();           // generic-proxy smem writes -> visible to the tensor core
-            mbar_arrive(bar_full0 + 8 * s);
+            fence_proxy_async();           // generic-proxy smem writes -> visible to the tensor core / bulk copy
+            if (SHARE) {
+                asm volatile("bar.sync 1, %0;" ::"r"(NPROD) : "memory");      // all 256 producers wrote their part
+                if (tid == 0) {
+                    mbar_arrive(bar_full0 + 8 * s);                            // local copy ready
+                    const uint32_t peer = my_rank ^ 1u;
+                    const uint32_t peer_full = mapa_peer(bar_full0 + 8 * s, peer);
+                    bulk_s2peer(mapa_peer(smem_u32(a_hi), peer), smem_u32(a_hi), A_TILE_BYTES, peer_full);
+                    if (want_lo) bulk_s2peer(mapa_peer(smem_u32(a_lo), peer), smem_u32(a_lo), A_TILE_BYTES, peer_full);
+                }
+            } else {
+                mbar_arrive(bar_full0 + 8 * s);
+            }
         }
         // ======================= epilogue =======================
         // TMEM -> registers (lane = pixel row) -> per-warp smem transpose (the drained stage-0
@@ -383,7 +432,9 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
         const ConvParams& c = P.c;
         const int q = warp & 3, half = warp >> 2;
         constexpr int TS = 36;                                 // tile row stride (floats): 16B-aligned rows
-        float* tile = reinterpret_cast<float*>(smem) + warp * (32 * TS);
+        // SHARE: stage my_rank's A buffers are the SOURCE of this CTA's outgoing DSMEM copies, which may
+        // still be draining; stage (my_rank ^ 1) only ever received data that the MMAs already consumed.
+        float* tile = reinterpret_cast<float*>(smem + (SHARE ? (size_t)(my_rank ^ 1u) * stage_bytes : 0)) + warp * (32 * TS);
         const int mbase = m0 + q * 32;
         const int nch32 = (P.bn_cta + 31) >> 5;               // 32-column chunks (last may be 16 wide)
         const int c_begin = half == 0 ? 0 : (nch32 + 1) / 2;
@@ -471,12 +522,14 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
         // ======================= weight tiles via TMA =======================
         if (lane == 0) {
             const uint32_t tx = (uint32_t)(want_lo ? 2 : 1) * (uint32_t)b_tile_bytes;
+            const uint32_t tx_a = (uint32_t)(want_lo ? 2 : 1) * (uint32_t)A_TILE_BYTES;
             for (int kb = 0; kb < P.n_kblocks; ++kb) {
                 const int s = kb % P.stages;
                 const uint32_t it = (uint32_t)(kb / P.stages);
                 mbar_wait(bar_empty0 + 8 * s, (it & 1) ^ 1);
                 const uint32_t full = bar_full0 + 8 * s;
-                mbar_arrive_expect_tx(full, tx);
+                // SHARE: K-blocks produced by the peer deliver their A tile as transaction bytes
+                mbar_arrive_expect_tx(full, tx + ((SHARE && (uint32_t)s != my_rank) ? tx_a : 0u));
                 const uint32_t b_hi = smem_u32(smem + (size_t)s * stage_bytes + 2 * A_TILE_BYTES);
                 const uint32_t b_lo = b_hi + (uint32_t)b_tile_bytes;
                 for (int sub = 0; sub < P.nsub; ++sub) {
@@ -512,13 +565,14 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
                         }
                     }
                 }
-                umma_commit(bar_empty0 + 8 * s);      // frees this smem stage when the MMAs retire
+                if (SHARE) umma_commit_pair(bar_empty0 + 8 * s);   // both CTAs must release the stage
+                else umma_commit(bar_empty0 + 8 * s);              // frees this smem stage when the MMAs retire
             }
             umma_commit(bar_tmem);                    // accumulators complete -> epilogue
         }
     }
     tc_fence_before();
-    __syncthreads();
+    if (SHARE) cluster_sync_all(); else __syncthreads();
     if (warp == WARP_MMA) {
         tc_fence_after();
         tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
@@ -606,7 +660,6 @@ bool dh_tc_supported(const ConvParams& p, const dh_packed_w* packed, bool separa
 int dh_launch_conv_tc(dh_ctx* ctx, const ConvParams& p, const dh_packed_w* packed, bool separable, int precision,
                       cudaStream_t s) {
     using namespace tc;
-    (void)ctx;
     TcParams P;
     P.c = p;
     const int K = separable ? p.Cin : p.kh * p.kw * p.Cin;
@@ -643,17 +696,32 @@ int dh_launch_conv_tc(dh_ctx* ctx, const ConvParams& p, const dh_packed_w* packe
     }
     dim3 grid((p.M + BM - 1) / BM, gy);
     cudaError_t e;
+    // A-tile sharing across the two N-half CTAs (cluster 1x2x1): separable layers with Cout split in 2
+    const bool share = separable && gy == 2 && stages == 2 && P.n_kblocks >= 2 && ctx->share_a;
 #define DH_TC_LAUNCH(MODE)                                                                                   \
     do {                                                                                                     \
-        e = cudaFuncSetAttribute(conv_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        if (e == cudaSuccess) conv_tc_kernel<MODE><<<grid, NTHREADS, smem, s>>>(P, map_hi, map_lo);           \
+        if (share) {                                                                                         \
+            e = cudaFuncSetAttribute(conv_tc_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            if (e == cudaSuccess) {                                                                          \
+                cudaLaunchConfig_t cfg = {};                                                                 \
+                cfg.gridDim = grid; cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s; \
+                cudaLaunchAttribute at[1];                                                                   \
+                at[0].id = cudaLaunchAttributeClusterDimension;                                              \
+                at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 2; at[0].val.clusterDim.z = 1;          \
+                cfg.attrs = at; cfg.numAttrs = 1;                                                            \
+                e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<MODE, true>, P, map_hi, map_lo);                 \
+            }                                                                                                \
+        } else {                                                                                             \
+            e = cudaFuncSetAttribute(conv_tc_kernel<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            if (e == cudaSuccess) conv_tc_kernel<MODE, false><<<grid, NTHREADS, smem, s>>>(P, map_hi, map_lo); \
+        }                                                                                                    \
     } while (0)
     if (!separable) DH_TC_LAUNCH(0);
     else if (p.kh == 3) DH_TC_LAUNCH(3);
     else DH_TC_LAUNCH(5);
 #undef DH_TC_LAUNCH
     if (e != cudaSuccess) {
-        dh_set_error("dh_launch_conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        dh_set_error("dh_launch_conv_tc: launch setup failed: %s", cudaGetErrorString(e));
         return (int)e;
     }
     return 0;

@@ -13,30 +13,48 @@ struct PoolParams {
 };
 
 // mode 0: max ; mode 1: max + min  (layers.py:411-425 max_min_pooling = max(x) - max(-x))
-template <int MODE>
+// VEC = 4: one thread handles 4 consecutive channels with 16-byte loads/stores (C, ld % 4 == 0).
+template <int MODE, int VEC>
 __global__ void __launch_bounds__(256) pool_kernel(PoolParams p) {
-    const int64_t total = (int64_t)p.N * p.Ho * p.Wo * p.C;
+    const int CV = p.C / VEC;
+    const int64_t total = (int64_t)p.N * p.Ho * p.Wo * CV;
     for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
          idx += (int64_t)gridDim.x * blockDim.x) {
-        int c = (int)(idx % p.C);
-        int64_t m = idx / p.C;
+        int c = (int)(idx % CV) * VEC;
+        int64_t m = idx / CV;
         int ox = (int)(m % p.Wo);
         int64_t t = m / p.Wo;
         int oy = (int)(t % p.Ho);
         int n = (int)(t / p.Ho);
-        float mx = -FLT_MAX, mn = FLT_MAX;
+        float mx[VEC], mn[VEC];
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) { mx[e] = -FLT_MAX; mn[e] = FLT_MAX; }
         for (int ky = 0; ky < p.kh; ++ky) {
             int iy = oy * p.sh - p.pt + ky;
             if (iy < 0 || iy >= p.H) continue;
             for (int kx = 0; kx < p.kw; ++kx) {
                 int ix = ox * p.sw - p.pl + kx;
                 if (ix < 0 || ix >= p.W) continue;
-                float v = __ldg(p.x + ((size_t)(n * p.H + iy) * p.W + ix) * p.ldx + c);
-                mx = fmaxf(mx, v);
-                mn = fminf(mn, v);
+                const float* src = p.x + ((size_t)(n * p.H + iy) * p.W + ix) * p.ldx + c;
+                float v[VEC];
+                if (VEC == 4) {
+                    float4 q = __ldg(reinterpret_cast<const float4*>(src));
+                    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+                } else {
+                    v[0] = __ldg(src);
+                }
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) { mx[e] = fmaxf(mx[e], v[e]); mn[e] = fminf(mn[e], v[e]); }
             }
         }
-        p.out[(size_t)m * p.ldo + c] = MODE == 0 ? mx : mx + mn;
+        float* dst = p.out + (size_t)m * p.ldo + c;
+        if (VEC == 4) {
+            float4 o = MODE == 0 ? make_float4(mx[0], mx[1], mx[2], mx[3])
+                                 : make_float4(mx[0] + mn[0], mx[1] + mn[1], mx[2] + mn[2], mx[3] + mn[3]);
+            *reinterpret_cast<float4*>(dst) = o;
+        } else {
+            dst[0] = MODE == 0 ? mx[0] : mx[0] + mn[0];
+        }
     }
 }
 
@@ -47,20 +65,33 @@ struct UpParams {
     int N, H, W, C;  // output dims
 };
 
+template <int VEC>
 __global__ void __launch_bounds__(256) upsample2x_add_kernel(UpParams p) {
-    const int64_t total = (int64_t)p.N * p.H * p.W * p.C;
+    const int CV = p.C / VEC;
+    const int64_t total = (int64_t)p.N * p.H * p.W * CV;
     const int Hb = p.H / 2, Wb = p.W / 2;
     for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
          idx += (int64_t)gridDim.x * blockDim.x) {
-        int c = (int)(idx % p.C);
-        int64_t m = idx / p.C;
+        int c = (int)(idx % CV) * VEC;
+        int64_t m = idx / CV;
         int x = (int)(m % p.W);
         int64_t t = m / p.W;
         int y = (int)(t % p.H);
         int n = (int)(t / p.H);
-        float v = __ldg(p.b + ((size_t)(n * Hb + (y >> 1)) * Wb + (x >> 1)) * p.ldb + c);
-        if (p.a) v += __ldg(p.a + (size_t)m * p.lda + c);
-        p.out[(size_t)m * p.ldo + c] = v;
+        const float* bp = p.b + ((size_t)(n * Hb + (y >> 1)) * Wb + (x >> 1)) * p.ldb + c;
+        float* dst = p.out + (size_t)m * p.ldo + c;
+        if (VEC == 4) {
+            float4 v = __ldg(reinterpret_cast<const float4*>(bp));
+            if (p.a) {
+                float4 a = __ldg(reinterpret_cast<const float4*>(p.a + (size_t)m * p.lda + c));
+                v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+            }
+            *reinterpret_cast<float4*>(dst) = v;
+        } else {
+            float v = __ldg(bp);
+            if (p.a) v += __ldg(p.a + (size_t)m * p.lda + c);
+            dst[0] = v;
+        }
     }
 }
 
@@ -72,19 +103,36 @@ struct AddParams {
     int64_t M; int C;
 };
 
+template <int VEC>
 __global__ void __launch_bounds__(256) add_n_kernel(AddParams p) {
-    const int64_t total = p.M * p.C;
+    const int CV = p.C / VEC;
+    const int64_t total = p.M * CV;
     for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
          idx += (int64_t)gridDim.x * blockDim.x) {
-        int c = (int)(idx % p.C);
-        int64_t m = idx / p.C;
-        float v = 0.f;
+        int c = (int)(idx % CV) * VEC;
+        int64_t m = idx / CV;
+        float v[VEC];
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) v[e] = 0.f;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-            if (i < p.n_in) v += __ldg(p.in[i] + (size_t)m * p.ld[i] + c);
-        if (p.scale) v = fmaf(v, __ldg(p.scale + c), __ldg(p.shift + c));
-        if (p.relu) v = fmaxf(v, 0.f);
-        p.out[(size_t)m * p.ldo + c] = v;
+            if (i < p.n_in) {
+                const float* src = p.in[i] + (size_t)m * p.ld[i] + c;
+                if (VEC == 4) {
+                    float4 q = __ldg(reinterpret_cast<const float4*>(src));
+                    v[0] += q.x; v[1] += q.y; v[2] += q.z; v[3] += q.w;
+                } else {
+                    v[0] += __ldg(src);
+                }
+            }
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            if (p.scale) v[e] = fmaf(v[e], __ldg(p.scale + c + e), __ldg(p.shift + c + e));
+            if (p.relu) v[e] = fmaxf(v[e], 0.f);
+        }
+        float* dst = p.out + (size_t)m * p.ldo + c;
+        if (VEC == 4) *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+        else dst[0] = v[0];
     }
 }
 
@@ -142,11 +190,13 @@ static int pool_common(dh_ctx* ctx, const dh_view* x, int kh, int kw, int sh, in
     p.x = x->p; p.N = x->n; p.H = x->h; p.W = x->w; p.C = x->c; p.ldx = x->ld;
     p.out = out->p; p.Ho = ho; p.Wo = wo; p.ldo = out->ld;
     p.kh = kh; p.kw = kw; p.sh = sh; p.sw = sw; p.pt = pt; p.pl = pl;
-    int64_t total = (int64_t)p.N * ho * wo * p.C;
-    if (mode == 0)
-        pool_kernel<0><<<grid_for(total, ctx->num_sms), 256, 0, (cudaStream_t)stream>>>(p);
-    else
-        pool_kernel<1><<<grid_for(total, ctx->num_sms), 256, 0, (cudaStream_t)stream>>>(p);
+    const bool vec = (p.C % 4 == 0) && (p.ldx % 4 == 0) && (p.ldo % 4 == 0) && dh_aligned16(p.x) && dh_aligned16(p.out);
+    int64_t total = (int64_t)p.N * ho * wo * (vec ? p.C / 4 : p.C);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mode == 0 && vec) pool_kernel<0, 4><<<grid_for(total, ctx->num_sms), 256, 0, st>>>(p);
+    else if (mode == 0) pool_kernel<0, 1><<<grid_for(total, ctx->num_sms), 256, 0, st>>>(p);
+    else if (vec) pool_kernel<1, 4><<<grid_for(total, ctx->num_sms), 256, 0, st>>>(p);
+    else pool_kernel<1, 1><<<grid_for(total, ctx->num_sms), 256, 0, st>>>(p);
     DH_LAUNCH_EPILOGUE(ctx, 1);
 }
 
@@ -173,8 +223,11 @@ extern "C" int dh_upsample2x_add_f32(dh_ctx* ctx, const dh_view* a, const dh_vie
     }
     p.b = b->p; p.ldb = b->ld; p.out = out->p; p.ldo = out->ld;
     p.N = out->n; p.H = out->h; p.W = out->w; p.C = out->c;
-    int64_t total = (int64_t)p.N * p.H * p.W * p.C;
-    upsample2x_add_kernel<<<grid_for(total, ctx->num_sms), 256, 0, (cudaStream_t)stream>>>(p);
+    const bool vec = (p.C % 4 == 0) && (p.ldb % 4 == 0) && (p.ldo % 4 == 0) && dh_aligned16(p.b) && dh_aligned16(p.out) &&
+                     (!p.a || ((p.lda % 4 == 0) && dh_aligned16(p.a)));
+    int64_t total = (int64_t)p.N * p.H * p.W * (vec ? p.C / 4 : p.C);
+    if (vec) upsample2x_add_kernel<4><<<grid_for(total, ctx->num_sms), 256, 0, (cudaStream_t)stream>>>(p);
+    else upsample2x_add_kernel<1><<<grid_for(total, ctx->num_sms), 256, 0, (cudaStream_t)stream>>>(p);
     DH_LAUNCH_EPILOGUE(ctx, 1);
 }
 
@@ -194,7 +247,11 @@ extern "C" int dh_add_n_f32(dh_ctx* ctx, const dh_view* in, int n_in, const floa
     p.n_in = n_in; p.scale = scale; p.shift = shift; p.relu = relu;
     p.out = out->p; p.ldo = out->ld;
     p.M = (int64_t)out->n * out->h * out->w; p.C = out->c;
-    add_n_kernel<<<grid_for(p.M * p.C, ctx->num_sms), 256, 0, (cudaStream_t)stream>>>(p);
+    bool vec = (p.C % 4 == 0) && (p.ldo % 4 == 0) && dh_aligned16(p.out) &&
+               (!scale || (dh_aligned16(scale) && dh_aligned16(shift)));
+    for (int i = 0; i < n_in; ++i) vec = vec && (p.ld[i] % 4 == 0) && dh_aligned16(p.in[i]);
+    if (vec) add_n_kernel<4><<<grid_for(p.M * (p.C / 4), ctx->num_sms), 256, 0, (cudaStream_t)stream>>>(p);
+    else add_n_kernel<1><<<grid_for(p.M * p.C, ctx->num_sms), 256, 0, (cudaStream_t)stream>>>(p);
     DH_LAUNCH_EPILOGUE(ctx, 1);
 }
 

@@ -79,6 +79,8 @@ int         dh_version(void);
 int64_t     dh_launch_count(dh_ctx* ctx, int reset);
 /* scratch for two-kernel ops (owned by the caller): set before use */
 int         dh_set_workspace(dh_ctx* ctx, void* ptr, int64_t bytes);
+/* tuning switches: "share_a" (default 1) = 2-CTA clusters share the separable A tile over DSMEM */
+int         dh_set_option(dh_ctx* ctx, const char* name, int value);
 
 /* --- convolutions -------------------------------------------------------- */
 /* Tensor-core weight packing geometry: dh_packed_w.hi/lo are bf16 [dh_tc_cout_pad(Cout)][dh_tc_k_pad(K)]

@@ -150,3 +150,16 @@ def test_tc_channel_views(dev):
     got = cat.cpu().numpy()
     assert _err(got[..., 4:36], ref) <= TOL3
     assert np.all(got[..., :4] == 7.0) and np.all(got[..., 36:] == 7.0)
+
+
+@pytest.mark.parametrize('share', [1, 0])
+def test_sepconv_cluster_share_matches(dev, share):
+    """Cout = 576 layers run as 2-CTA clusters sharing the depthwise A tile over DSMEM (share_a = 1);
+    the result must match the oracle exactly like the independent-CTA path (share_a = 0)."""
+    _ffi.check(dev.lib.dh_set_option(dev.ctx.handle, b'share_a', share))
+    try:
+        for case in [(3, 32, 32, 576, 576, 5, 'act_bn_res'), (2, 16, 16, 288, 576, 5, 'act_bn_res'),
+                     (1, 32, 32, 384, 576, 3, 'act_bn_res'), (5, 8, 8, 128, 576, 5, 'bn_act')]:
+            test_sepconv_tc(dev, case, 3)
+    finally:
+        _ffi.check(dev.lib.dh_set_option(dev.ctx.handle, b'share_a', 1))
