@@ -197,8 +197,15 @@ __device__ __forceinline__ void dense_rows_init(const ConvParams& c, int m0, int
     }
 }
 
-__device__ __forceinline__ void produce_dense(const TcParams& P, const DenseRows& R, int kb, uint8_t* a_hi,
-                                              uint8_t* a_lo, int tid, bool want_lo) {
+// Loads of K-block kb (8 x 16 B per thread) -- issued one K-block AHEAD of the shared-memory
+// stage they will be written to, so the global/L2 latency overlaps the previous block's work.
+struct DenseRegs {
+    float4 v[8];
+    unsigned ok;       // bit i: element i is inside the image (and k < K)
+    float4 ps, pb;
+};
+
+__device__ __forceinline__ void dense_load(const TcParams& P, const DenseRows& R, int kb, int tid, DenseRegs& D) {
     const ConvParams& c = P.c;
     const int j = tid & 15;
     const int k = kb * BK + j * 4;          // k = tap*Cin + ci, groups of 4 never straddle a tap (Cin % 4 == 0)
@@ -210,26 +217,35 @@ __device__ __forceinline__ void produce_dense(const TcParams& P, const DenseRows
         ky = tap / c.kw;
         kx = tap - ky * c.kw;
     }
-    float4 ps = make_float4(1.f, 1.f, 1.f, 1.f), pb = make_float4(0.f, 0.f, 0.f, 0.f);
+    D.ps = make_float4(1.f, 1.f, 1.f, 1.f);
+    D.pb = make_float4(0.f, 0.f, 0.f, 0.f);
     if (kval && c.pre_scale) {
-        ps = __ldg(reinterpret_cast<const float4*>(c.pre_scale + ci));
-        pb = __ldg(reinterpret_cast<const float4*>(c.pre_shift + ci));
+        D.ps = __ldg(reinterpret_cast<const float4*>(c.pre_scale + ci));
+        D.pb = __ldg(reinterpret_cast<const float4*>(c.pre_shift + ci));
     }
-    float4 v[8];
-    bool ok[8];
+    D.ok = 0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int iy = (R.yx[i] >> 16) + ky, ix = (int)(short)(R.yx[i] & 0xffff) + kx;
-        ok[i] = kval && R.base[i] >= 0 && iy >= 0 && iy < c.H && ix >= 0 && ix < c.W;
-        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ok[i]) v[i] = __ldg(reinterpret_cast<const float4*>(c.x + (size_t)(R.base[i] + iy * c.W + ix) * c.ldx + ci));
+        const bool ok = kval && R.base[i] >= 0 && iy >= 0 && iy < c.H && ix >= 0 && ix < c.W;
+        D.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok) {
+            D.ok |= 1u << i;
+            D.v[i] = __ldg(reinterpret_cast<const float4*>(c.x + (size_t)(R.base[i] + iy * c.W + ix) * c.ldx + ci));
+        }
     }
+}
+
+__device__ __forceinline__ void dense_store(const TcParams& P, const DenseRegs& D, uint8_t* a_hi, uint8_t* a_lo,
+                                            int tid, bool want_lo) {
+    const ConvParams& c = P.c;
+    const int j = tid & 15;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        float4 t = v[i];
-        if (ok[i]) {
-            t.x = fmaf(t.x, ps.x, pb.x); t.y = fmaf(t.y, ps.y, pb.y);
-            t.z = fmaf(t.z, ps.z, pb.z); t.w = fmaf(t.w, ps.w, pb.w);
+        float4 t = D.v[i];
+        if ((D.ok >> i) & 1u) {
+            t.x = fmaf(t.x, D.ps.x, D.pb.x); t.y = fmaf(t.y, D.ps.y, D.pb.y);
+            t.z = fmaf(t.z, D.ps.z, D.pb.z); t.w = fmaf(t.w, D.ps.w, D.pb.w);
             if (c.pre_relu) {
                 t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f);
             }
@@ -399,15 +415,22 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
     if (warp < 8) {
         // ======================= A producers =======================
         DenseRows rows;
-        if (MODE == 0) dense_rows_init(P.c, m0, tid, rows);
+        DenseRegs cur, nxt;
+        if (MODE == 0) {
+            dense_rows_init(P.c, m0, tid, rows);
+            dense_load(P, rows, 0, tid, cur);
+        }
         for (int kb = SHARE ? (int)my_rank : 0; kb < P.n_kblocks; kb += SHARE ? 2 : 1) {
             const int s = kb % P.stages;
             const uint32_t it = (uint32_t)(kb / P.stages);
+            if (MODE == 0 && kb + 1 < P.n_kblocks) dense_load(P, rows, kb + 1, tid, nxt);   // prefetch next K-block
             mbar_wait(bar_empty0 + 8 * s, (it & 1) ^ 1);
             uint8_t* a_hi = smem + (size_t)s * stage_bytes;
             uint8_t* a_lo = a_hi + A_TILE_BYTES;
-            if (MODE == 0) produce_dense(P, rows, kb, a_hi, a_lo, tid, want_lo);
-            else if (MODE == 3) produce_sep<3>(P, kb, a_hi, a_lo, m0, tid, want_lo);
+            if (MODE == 0) {
+                dense_store(P, cur, a_hi, a_lo, tid, want_lo);
+                cur = nxt;
+            } else if (MODE == 3) produce_sep<3>(P, kb, a_hi, a_lo, m0, tid, want_lo);
             else produce_sep<5>(P, kb, a_hi, a_lo, m0, tid, want_lo);
             fence_proxy_async();           // generic-proxy smem writes -> visible to the tensor core / bulk copy
             if (SHARE) {
