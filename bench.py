@@ -139,7 +139,7 @@ def run_reference(args):
         'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': fps, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 def softargmax_microbench(torch, model, peaks):
@@ -327,9 +327,13 @@ def main():
                                 'sample': '%d frames (batches of 4) of the same model, torch-CPU fp32 port '
                                           'of the Keras graph, %.1f s' % (done, dtc)}
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        try:
+            dist.barrier()
+            dist.destroy_process_group()
+        except Exception as e:      # the JSON line is already out; never fail the run on teardown
+            print('teardown: %r' % (e,), file=sys.stderr)
 
 
 if __name__ == '__main__':
