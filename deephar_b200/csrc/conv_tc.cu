@@ -29,9 +29,13 @@ namespace tc {
 
 constexpr int BM = 128;
 constexpr int BK = 64;                 // bf16 per K-block = one 128-byte swizzle row
-constexpr int NPROD = 256;             // producer / epilogue threads (warps 0..7)
-constexpr int WARP_TMA = 8, WARP_MMA = 9;
-constexpr int NTHREADS = NPROD + 64;
+constexpr int NPROD = 256;             // A producers: warps 0..7 (two warpgroups)
+constexpr int NEPI = 128;              // epilogue: warps 8..11 (one warpgroup; warp % 4 = TMEM lane quarter)
+constexpr int WARP_EPI0 = 8, WARP_TMA = 12, WARP_MMA = 13;
+constexpr int NTHREADS = 512;          // 4 warpgroups; the last one holds the TMA + MMA threads
+constexpr int EPI_STAGE_BYTES = 4 * 32 * 128;   // per epilogue warp: 32 rows x 32 fp32, XOR-swizzled
+// register budget (setmaxnreg): 256*168 + 128*136 + 128*40 = 65536
+constexpr int REGS_PROD = 168, REGS_EPI = 136, REGS_CTRL = 40;
 constexpr int A_TILE_BYTES = BM * 128; // 16 KB per (hi | lo)
 constexpr int MAX_STAGES = 4;
 constexpr int MAX_BN_CTA = 288;
@@ -46,6 +50,8 @@ struct TcParams {
     uint32_t idesc;
     int ks;                 // separable: depthwise kernel size (3 | 5); 0 = dense
     int k_pad;
+    int n_mtiles;           // ceil(M / 128); CTA (x, y) loops over tiles x, x + gridDim.x, ...
+    int nacc, acc_stride;   // TMEM accumulator ring: 1 or 2 buffers of acc_stride columns
 };
 
 // ---------------------------------------------------------------------------
@@ -133,6 +139,8 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
                  ::"r"(bar), "h"((uint16_t)3)
                  : "memory");
 }
+template <int R> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
+template <int R> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
     uint32_t r[16];
     asm volatile(
@@ -365,10 +373,17 @@ __device__ __forceinline__ void produce_sep(const TcParams& P, int kb, uint8_t* 
 // ---------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------
+// Persistent, warp-specialised kernel.  Every CTA (one per SM) loops over 128-pixel tiles
+//   warps 0-7   A producers (CUDA cores)          warps 8-11  epilogue (TMEM -> global)
+//   warp 12     TMA weight tiles (one thread)      warp 13     tcgen05.mma issue (one thread)
+// connected by three mbarrier rings: smem stages full[s]/empty[s] (K-blocks, counted across
+// tiles), TMEM accumulators tmem_full[a]/tmem_empty[a] (1 or 2 buffers: the epilogue of tile i
+// overlaps the production / MMAs of tile i+1).  Registers are rebalanced with setmaxnreg.
+//
 // SHARE: the two CTAs (N halves) of one 128-pixel tile form a cluster (1,2,1) and split the A
-// production: CTA r produces the K-blocks with kb % 2 == r (stages == 2, so stage r is "its"
-// stage), pushes the finished tile to the peer with a DSMEM bulk copy that completes on the
-// peer's full[r] barrier, and every MMA commit is multicast to both CTAs' empty barriers.
+// production: with 2 stages, CTA r owns stage r (global K-block counter g with g % 2 == r); it
+// pushes each finished tile to the peer with a DSMEM bulk copy that completes on the peer's
+// full[r] barrier, and every MMA commit is multicast to both CTAs' empty barriers.
 template <int MODE, bool SHARE>   // MODE: 0 dense/1x1, 3 separable 3x3, 5 separable 5x5
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUtensorMap map_hi,
@@ -380,13 +395,14 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
     const bool want_lo = P.precision == 3;
     const int b_tile_bytes = P.bn_cta * 128;
     const int stage_bytes = 2 * A_TILE_BYTES + 2 * b_tile_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)P.stages * stage_bytes);
-    // bars[0..S) full, [S..2S) empty, [2S] tmem_full ; then the TMEM base address word
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 1);
-    const uint32_t bar_full0 = smem_u32(bars), bar_empty0 = smem_u32(bars + P.stages),
-                   bar_tmem = smem_u32(bars + 2 * P.stages);
-    const int m0 = blockIdx.x * BM;
+    uint8_t* epi_stage = smem + (size_t)P.stages * stage_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage + EPI_STAGE_BYTES);
+    // bars: full[MAX_STAGES] | empty[MAX_STAGES] | tmem_full[2] | tmem_empty[2] ; then the TMEM base word
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
+    const uint32_t bar_full0 = smem_u32(bars), bar_empty0 = smem_u32(bars + MAX_STAGES),
+                   bar_tfull0 = smem_u32(bars + 2 * MAX_STAGES), bar_tempty0 = smem_u32(bars + 2 * MAX_STAGES + 2);
     const int n0 = blockIdx.y * P.bn_cta;
+    const int nkb = P.n_kblocks;
 
     if (warp == WARP_TMA && lane == 0) {
         tma_prefetch_desc(&map_hi);
@@ -402,196 +418,240 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
                 mbar_init(bar_empty0 + 8 * s, 1);
             }
         }
-        mbar_init(bar_tmem, 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(bar_tfull0 + 8 * a, 1);
+            mbar_init(bar_tempty0 + 8 * a, NEPI);
+        }
         fence_barrier_init();
     }
     if (warp == WARP_MMA) tmem_alloc(smem_u32(tmem_slot), (uint32_t)P.tmem_cols);
     tc_fence_before();
     if (SHARE) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
-    const uint32_t my_rank = SHARE ? cluster_ctarank() : 0u;
     const uint32_t tmem_base = *tmem_slot;
+    const uint32_t my_rank = SHARE ? cluster_ctarank() : 0u;
 
-    if (warp < 8) {
+    if (warp < WARP_EPI0) {
         // ======================= A producers =======================
+        reg_inc<REGS_PROD>();
         DenseRows rows;
         DenseRegs cur, nxt;
-        if (MODE == 0) {
-            dense_rows_init(P.c, m0, tid, rows);
-            dense_load(P, rows, 0, tid, cur);
-        }
-        for (int kb = SHARE ? (int)my_rank : 0; kb < P.n_kblocks; kb += SHARE ? 2 : 1) {
-            const int s = kb % P.stages;
-            const uint32_t it = (uint32_t)(kb / P.stages);
-            if (MODE == 0 && kb + 1 < P.n_kblocks) dense_load(P, rows, kb + 1, tid, nxt);   // prefetch next K-block
-            mbar_wait(bar_empty0 + 8 * s, (it & 1) ^ 1);
-            uint8_t* a_hi = smem + (size_t)s * stage_bytes;
-            uint8_t* a_lo = a_hi + A_TILE_BYTES;
+        int ti = 0;
+        for (int t = blockIdx.x; t < P.n_mtiles; t += gridDim.x, ++ti) {
+            const int m0 = t * BM;
+            const int g0 = ti * nkb;
+            const int kb_first = SHARE ? (int)((my_rank ^ (uint32_t)g0) & 1u) : 0;   // (g0 + kb) % 2 == my_rank
             if (MODE == 0) {
-                dense_store(P, cur, a_hi, a_lo, tid, want_lo);
-                cur = nxt;
-            } else if (MODE == 3) produce_sep<3>(P, kb, a_hi, a_lo, m0, tid, want_lo);
-            else produce_sep<5>(P, kb, a_hi, a_lo, m0, tid, want_lo);
-            fence_proxy_async();           // generic-proxy smem writes -> visible to the tensor core / bulk copy
-            if (SHARE) {
-                asm volatile("bar.sync 1, %0;" ::"r"(NPROD) : "memory");      // all 256 producers wrote their part
-                if (tid == 0) {
-                    mbar_arrive(bar_full0 + 8 * s);                            // local copy ready
-                    const uint32_t peer = my_rank ^ 1u;
-                    const uint32_t peer_full = mapa_peer(bar_full0 + 8 * s, peer);
-                    bulk_s2peer(mapa_peer(smem_u32(a_hi), peer), smem_u32(a_hi), A_TILE_BYTES, peer_full);
-                    if (want_lo) bulk_s2peer(mapa_peer(smem_u32(a_lo), peer), smem_u32(a_lo), A_TILE_BYTES, peer_full);
+                dense_rows_init(P.c, m0, tid, rows);
+                dense_load(P, rows, 0, tid, cur);
+            }
+            for (int kb = kb_first; kb < nkb; kb += SHARE ? 2 : 1) {
+                const int g = g0 + kb;
+                const int s = g % P.stages;
+                const uint32_t it = (uint32_t)(g / P.stages);
+                if (MODE == 0 && kb + 1 < nkb) dense_load(P, rows, kb + 1, tid, nxt);   // prefetch next K-block
+                mbar_wait(bar_empty0 + 8 * s, (it & 1) ^ 1);
+                uint8_t* a_hi = smem + (size_t)s * stage_bytes;
+                uint8_t* a_lo = a_hi + A_TILE_BYTES;
+                if (MODE == 0) {
+                    dense_store(P, cur, a_hi, a_lo, tid, want_lo);
+                    cur = nxt;
+                } else if (MODE == 3) produce_sep<3>(P, kb, a_hi, a_lo, m0, tid, want_lo);
+                else produce_sep<5>(P, kb, a_hi, a_lo, m0, tid, want_lo);
+                fence_proxy_async();           // generic-proxy smem writes -> visible to the tensor core / bulk copy
+                if (SHARE) {
+                    asm volatile("bar.sync 1, %0;" ::"r"(NPROD) : "memory");      // all 256 producers wrote their part
+                    if (tid == 0) {
+                        mbar_arrive(bar_full0 + 8 * s);                            // local copy ready
+                        const uint32_t peer = my_rank ^ 1u;
+                        const uint32_t peer_full = mapa_peer(bar_full0 + 8 * s, peer);
+                        bulk_s2peer(mapa_peer(smem_u32(a_hi), peer), smem_u32(a_hi), A_TILE_BYTES, peer_full);
+                        if (want_lo) bulk_s2peer(mapa_peer(smem_u32(a_lo), peer), smem_u32(a_lo), A_TILE_BYTES, peer_full);
+                    }
+                } else {
+                    mbar_arrive(bar_full0 + 8 * s);
                 }
-            } else {
-                mbar_arrive(bar_full0 + 8 * s);
             }
         }
+    } else if (warp < WARP_TMA) {
         // ======================= epilogue =======================
-        // TMEM -> registers (lane = pixel row) -> per-warp smem transpose (the drained stage-0
-        // buffers are reused) -> lane = output channel: every global access below is a fully
-        // coalesced 128-byte row segment; BN affine / ReLU / residual adds are fused here.
-        mbar_wait(bar_tmem, 0);
-        tc_fence_after();
+        // TMEM -> registers (lane = pixel row) -> per-warp XOR-swizzled smem transpose -> lane = 4
+        // consecutive output channels: every global access is a coalesced 128-byte row segment;
+        // BN affine / ReLU / residual adds are fused here.
+        reg_inc<REGS_EPI>();       // 136 > the 128 launch registers: this is an increase
         const ConvParams& c = P.c;
-        const int q = warp & 3, half = warp >> 2;
-        constexpr int TS = 36;                                 // tile row stride (floats): 16B-aligned rows
-        // SHARE: stage my_rank's A buffers are the SOURCE of this CTA's outgoing DSMEM copies, which may
-        // still be draining; stage (my_rank ^ 1) only ever received data that the MMAs already consumed.
-        float* tile = reinterpret_cast<float*>(smem + (SHARE ? (size_t)(my_rank ^ 1u) * stage_bytes : 0)) + warp * (32 * TS);
-        const int mbase = m0 + q * 32;
+        const int q = warp & 3;
+        float* tile = reinterpret_cast<float*>(epi_stage) + q * (32 * 32);
         const int nch32 = (P.bn_cta + 31) >> 5;               // 32-column chunks (last may be 16 wide)
-        const int c_begin = half == 0 ? 0 : (nch32 + 1) / 2;
-        const int c_end = half == 0 ? (nch32 + 1) / 2 : nch32;
-        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
         const bool vec_ok = ((c.ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(c.out) & 15) == 0) &&
                             (!c.res0 || (((c.ldr0 & 3) == 0) && ((reinterpret_cast<uintptr_t>(c.res0) & 15) == 0))) &&
                             (!c.res1 || (((c.ldr1 & 3) == 0) && ((reinterpret_cast<uintptr_t>(c.res1) & 15) == 0))) &&
                             ((c.Cout & 3) == 0) &&
                             (!c.post_scale || (((reinterpret_cast<uintptr_t>(c.post_scale) & 15) == 0) &&
                                                ((reinterpret_cast<uintptr_t>(c.post_shift) & 15) == 0)));
-        for (int ck = c_begin; ck < c_end; ++ck) {
-            const int col0 = ck * 32;
-            const int width = min(32, P.bn_cta - col0);        // 32 or 16
-            {
-                float v[32];
-                tmem_ld16(trow + (uint32_t)col0, v);
-                if (width == 32) tmem_ld16(trow + (uint32_t)(col0 + 16), v + 16);
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    if (j * 4 < width)
-                        *reinterpret_cast<float4*>(tile + lane * TS + j * 4) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            }
-            __syncwarp();
-            if (vec_ok) {
-                // lane = (row r4 = lane/8 + 4*i, 4 columns c4 = lane%8): 4 rows x 128 B per instruction
-                const int c4 = (lane & 7) * 4;
-                const int co = n0 + col0 + c4;
-                const bool cok = c4 < width && co < c.Cout;
-                float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (cok && c.post_scale) {
-                    sc = __ldg(reinterpret_cast<const float4*>(c.post_scale + co));
-                    sh = __ldg(reinterpret_cast<const float4*>(c.post_shift + co));
-                }
-                float4 ra[8], rb[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int m = mbase + (lane >> 3) + 4 * i;
-                    ra[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    rb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (cok && m < c.M) {
-                        if (c.res0) ra[i] = __ldg(reinterpret_cast<const float4*>(c.res0 + (size_t)m * c.ldr0 + co));
-                        if (c.res1) rb[i] = __ldg(reinterpret_cast<const float4*>(c.res1 + (size_t)m * c.ldr1 + co));
+        int ti = 0;
+        for (int t = blockIdx.x; t < P.n_mtiles; t += gridDim.x, ++ti) {
+            const int acc = ti % P.nacc;
+            const uint32_t acc_it = (uint32_t)(ti / P.nacc);
+            const int mbase = t * BM + q * 32;
+            // while the MMAs of this tile run: pull this warp's residual rows into L2
+            if (c.res0 || c.res1) {
+                const int m = mbase + lane;
+                if (m < c.M) {
+                    const int cols = min(P.bn_cta, c.Cout - n0);
+                    for (int cb = 0; cb < cols; cb += 32) {
+                        if (c.res0) asm volatile("prefetch.global.L2 [%0];" ::"l"(c.res0 + (size_t)m * c.ldr0 + n0 + cb));
+                        if (c.res1) asm volatile("prefetch.global.L2 [%0];" ::"l"(c.res1 + (size_t)m * c.ldr1 + n0 + cb));
                     }
                 }
+            }
+            mbar_wait(bar_tfull0 + 8 * acc, acc_it & 1);
+            tc_fence_after();
+            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * P.acc_stride);
+            for (int ck = 0; ck < nch32; ++ck) {
+                const int col0 = ck * 32;
+                const int width = min(32, P.bn_cta - col0);        // 32 or 16
+                {
+                    float v[32];
+                    tmem_ld16(trow + (uint32_t)col0, v);
+                    if (width == 32) tmem_ld16(trow + (uint32_t)(col0 + 16), v + 16);
+                    if (ck == nch32 - 1) {                          // accumulator fully read -> MMA may reuse it
+                        tc_fence_before();
+                        mbar_arrive(bar_tempty0 + 8 * acc);
+                    }
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int r = (lane >> 3) + 4 * i;
-                    const int m = mbase + r;
-                    if (cok && m < c.M) {
-                        float4 t = *reinterpret_cast<const float4*>(tile + r * TS + c4);
-                        t.x = fmaf(t.x, sc.x, sh.x); t.y = fmaf(t.y, sc.y, sh.y);
-                        t.z = fmaf(t.z, sc.z, sh.z); t.w = fmaf(t.w, sc.w, sh.w);
-                        if (c.post_relu) {
-                            t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f);
+                    for (int j = 0; j < 8; ++j)
+                        if (j * 4 < width)
+                            *reinterpret_cast<float4*>(tile + lane * 32 + ((j ^ (lane & 7)) << 2)) =
+                                make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                }
+                __syncwarp();
+                if (vec_ok) {
+                    // lane = (row r = lane/8 + 4*i, 4 columns c4 = 4*(lane%8)): 4 rows x 128 B per instruction
+                    const int b4 = lane & 7;
+                    const int co = n0 + col0 + b4 * 4;
+                    const bool cok = b4 * 4 < width && co < c.Cout;
+                    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (cok && c.post_scale) {
+                        sc = __ldg(reinterpret_cast<const float4*>(c.post_scale + co));
+                        sh = __ldg(reinterpret_cast<const float4*>(c.post_shift + co));
+                    }
+                    float4 ra[8], rb[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int m = mbase + (lane >> 3) + 4 * i;
+                        ra[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        rb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (cok && m < c.M) {
+                            if (c.res0) ra[i] = __ldg(reinterpret_cast<const float4*>(c.res0 + (size_t)m * c.ldr0 + co));
+                            if (c.res1) rb[i] = __ldg(reinterpret_cast<const float4*>(c.res1 + (size_t)m * c.ldr1 + co));
                         }
-                        t.x += ra[i].x + rb[i].x; t.y += ra[i].y + rb[i].y;
-                        t.z += ra[i].z + rb[i].z; t.w += ra[i].w + rb[i].w;
-                        *reinterpret_cast<float4*>(c.out + (size_t)m * c.ldo + co) = t;
                     }
-                }
-            } else {
-                const int co = n0 + col0 + lane;
-                const bool cok = lane < width && co < c.Cout;
-                float sc = 1.f, sh = 0.f;
-                if (cok && c.post_scale) {
-                    sc = __ldg(c.post_scale + co);
-                    sh = __ldg(c.post_shift + co);
-                }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int r = (lane >> 3) + 4 * i;
+                        const int m = mbase + r;
+                        if (cok && m < c.M) {
+                            float4 tt = *reinterpret_cast<const float4*>(tile + r * 32 + ((b4 ^ (r & 7)) << 2));
+                            tt.x = fmaf(tt.x, sc.x, sh.x); tt.y = fmaf(tt.y, sc.y, sh.y);
+                            tt.z = fmaf(tt.z, sc.z, sh.z); tt.w = fmaf(tt.w, sc.w, sh.w);
+                            if (c.post_relu) {
+                                tt.x = fmaxf(tt.x, 0.f); tt.y = fmaxf(tt.y, 0.f);
+                                tt.z = fmaxf(tt.z, 0.f); tt.w = fmaxf(tt.w, 0.f);
+                            }
+                            tt.x += ra[i].x + rb[i].x; tt.y += ra[i].y + rb[i].y;
+                            tt.z += ra[i].z + rb[i].z; tt.w += ra[i].w + rb[i].w;
+                            *reinterpret_cast<float4*>(c.out + (size_t)m * c.ldo + co) = tt;
+                        }
+                    }
+                } else {
+                    const int co = n0 + col0 + lane;
+                    const bool cok = lane < width && co < c.Cout;
+                    float sc = 1.f, sh = 0.f;
+                    if (cok && c.post_scale) {
+                        sc = __ldg(c.post_scale + co);
+                        sh = __ldg(c.post_shift + co);
+                    }
 #pragma unroll 8
-                for (int r = 0; r < 32; ++r) {
-                    const int m = mbase + r;
-                    if (cok && m < c.M) {
-                        float t = fmaf(tile[r * TS + lane], sc, sh);
-                        if (c.post_relu) t = fmaxf(t, 0.f);
-                        if (c.res0) t += __ldg(c.res0 + (size_t)m * c.ldr0 + co);
-                        if (c.res1) t += __ldg(c.res1 + (size_t)m * c.ldr1 + co);
-                        c.out[(size_t)m * c.ldo + co] = t;
+                    for (int r = 0; r < 32; ++r) {
+                        const int m = mbase + r;
+                        if (cok && m < c.M) {
+                            float tt = fmaf(tile[r * 32 + ((((lane >> 2) ^ (r & 7)) << 2) | (lane & 3))], sc, sh);
+                            if (c.post_relu) tt = fmaxf(tt, 0.f);
+                            if (c.res0) tt += __ldg(c.res0 + (size_t)m * c.ldr0 + co);
+                            if (c.res1) tt += __ldg(c.res1 + (size_t)m * c.ldr1 + co);
+                            c.out[(size_t)m * c.ldo + co] = tt;
+                        }
                     }
                 }
-            }
-            __syncwarp();
-        }
-    } else if (warp == WARP_TMA) {
-        // ======================= weight tiles via TMA =======================
-        if (lane == 0) {
-            const uint32_t tx = (uint32_t)(want_lo ? 2 : 1) * (uint32_t)b_tile_bytes;
-            const uint32_t tx_a = (uint32_t)(want_lo ? 2 : 1) * (uint32_t)A_TILE_BYTES;
-            for (int kb = 0; kb < P.n_kblocks; ++kb) {
-                const int s = kb % P.stages;
-                const uint32_t it = (uint32_t)(kb / P.stages);
-                mbar_wait(bar_empty0 + 8 * s, (it & 1) ^ 1);
-                const uint32_t full = bar_full0 + 8 * s;
-                // SHARE: K-blocks produced by the peer deliver their A tile as transaction bytes
-                mbar_arrive_expect_tx(full, tx + ((SHARE && (uint32_t)s != my_rank) ? tx_a : 0u));
-                const uint32_t b_hi = smem_u32(smem + (size_t)s * stage_bytes + 2 * A_TILE_BYTES);
-                const uint32_t b_lo = b_hi + (uint32_t)b_tile_bytes;
-                for (int sub = 0; sub < P.nsub; ++sub) {
-                    tma_load_2d(b_hi + (uint32_t)(sub * P.nw * 128), &map_hi, kb * BK, n0 + sub * P.nw, full);
-                    if (want_lo)
-                        tma_load_2d(b_lo + (uint32_t)(sub * P.nw * 128), &map_lo, kb * BK, n0 + sub * P.nw, full);
-                }
+                __syncwarp();
             }
         }
     } else {
-        // ======================= MMA issue (one thread) =======================
-        if (lane == 0) {
-            for (int kb = 0; kb < P.n_kblocks; ++kb) {
-                const int s = kb % P.stages;
-                const uint32_t it = (uint32_t)(kb / P.stages);
-                mbar_wait(bar_full0 + 8 * s, it & 1);
-                tc_fence_after();
-                const uint32_t a_hi = smem_u32(smem + (size_t)s * stage_bytes);
-                const uint32_t a_lo = a_hi + A_TILE_BYTES;
-                const uint32_t b_hi = a_hi + 2 * A_TILE_BYTES;
-                const uint32_t b_lo = b_hi + (uint32_t)b_tile_bytes;
-                for (int sub = 0; sub < P.nsub; ++sub) {
-                    const uint32_t d = tmem_base + (uint32_t)(sub * P.nw);
-                    const uint32_t bo = (uint32_t)(sub * P.nw * 128);
-#pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        const uint32_t ko = (uint32_t)(k * 32);      // 16 bf16 = 32 B along the swizzle row
-                        const uint32_t acc0 = (kb > 0 || k > 0) ? 1u : 0u;
-                        umma_bf16(d, make_desc(a_hi + ko), make_desc(b_hi + bo + ko), P.idesc, acc0);
-                        if (want_lo) {
-                            umma_bf16(d, make_desc(a_lo + ko), make_desc(b_hi + bo + ko), P.idesc, 1u);
-                            umma_bf16(d, make_desc(a_hi + ko), make_desc(b_lo + bo + ko), P.idesc, 1u);
+        reg_dec<REGS_CTRL>();
+        if (warp == WARP_TMA) {
+            // ======================= weight tiles via TMA =======================
+            if (lane == 0) {
+                const uint32_t tx = (uint32_t)(want_lo ? 2 : 1) * (uint32_t)b_tile_bytes;
+                const uint32_t tx_a = (uint32_t)(want_lo ? 2 : 1) * (uint32_t)A_TILE_BYTES;
+                int g = 0;
+                for (int t = blockIdx.x; t < P.n_mtiles; t += gridDim.x) {
+                    for (int kb = 0; kb < nkb; ++kb, ++g) {
+                        const int s = g % P.stages;
+                        const uint32_t it = (uint32_t)(g / P.stages);
+                        mbar_wait(bar_empty0 + 8 * s, (it & 1) ^ 1);
+                        const uint32_t full = bar_full0 + 8 * s;
+                        // SHARE: K-blocks produced by the peer deliver their A tile as transaction bytes
+                        mbar_arrive_expect_tx(full, tx + ((SHARE && (uint32_t)s != my_rank) ? tx_a : 0u));
+                        const uint32_t b_hi = smem_u32(smem + (size_t)s * stage_bytes + 2 * A_TILE_BYTES);
+                        const uint32_t b_lo = b_hi + (uint32_t)b_tile_bytes;
+                        for (int sub = 0; sub < P.nsub; ++sub) {
+                            tma_load_2d(b_hi + (uint32_t)(sub * P.nw * 128), &map_hi, kb * BK, n0 + sub * P.nw, full);
+                            if (want_lo)
+                                tma_load_2d(b_lo + (uint32_t)(sub * P.nw * 128), &map_lo, kb * BK, n0 + sub * P.nw, full);
                         }
                     }
                 }
-                if (SHARE) umma_commit_pair(bar_empty0 + 8 * s);   // both CTAs must release the stage
-                else umma_commit(bar_empty0 + 8 * s);              // frees this smem stage when the MMAs retire
             }
-            umma_commit(bar_tmem);                    // accumulators complete -> epilogue
+        } else if (warp == WARP_MMA) {
+            // ======================= MMA issue (one thread) =======================
+            if (lane == 0) {
+                int g = 0, ti = 0;
+                for (int t = blockIdx.x; t < P.n_mtiles; t += gridDim.x, ++ti) {
+                    const int acc = ti % P.nacc;
+                    const uint32_t acc_it = (uint32_t)(ti / P.nacc);
+                    mbar_wait(bar_tempty0 + 8 * acc, (acc_it & 1) ^ 1);      // epilogue drained this accumulator
+                    tc_fence_after();
+                    const uint32_t dacc = tmem_base + (uint32_t)(acc * P.acc_stride);
+                    for (int kb = 0; kb < nkb; ++kb, ++g) {
+                        const int s = g % P.stages;
+                        const uint32_t it = (uint32_t)(g / P.stages);
+                        mbar_wait(bar_full0 + 8 * s, it & 1);
+                        tc_fence_after();
+                        const uint32_t a_hi = smem_u32(smem + (size_t)s * stage_bytes);
+                        const uint32_t a_lo = a_hi + A_TILE_BYTES;
+                        const uint32_t b_hi = a_hi + 2 * A_TILE_BYTES;
+                        const uint32_t b_lo = b_hi + (uint32_t)b_tile_bytes;
+                        for (int sub = 0; sub < P.nsub; ++sub) {
+                            const uint32_t d = dacc + (uint32_t)(sub * P.nw);
+                            const uint32_t bo = (uint32_t)(sub * P.nw * 128);
+#pragma unroll
+                            for (int k = 0; k < BK / 16; ++k) {
+                                const uint32_t ko = (uint32_t)(k * 32);      // 16 bf16 = 32 B along the swizzle row
+                                const uint32_t acc0 = (kb > 0 || k > 0) ? 1u : 0u;
+                                umma_bf16(d, make_desc(a_hi + ko), make_desc(b_hi + bo + ko), P.idesc, acc0);
+                                if (want_lo) {
+                                    umma_bf16(d, make_desc(a_lo + ko), make_desc(b_hi + bo + ko), P.idesc, 1u);
+                                    umma_bf16(d, make_desc(a_hi + ko), make_desc(b_lo + bo + ko), P.idesc, 1u);
+                                }
+                            }
+                        }
+                        if (SHARE) umma_commit_pair(bar_empty0 + 8 * s);   // both CTAs must release the stage
+                        else umma_commit(bar_empty0 + 8 * s);              // frees this smem stage when the MMAs retire
+                    }
+                    umma_commit(bar_tfull0 + 8 * acc);                     // accumulator complete -> epilogue
+                }
+            }
         }
     }
     tc_fence_before();
@@ -693,14 +753,17 @@ int dh_launch_conv_tc(dh_ctx* ctx, const ConvParams& p, const dh_packed_w* packe
     tile_n(p.Cout, &P.bn_cta, &gy, &P.nsub, &P.nw);
     P.precision = (precision == 1) ? 1 : 3;
     P.ks = separable ? p.kh : 0;
+    P.acc_stride = (P.bn_cta + 31) / 32 * 32;
+    P.nacc = (2 * P.acc_stride <= 512) ? 2 : 1;
     int tm = 32;
-    while (tm < P.bn_cta) tm <<= 1;
+    while (tm < P.nacc * P.acc_stride) tm <<= 1;
     P.tmem_cols = tm;
+    P.n_mtiles = (p.M + BM - 1) / BM;
     // cute::UMMA::InstrDescriptor: c_format F32 [4,6)=1, a/b_format BF16 [7,10)/[10,13)=1, K-major A and B,
     // n_dim = N>>3 at [17,23), m_dim = M>>4 at [24,29)
     P.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.nw >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
     const int stage_bytes = 2 * A_TILE_BYTES + 2 * P.bn_cta * 128;
-    const int budget = 227 * 1024 - 1024 /*alignment*/ - 256 /*barriers*/;
+    const int budget = 227 * 1024 - 1024 /*alignment*/ - 256 /*barriers*/ - EPI_STAGE_BYTES;
     int stages = budget / stage_bytes;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     if (stages > P.n_kblocks) stages = P.n_kblocks;
@@ -709,7 +772,7 @@ int dh_launch_conv_tc(dh_ctx* ctx, const ConvParams& p, const dh_packed_w* packe
         return -1;
     }
     P.stages = stages;
-    const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
+    const size_t smem = (size_t)stages * stage_bytes + EPI_STAGE_BYTES + 1024 + 256;
 
     CUtensorMap map_hi, map_lo;
     if (!make_map(&map_hi, packed->hi, packed->k, packed->cout_pad, P.nw) ||
@@ -717,7 +780,11 @@ int dh_launch_conv_tc(dh_ctx* ctx, const ConvParams& p, const dh_packed_w* packe
         dh_set_error("dh_launch_conv_tc: cuTensorMapEncodeTiled failed");
         return -1;
     }
-    dim3 grid((p.M + BM - 1) / BM, gy);
+    // persistent: one CTA per SM; CTA (x, y) handles M-tiles x, x + gridDim.x, ... of N part y
+    int gx = ctx->num_sms / gy;
+    if (gx < 1) gx = 1;
+    if (gx > P.n_mtiles) gx = P.n_mtiles;
+    dim3 grid(gx, gy);
     cudaError_t e;
     // A-tile sharing across the two N-half CTAs (cluster 1x2x1): separable layers with Cout split in 2
     const bool share = separable && gy == 2 && stages == 2 && P.n_kblocks >= 2 && ctx->share_a;
