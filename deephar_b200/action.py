@@ -1,0 +1,195 @@
+"""B200-native drop-in for deephar/models/action.py::build_merge_model -- the CVPR'18 clip model
+(ReceptionNet pose estimation re-wired under TimeDistributed + PoseAR + GuidedVisAR action nets),
+2-D pose variant as used by exp/pennaction/eval_penn_ar_pe_merge.py:42-62.
+
+Signature, output order ([pose, visibility,] p1..p4, v1..v4, m: action.py:340-396) and weight
+names (backbone keeps the ReceptionNet layer names; PoseAR/, GuidedVisAR/ sub-models) follow the
+reference.  The 3-D variant (`pose_dim=3`) only has a stale script in the reference
+(exp/ntu/eval_ntu_ar_pe_merge.py:11 imports a module that does not exist) and is not built.
+"""
+from . import reception as R
+from .graph import Graph
+from .layers import (MaxPooling2D, UpSampling2D, act_conv, act_conv_bn, add, channel_slice,
+                     channel_softmax_2d, concatenate, conv_bn, conv_bn_act, frames_to_clip,
+                     global_max_min_pooling, kronecker_prod, mask_multiply, max_min_pooling,
+                     sepconv2d, softmax_lastaxis)
+
+
+def action_top(x, name=None):
+    """action.py:14-17."""
+    x = global_max_min_pooling(x)
+    return softmax_lastaxis(x, name=name)
+
+
+def build_act_pred_block(x, num_out, name=None, last=False, include_top=True):
+    """action.py:20-42."""
+    num_features = x.channels
+
+    ident = x
+    x = act_conv_bn(x, int(num_features / 2), (1, 1))
+    x = act_conv_bn(x, num_features, (3, 3))
+    x = add([ident, x])
+
+    ident = x
+    x1 = act_conv_bn(x, num_features, (3, 3))
+    x = max_min_pooling(x1, (2, 2))
+    action_hm = act_conv(x, num_out, (3, 3))
+    y = action_hm
+    if include_top:
+        y = action_top(y)
+
+    if not last:
+        action_hm = UpSampling2D(action_hm, (2, 2))
+        action_hm = act_conv_bn(action_hm, num_features, (3, 3))
+        x = add([ident, x1, action_hm])
+
+    return x, y
+
+
+def build_pose_model(y, p, num_actions, name='PoseAR', include_top=True, network_version='v1'):
+    """action.py:45-90 applied to clip tensors y (T,nj,dim), p (T,nj,1)."""
+    with y.g.scope(name):
+        x = mask_multiply(y, p)
+        if network_version == 'v1':
+            a = conv_bn_act(x, 8, (3, 1))
+            b = conv_bn_act(x, 16, (3, 3))
+            c = conv_bn_act(x, 24, (3, 5))
+            x = concatenate([a, b, c])
+            a = conv_bn(x, 56, (3, 3))
+            b = conv_bn(x, 32, (1, 1))
+            b = conv_bn(b, 56, (3, 3))
+            x = concatenate([a, b])
+            x = max_min_pooling(x, (2, 2))
+        elif network_version == 'v2':
+            a = conv_bn_act(x, 12, (3, 1))
+            b = conv_bn_act(x, 24, (3, 3))
+            c = conv_bn_act(x, 36, (3, 5))
+            x = concatenate([a, b, c])
+            a = conv_bn(x, 112, (3, 3))
+            b = conv_bn(x, 64, (1, 1))
+            b = conv_bn(b, 112, (3, 3))
+            x = concatenate([a, b])
+            x = max_min_pooling(x, (2, 2))
+        else:
+            raise Exception('Unkown network version "{}"'.format(network_version))
+
+        x, y1 = build_act_pred_block(x, num_actions, name='y1', include_top=include_top)
+        x, y2 = build_act_pred_block(x, num_actions, name='y2', include_top=include_top)
+        x, y3 = build_act_pred_block(x, num_actions, name='y3', include_top=include_top)
+        _, y4 = build_act_pred_block(x, num_actions, name='y4', include_top=include_top, last=True)
+    return [y1, y2, y3, y4]
+
+
+def build_visual_model(f, num_actions, name='GuidedVisAR', include_top=True):
+    """action.py:93-109 applied to the clip tensor f (T,nj,F)."""
+    with f.g.scope(name):
+        x = conv_bn(f, 256, (1, 1))
+        x = MaxPooling2D(x, (2, 2))
+        x, y1 = build_act_pred_block(x, num_actions, name='y1', include_top=include_top)
+        x, y2 = build_act_pred_block(x, num_actions, name='y2', include_top=include_top)
+        x, y3 = build_act_pred_block(x, num_actions, name='y3', include_top=include_top)
+        _, y4 = build_act_pred_block(x, num_actions, name='y4', include_top=include_top, last=True)
+    return [y1, y2, y3, y4]
+
+
+def _get_2d_pose_estimation_from_model(inp, num_joints, num_blocks, num_context_per_joint, ksize):
+    """action.py:112-203: the ReceptionNet layers re-wired so that only the last block regresses
+    the pose.  Layers are created in reception.build's order so the weight names are identical."""
+    x1 = R._stem(inp)
+    xb1 = R.build_reception_block(x1, name='rBlock1', ksize=ksize)
+    nfilt = xb1.channels
+    num_heatmaps = (num_context_per_joint + 1) * num_joints
+
+    x2 = R.build_sconv_block(xb1, name='SepConv1', ksize=ksize)
+    x3 = R.build_fremap_block(R.build_regmap_block(x2, num_heatmaps, name='RegMap1'), nfilt, name='fReMap1')
+    x = add([xb1, x2, x3])
+    for i in range(2, num_blocks):
+        t1 = R.build_reception_block(x, name='rBlock%d' % i, ksize=ksize)
+        t2 = R.build_sconv_block(t1, name='SepConv%d' % i, ksize=ksize)
+        t3 = R.build_fremap_block(R.build_regmap_block(t2, num_heatmaps, name='RegMap%d' % i), nfilt,
+                                  name='fReMap%d' % i)
+        x = add([t1, t2, t3])
+    x = R.build_reception_block(x, name='rBlock%d' % num_blocks, ksize=ksize)
+    x = R.build_sconv_block(x, name='SepConv%d' % num_blocks, ksize=ksize)
+    h = R.build_regmap_block(x, num_heatmaps, name='RegMap%d' % num_blocks)
+
+    # ys/yc/pc/Agg (alpha 0.8) = the same parameter-free head as reception.py:167-182
+    y, vis, _ = R.pose_regression_2d_context(h, num_joints, num_context_per_joint, 0.8)
+    # p = sjProb(4 * hs)  (action.py:200): 4 x the raw 2x2-window maximum
+    p = y.g.op('scale', [vis], vis.shape, {'value': 4.0})
+    hs = channel_slice(h, 0, num_joints)
+    hs = channel_softmax_2d(hs, name='td_ChannelSoftmax')                 # action.py:202-203
+    return y, p, hs, xb1
+
+
+def build_merge_model(model_pe,
+                      num_actions,
+                      input_shape,
+                      num_frames,
+                      num_joints,
+                      num_blocks,
+                      pose_dim=2,
+                      depth_maps=8,
+                      num_context_per_joint=2,
+                      pose_net_version='v1',
+                      output_poses=False,
+                      weighted_merge=True,
+                      ar_pose_weights=None,
+                      ar_visual_weights=None,
+                      full_trainable=False):
+    """action.py:319-400."""
+    from .model import Model
+
+    if pose_dim != 2:
+        raise NotImplementedError('only the 2-D merge model has a working script in the reference')
+    if ar_pose_weights is not None or ar_visual_weights is not None:
+        raise NotImplementedError('load the merged weight file with Model.load_weights instead')
+    ksize = getattr(model_pe, 'build_args', {}).get('ksize', (3, 3))
+
+    g = Graph('MergeModel')
+    g.frames_per_clip = int(num_frames)
+    inp = g.input(tuple(input_shape))
+    outputs = []
+
+    y, p, hs, xb1 = _get_2d_pose_estimation_from_model(inp, num_joints, num_blocks,
+                                                       num_context_per_joint, ksize)
+    n_backbone = len(g.weight_specs)
+    if g.weight_specs != model_pe.weight_specs[:n_backbone] or n_backbone != len(model_pe.weight_specs):
+        raise ValueError('model_pe does not match (num_joints, num_blocks, num_context_per_joint)')
+
+    if output_poses:
+        outputs.append(y)
+        outputs.append(p)
+
+    yc, pc = frames_to_clip(y), frames_to_clip(p)
+    out_pose = build_pose_model(yc, pc, num_actions, include_top=False, name='PoseAR',
+                                network_version=pose_net_version)
+
+    f = kronecker_prod(hs, xb1)
+    out_vis = build_visual_model(frames_to_clip(f), num_actions, include_top=False, name='GuidedVisAR')
+
+    for i in range(len(out_pose)):
+        outputs.append(action_top(out_pose[i], name='p%d' % (i + 1)))
+    for i in range(len(out_vis)):
+        outputs.append(action_top(out_vis[i], name='v%d' % (i + 1)))
+
+    pm = out_pose[-1]
+    vm = out_vis[-1]
+
+    def _heatmap_weighting(t):
+        """action.py:377-390: SeparableConv2D(C, (1,1)) initialised to identity (its weights are part of
+        the model's weight list, so a trained file may hold anything)."""
+        return sepconv2d(t, t.channels, (1, 1))
+
+    if weighted_merge:
+        pm = _heatmap_weighting(pm)
+        vm = _heatmap_weighting(vm)
+
+    m = add([pm, vm])
+    outputs.append(action_top(m, name='m'))
+
+    g.outputs = outputs
+    model = Model(g, calib_key='merge_j%d_b%d_k%d' % (num_joints, num_blocks, ksize[0]), name='MergeModel')
+    if getattr(model_pe, '_host_weights', None):
+        model._backbone_weights = dict(model_pe._host_weights)      # shared layers (Keras shares them)
+    return model

@@ -16,7 +16,7 @@ whole forward fits comfortably in HBM and micro-batches stay L2-resident.
 from collections import defaultdict
 
 CONV_OPS = ('conv', 'sepconv')
-DENSE_OUT_OPS = ('pose_regression_2d_context', 'pose_regression_2d', 'pose_regression_3d',
+DENSE_OUT_OPS = ('scale', 'pose_regression_2d_context', 'pose_regression_2d', 'pose_regression_3d',
                  'sam2d', 'kron', 'global_maxmin_softmax', 'mask_mul')
 
 
@@ -259,9 +259,18 @@ def compile_graph(g):
             kc = [u for u in users if u.op == 'keypoint_confidence']
             de = [u for u in users if u.op == 'depth_expect']
             kr = [u for u in users if u.op == 'kron']
-            if len(sa) != 1 or len(kc) != 1 or len(de) > 1 or len(sa) + len(kc) + len(de) + len(kr) != len(users) \
-                    or n.out.id in out_ids:
+            if len(sa) > 1 or len(kc) > 1 or len(de) > 1 or len(sa) + len(kc) + len(de) + len(kr) != len(users) \
+                    or n.out.id in out_ids or (de and not sa) or len(sa) != len(kc):
                 raise NotImplementedError('unsupported use of channel_softmax_2d output')
+            if not sa:
+                # probabilities only (merge model: softmax(hs) -> kronecker_prod, action.py:202,359):
+                # the kernel still needs somewhere to put (x, y) and the confidence -> scratch tensors
+                from .graph import Tensor
+                c_ = n.out.shape[2]
+                scratch = [Tensor(g, (1, c_, 2), n.out.kind, n, 1), Tensor(g, (1, c_, 1), n.out.kind, n, 2)]
+                emit('sam2d', [n.inputs[0]], scratch + [n.out], {'alpha': n.attrs['alpha'], 'depth': False,
+                                                                 'prob': True}, n.id)
+                continue
             pose_t, pos, ins = sa[0].out, max(sa[0].id, kc[0].id), [n.inputs[0]]
             sam_skip.update([sa[0].id, kc[0].id])
             if de:

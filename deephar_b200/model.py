@@ -106,7 +106,9 @@ class Model(object):
 
     def init_synthetic_weights(self, seed=1234):
         calib = load_calibration(self.calib_key) if self.calib_key else {}
-        self.set_weights(synthetic_weights(self.weight_specs, seed, calib))
+        table = synthetic_weights(self.weight_specs, seed, calib)
+        table.update(getattr(self, '_backbone_weights', {}))     # layers shared with another model
+        self.set_weights(table)
         return self
 
     def load_weights(self, path, by_name=False):
@@ -161,6 +163,11 @@ class Model(object):
                                                   hw[w['beta']], hw[w['mean']], hw[w['var']])
                     put('fold:' + bn['name'], scale)
                     put('shift:' + bn['name'], shift)
+        scales = [k for k in self.plan.kops if k.kind == 'scale']     # per-channel constant vectors
+        if scales:
+            cmax = max(4, max(k.ins[0].shape[2] for k in scales))
+            for val in sorted(set([0.0] + [float(k.attrs['value']) for k in scales])):
+                put('const:%r' % val, np.full(cmax, val, np.float32))
         flat = np.concatenate(chunks) if chunks else np.zeros(4, np.float32)
         self._dev = torch.from_numpy(flat).cuda()
         base = self._dev.data_ptr()
@@ -312,6 +319,11 @@ class Model(object):
                 a = k.attrs
                 args = (lib.dh_softargmax3d_f32, ctxh, C.byref(view(k.ins[0])), a['num_joints'],
                         a['depth_maps'], dense_ptr(k.outs[0]), dense_ptr(k.outs[1]))
+            elif kd == 'scale':
+                key = 'const:%r' % float(k.attrs['value'])
+                arr = (_ffi.dh_view * 1)(view(k.ins[0]))
+                b.keep.append(arr)
+                args = (lib.dh_add_n_f32, ctxh, arr, 1, P[key], P['const:0.0'], 0, C.byref(view(k.outs[0])))
             elif kd == 'sam2d':
                 a = k.attrs
                 dv = C.byref(view(k.ins[1])) if a['depth'] else nullv

@@ -200,4 +200,7 @@ def build(input_shape, num_joints, dim,
 
     g.outputs = outputs
     calib_key = 'reception_j%d_d%d_c%s_k%d' % (num_joints, dim, num_context_per_joint, ksize[0])
-    return Model(g, calib_key=calib_key)
+    m = Model(g, calib_key=calib_key)
+    m.build_args = dict(num_joints=num_joints, dim=dim, num_context_per_joint=num_context_per_joint,
+                        num_blocks=num_blocks, ksize=tuple(ksize))
+    return m

@@ -7,7 +7,7 @@ import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
-from oracle import ops_torch, reception, spnet, synth  # noqa: E402
+from oracle import action, ops_torch, reception, spnet, synth  # noqa: E402
 import numpy as np  # noqa: E402
 
 OUT = os.path.join('deephar_b200', 'synth_calib')
@@ -50,3 +50,9 @@ if __name__ == '__main__':
                               action_pyramids=[1, 2], num_levels=4, pose_replica=True, num_pose_features=160,
                               num_visual_features=160)
     calibrate_spnet('spnet_j16_d2_p2_a1-2_r1_f160', small, 128, 2)
+    cal = synth.Calibrator(1234)
+    x = np.stack([synth.synth_frames(16, 128, 128, seed=70 + i) for i in range(2)])
+    action.forward(ops_torch, cal, x, 15, 16, 4, num_context_per_joint=2, ksize=(5, 5))
+    with open(os.path.join(OUT, 'merge_j16_b4_k5.json'), 'w') as f:
+        json.dump(cal.calib, f, indent=0, sort_keys=True)
+    print('merge_j16_b4_k5', len(cal.calib), 'entries')
