@@ -40,6 +40,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "memory");
     } while (!ok);
 }
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                  "l"(src), "r"(bytes), "r"(bar)
@@ -66,10 +71,15 @@ __global__ void __launch_bounds__(512, 1) sam_stream_kernel(Params p) {
     float* ring = reinterpret_cast<float*>(smem_raw);
     float* s_red = ring + (size_t)STAGES * p.chunk_floats;           // [4][W][C] : m, s, sy, wmax
     float* s_res = s_red + 4 * p.W * p.C;                            // [3][C]    : x, y, conf
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_res + 3 * p.C + ((3 * p.C) & 1));
+    float* s_gy = s_res + 3 * p.C;                                   // [H] : linspace(0,1,H) as float32
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_gy + p.H + ((3 * p.C + p.H) & 1));
     const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + STAGES);
     const int ncons_warps = (NCONS + 31) >> 5;
 
+    {
+        const double ystep = p.H > 1 ? 1.0 / (double)(p.H - 1) : 0.0;   // np.linspace(0,1,H) -> float32
+        for (int i = tid; i < p.H; i += blockDim.x) s_gy[i] = (p.H > 1 && i == p.H - 1) ? 1.0f : (float)(i * ystep);
+    }
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(bar_full + 8 * s, 1);
@@ -101,18 +111,20 @@ __global__ void __launch_bounds__(512, 1) sam_stream_kernel(Params p) {
     }
 
     // ===================== consumers =====================
+    // e = ex2((v - m) * log2e): the difference is formed first (exact for nearby values), then one
+    // packed multiply and one MUFU.EX2 per element; sums use packed f32x2 adds / FMAs.
     const int c = tid / Q, q = tid - c * Q;
     const int lane = tid & 31;
     const bool has_right = c + 1 < p.W;
-    const float gx = (p.W > 1) ? (c == p.W - 1 ? 1.0f : (float)(c * (1.0 / (double)(p.W - 1)))) : 0.f;
-    const double ystep = p.H > 1 ? 1.0 / (double)(p.H - 1) : 0.0;
+    constexpr float LOG2E = 1.4426950408889634f;
     int chunk_idx = 0;
     for (int fi = 0; fi < frames_mine; ++fi) {
         const int f = blockIdx.x + fi * gridDim.x;
-        float m[4] = {-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
-        float s[4] = {0.f, 0.f, 0.f, 0.f}, sy[4] = {0.f, 0.f, 0.f, 0.f};
+        float m2[4] = {-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
+        float2 s01 = make_float2(0.f, 0.f), s23 = make_float2(0.f, 0.f);
+        float2 sy01 = make_float2(0.f, 0.f), sy23 = make_float2(0.f, 0.f);
         float wm[4] = {-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
-        float4 pv = make_float4(0.f, 0.f, 0.f, 0.f), pr = make_float4(0.f, 0.f, 0.f, 0.f);   // previous row (own, right)
+        float2 pp01 = make_float2(0.f, 0.f), pp23 = make_float2(0.f, 0.f);   // previous row: own + right
         for (int ck = 0; ck < p.chunks_per_frame; ++ck, ++chunk_idx) {
             const int st = chunk_idx % STAGES;
             const uint32_t it = (uint32_t)(chunk_idx / STAGES);
@@ -127,41 +139,53 @@ __global__ void __launch_bounds__(512, 1) sam_stream_kernel(Params p) {
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_empty + 8 * st);      // this warp is done with the stage
-            // chunk maxima -> one rescale per chunk
+            // chunk maxima -> at most one rescale per chunk
             float cm[4] = {v[0].x, v[0].y, v[0].z, v[0].w};
 #pragma unroll
             for (int r = 1; r < ROWS_PER_CHUNK; ++r) {
                 cm[0] = fmaxf(cm[0], v[r].x); cm[1] = fmaxf(cm[1], v[r].y);
                 cm[2] = fmaxf(cm[2], v[r].z); cm[3] = fmaxf(cm[3], v[r].w);
             }
+            float sc[4] = {1.f, 1.f, 1.f, 1.f};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                if (cm[e] > m[e]) {
-                    const float sc = __expf(m[e] - cm[e]);
-                    s[e] *= sc;
-                    sy[e] *= sc;
-                    m[e] = cm[e];
+                if (cm[e] > m2[e]) {
+                    sc[e] = ex2_approx((m2[e] - cm[e]) * LOG2E);
+                    m2[e] = cm[e];
                 }
             }
+            s01.x *= sc[0]; s01.y *= sc[1]; s23.x *= sc[2]; s23.y *= sc[3];
+            sy01.x *= sc[0]; sy01.y *= sc[1]; sy23.x *= sc[2]; sy23.y *= sc[3];
+            const float2 nm01 = make_float2(-m2[0], -m2[1]), nm23 = make_float2(-m2[2], -m2[3]);
+            const float2 l2 = make_float2(LOG2E, LOG2E);
 #pragma unroll
             for (int r = 0; r < ROWS_PER_CHUNK; ++r) {
                 const int row = ck * ROWS_PER_CHUNK + r;
-                const float gy = (p.H > 1 && row == p.H - 1) ? 1.0f : (float)(row * ystep);
-                const float e0 = __expf(v[r].x - m[0]), e1 = __expf(v[r].y - m[1]);
-                const float e2 = __expf(v[r].z - m[2]), e3 = __expf(v[r].w - m[3]);
-                s[0] += e0; s[1] += e1; s[2] += e2; s[3] += e3;
-                sy[0] = fmaf(e0, gy, sy[0]); sy[1] = fmaf(e1, gy, sy[1]);
-                sy[2] = fmaf(e2, gy, sy[2]); sy[3] = fmaf(e3, gy, sy[3]);
-                if (has_right && row > 0) {       // 2x2 window with top-left corner (row-1, c), raw values
-                    wm[0] = fmaxf(wm[0], (pv.x + pr.x) + (v[r].x + vr[r].x));
-                    wm[1] = fmaxf(wm[1], (pv.y + pr.y) + (v[r].y + vr[r].y));
-                    wm[2] = fmaxf(wm[2], (pv.z + pr.z) + (v[r].z + vr[r].z));
-                    wm[3] = fmaxf(wm[3], (pv.w + pr.w) + (v[r].w + vr[r].w));
+                const float gy = s_gy[row];
+                const float2 a01 = __fmul2_rn(__fadd2_rn(make_float2(v[r].x, v[r].y), nm01), l2);
+                const float2 a23 = __fmul2_rn(__fadd2_rn(make_float2(v[r].z, v[r].w), nm23), l2);
+                const float2 e01 = make_float2(ex2_approx(a01.x), ex2_approx(a01.y));
+                const float2 e23 = make_float2(ex2_approx(a23.x), ex2_approx(a23.y));
+                s01 = __fadd2_rn(s01, e01);
+                s23 = __fadd2_rn(s23, e23);
+                const float2 g2 = make_float2(gy, gy);
+                sy01 = __ffma2_rn(e01, g2, sy01);
+                sy23 = __ffma2_rn(e23, g2, sy23);
+                // 2x2 window with top-left corner (row-1, c), raw values: (own + right) of both rows
+                const float2 cp01 = __fadd2_rn(make_float2(v[r].x, v[r].y), make_float2(vr[r].x, vr[r].y));
+                const float2 cp23 = __fadd2_rn(make_float2(v[r].z, v[r].w), make_float2(vr[r].z, vr[r].w));
+                if (has_right && row > 0) {
+                    const float2 w01 = __fadd2_rn(pp01, cp01), w23 = __fadd2_rn(pp23, cp23);
+                    wm[0] = fmaxf(wm[0], w01.x); wm[1] = fmaxf(wm[1], w01.y);
+                    wm[2] = fmaxf(wm[2], w23.x); wm[3] = fmaxf(wm[3], w23.y);
                 }
-                pv = v[r];
-                pr = vr[r];
+                pp01 = cp01;
+                pp23 = cp23;
             }
         }
+        const float m[4] = {m2[0], m2[1], m2[2], m2[3]};
+        const float s[4] = {s01.x, s01.y, s23.x, s23.y};
+        const float sy[4] = {sy01.x, sy01.y, sy23.x, sy23.y};
         // ---- combine the W columns of every channel ----
         const int WC = p.W * p.C;
 #pragma unroll
@@ -217,7 +241,6 @@ __global__ void __launch_bounds__(512, 1) sam_stream_kernel(Params p) {
         }
         // s_red / s_res are rewritten only after the next frame's first bar.sync pair -> safe
     }
-    (void)gx;
 }
 
 }  // namespace sstream
@@ -231,7 +254,7 @@ bool dh_sam_stream_supported(const dh_view* h, int conf_on_prob, float alpha, bo
     if (ncons > 480 || ncons < 64 || (ncons & 31)) return false;
     const size_t chunk_bytes = (size_t)sstream::ROWS_PER_CHUNK * h->w * h->c * 4;
     if (chunk_bytes % 16 != 0) return false;
-    const size_t smem = sstream::STAGES * chunk_bytes + (size_t)(4 * h->w * h->c + 3 * h->c + 2) * 4 + 2 * sstream::STAGES * 8 + 128;
+    const size_t smem = sstream::STAGES * chunk_bytes + (size_t)(4 * h->w * h->c + 3 * h->c + h->h + 2) * 4 + 2 * sstream::STAGES * 8 + 128;
     if (smem > 227 * 1024) return false;
     if ((size_t)h->h * h->w * h->c * 4 < 64 * 1024) return false;    // small maps: the staged kernel is fine
     return true;
@@ -248,7 +271,7 @@ int dh_sam_stream_launch(dh_ctx* ctx, const dh_view* h, int nj, int n_ctx, float
     p.chunk_floats = ROWS_PER_CHUNK * h->w * h->c;
     const int ncons = h->w * (h->c >> 2);
     const int threads = ((ncons + 31) / 32) * 32 + 32;
-    const size_t smem = (size_t)STAGES * p.chunk_floats * 4 + (size_t)(4 * h->w * h->c + 3 * h->c + 2) * 4 +
+    const size_t smem = (size_t)STAGES * p.chunk_floats * 4 + (size_t)(4 * h->w * h->c + 3 * h->c + h->h + 2) * 4 +
                         2 * STAGES * 8 + 128;
     cudaError_t e = cudaFuncSetAttribute(sam_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {

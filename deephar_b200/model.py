@@ -411,16 +411,42 @@ class Model(object):
         for t in self.graph.outputs:
             shp = self._keras_shape(t, n if t.kind == 'clip' or T == 1 else n * T)
             res.append(torch.empty(shp, dtype=torch.float32).pin_memory())
-        for i in range(0, n, batch_size):
-            j = min(i + batch_size, n)
+        # The host->device copy of batch k+1 runs on a side stream while batch k computes
+        # (two device staging buffers; events order copy -> compute -> buffer reuse).
+        main = torch.cuda.current_stream()
+        if getattr(self, '_copy_stream', None) is None:
+            self._copy_stream = torch.cuda.Stream()
+        copy_stream = self._copy_stream
+        spans = [(i, min(i + batch_size, n)) for i in range(0, n, batch_size)]
+        dev = [None, None]
+        ready = [torch.cuda.Event(), torch.cuda.Event()]
+        consumed = [torch.cuda.Event(), torch.cuda.Event()]
+
+        def issue_copy(k):
+            i, j = spans[k]
+            slot = k & 1
             if pinned:
-                xb = xt[i:j].cuda(non_blocking=True)
+                src = xt[i:j]
             else:
-                st = self._stage[:(j - i) * item].view((j - i,) + tuple(x.shape[1:]))
-                torch.cuda.current_stream().synchronize()     # staging buffer reuse
-                st.copy_(xt[i:j])
-                xb = st.cuda(non_blocking=True)
-            outs = self.forward_device(xb)
+                copy_stream.synchronize()                     # pinned staging buffer reuse
+                src = self._stage[:(j - i) * item].view((j - i,) + tuple(x.shape[1:]))
+                src.copy_(xt[i:j])
+            with torch.cuda.stream(copy_stream):
+                if k >= 2:
+                    copy_stream.wait_event(consumed[slot])    # compute of batch k-2 has read the buffer
+                if dev[slot] is None or dev[slot].shape != src.shape:
+                    dev[slot] = torch.empty(src.shape, dtype=torch.float32, device='cuda')
+                dev[slot].copy_(src, non_blocking=True)
+                ready[slot].record(copy_stream)
+
+        issue_copy(0)
+        for k, (i, j) in enumerate(spans):
+            slot = k & 1
+            if k + 1 < len(spans):
+                issue_copy(k + 1)
+            main.wait_event(ready[slot])
+            outs = self.forward_device(dev[slot])
+            consumed[slot].record(main)
             for r, o in zip(res, outs):
                 r[i:j].copy_(o, non_blocking=True)
         torch.cuda.current_stream().synchronize()
