@@ -45,6 +45,7 @@ extern "C" int dh_ctx_create(dh_ctx** out, int device) {
     c->workspace_bytes = 0;
     c->last_conv_path = 0;
     c->share_a = 1;
+    c->sep_tma = 1;
     *out = c;
     return 0;
 }
@@ -64,6 +65,7 @@ extern "C" int64_t dh_launch_count(dh_ctx* ctx, int reset) {
 extern "C" int dh_set_option(dh_ctx* ctx, const char* name, int value) {
     DH_CHECK_ARG(ctx && name, "dh_set_option: NULL argument");
     if (!strcmp(name, "share_a")) { ctx->share_a = value; return 0; }
+    if (!strcmp(name, "sep_tma")) { ctx->sep_tma = value; return 0; }
     dh_set_error("dh_set_option: unknown option %s", name);
     return -1;
 }

@@ -33,6 +33,13 @@ extern "C" int dh_sepconv2d_f32(dh_ctx* ctx, const dh_view* x, const float* w_dw
     p.w = w_pw;
     p.w_dw = w_dw;
     cudaStream_t s = (cudaStream_t)stream;
+    if (packed_pw && packed_pw->hi && dh_tc_supported(p, packed_pw, true) && dh_sep_tma_supported(ctx, p, packed_pw)) {
+        p.K = p.Cin;
+        rc = dh_launch_sep_tma(ctx, p, packed_pw, d->precision, s);
+        if (rc) return rc;
+        ctx->last_conv_path = 2;
+        DH_LAUNCH_EPILOGUE(ctx, 1);
+    }
     if (packed_pw && packed_pw->hi && dh_tc_supported(p, packed_pw, true)) {
         p.K = p.Cin;
         rc = dh_launch_conv_tc(ctx, p, packed_pw, true, d->precision, s);

@@ -22,6 +22,10 @@ int dh_fill_conv_params(ConvParams* p, const dh_view* x, const dh_conv_desc* d, 
 void dh_launch_conv_simt(const ConvParams& p, cudaStream_t s);
 void dh_launch_depthwise_simt(const ConvParams& p, float* tmp, int num_sms, cudaStream_t s);
 
+// TMA-staged fused separable kernel (conv_sep.cu)
+bool dh_sep_tma_supported(const dh_ctx* ctx, const ConvParams& p, const dh_packed_w* packed);
+int dh_launch_sep_tma(dh_ctx* ctx, const ConvParams& p, const dh_packed_w* packed, int precision, cudaStream_t s);
+
 // tensor-core path (conv_tc.cu). Returns true if it took the op.
 bool dh_tc_supported(const ConvParams& p, const dh_packed_w* packed, bool separable);
 int dh_launch_conv_tc(dh_ctx* ctx, const ConvParams& p, const dh_packed_w* packed, bool separable,

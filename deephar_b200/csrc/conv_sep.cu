@@ -1,0 +1,422 @@
+// Fused SeparableConv2D, TMA-staged variant (the hot kernel of the ReceptionNet / SPNet stacks).
+//
+// replaces: Activation('relu') -> SeparableConv2D(kxk, same) -> BatchNormalization -> add
+// (deephar/layers.py:288-301, models/reception.py:43-59) -- depthwise + pointwise + BN + residual
+// in ONE kernel; the depthwise result never leaves the SM.
+//
+// Per 128-pixel tile and 32-channel K-block:
+//   patch : the zero-padded input window (tile rows + halo) x 32 channels, fp32, loaded by ONE 4-D TMA
+//           (cp.async.bulk.tensor.4d over the NHWC tensor; out-of-bounds coordinates are zero filled,
+//           which IS the TF 'SAME' padding since the prologue here is ReLU-only) into shared memory;
+//   A     : depthwise kxk on CUDA cores from the patch: each thread owns 2 channels x a 4x4 pixel
+//           block, taps in registers, packed FFMA2, shared-memory loads with immediate offsets and no
+//           bounds logic; result split into bf16 hi/lo and stored in the 64B-swizzled K-major UMMA layout;
+//   W     : bf16 hi/lo pointwise weight tiles by 2-D TMA (64B swizzle);
+//   D     : fp32 in TMEM, tcgen05.mma kind::f16, three MMAs per k-step (bf16x3, see conv_tc.cu);
+//   epilogue: shared with conv_tc.cu (tc_common.cuh).
+// Roles: warps 0-3 / 4-7 = two producer warpgroups working on alternate K-blocks (each with its own
+// patch buffer), warps 8-11 epilogue, warp 12 weight TMA, warp 13 MMA issue, warp 14 patch TMA.
+// Cout = 576 layers run as 2-CTA clusters: CTA r produces the K-blocks of stage r and pushes the
+// finished A tile to its peer over DSMEM (same protocol as conv_tc.cu).
+#include "tc_common.cuh"
+
+namespace tcs {
+using namespace tc;
+
+constexpr int SBK = 32;                    // channels (bf16 K elements) per K-block = one 64-byte swizzle row
+constexpr int A_BYTES = BM * 64;           // 8 KB per (hi | lo)
+constexpr int NWG = 128;                   // threads per producer warpgroup
+constexpr int WARP_PATCH = 14;
+
+struct SepParams {
+    TcParams t;
+    int patch_stride;       // bytes between the two patch buffers (>= patch_bytes, 1024-aligned)
+    int patch_bytes;
+    int ry, fn;             // tile rows per frame, frames per tile
+};
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
+                                            uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+        : "memory");
+}
+
+// K-major, 64-byte swizzle UMMA descriptor: SBO = 512 B (8 rows x 64 B), layout SWIZZLE_64B = 4.
+__device__ __forceinline__ uint64_t make_desc64(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) |
+           (4ull << 61);
+}
+// byte offset of element (row, k) inside a [rows][32 bf16] 64B-swizzled K-major tile (Swizzle<2,4,3>)
+__device__ __forceinline__ uint32_t swz64(int row, int k) {
+    return (uint32_t)(row * 64 + ((((k >> 3) ^ ((row >> 1) & 3)) << 4) | ((k & 7) << 1)));
+}
+
+// use `it` (0,1,2,...) of stage s may start once use it-1 has been consumed
+__device__ __forceinline__ void wait_stage_free(uint32_t bar_empty0, int s, uint32_t it) {
+    if (it >= 1) mbar_wait(bar_empty0 + 16 * s + 8 * ((it - 1) & 1), ((it - 1) >> 1) & 1);
+}
+
+template <int KS, int TW, bool SHARE>
+__global__ void __launch_bounds__(NTHREADS, 1)
+sep_tma_kernel(const __grid_constant__ SepParams SP, const __grid_constant__ CUtensorMap map_hi,
+               const __grid_constant__ CUtensorMap map_lo, const __grid_constant__ CUtensorMap map_x) {
+    constexpr int PAD = KS / 2;
+    constexpr int PC = TW + 2 * PAD;          // patch columns
+    constexpr int NR = 4 + KS - 1;            // input rows / cols per 4x4 block
+    const TcParams& P = SP.t;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const bool want_lo = P.precision == 3;
+    const int b_bytes = P.bn_cta * 64;                       // per (hi | lo)
+    const int stage_bytes = 2 * A_BYTES + 2 * b_bytes;
+    uint8_t* patch0 = smem + 2 * stage_bytes;
+    uint8_t* epi_stage = patch0 + 2 * SP.patch_stride;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage + EPI_STAGE_BYTES);
+    // bars: full[2] | empty[2 stages][2] | pfull[2] | pempty[2] | tfull[2] | tempty[2]
+    // empty[s][u & 1] is signalled when use u of stage s has been consumed by the MMAs.  Two barriers per
+    // stage, alternating by use: in the cluster variant the two producer warpgroups write the SAME stage on
+    // alternate uses, so with one barrier each warpgroup would skip every other phase -- and an mbarrier
+    // parity wait is only meaningful one phase ahead.  With two, every waiter sees consecutive phases.
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+    const uint32_t bar_full0 = smem_u32(bars), bar_empty0 = smem_u32(bars + 2), bar_pfull0 = smem_u32(bars + 6),
+                   bar_pempty0 = smem_u32(bars + 8), bar_tfull0 = smem_u32(bars + 10),
+                   bar_tempty0 = smem_u32(bars + 12);
+    const int n0 = blockIdx.y * P.bn_cta;
+    const int nkb = P.n_kblocks;
+    const uint32_t my_rank = SHARE ? cluster_ctarank() : 0u;
+
+    if (warp == WARP_TMA && lane == 0) {
+        tma_prefetch_desc(&map_hi);
+        if (want_lo) tma_prefetch_desc(&map_lo);
+        tma_prefetch_desc(&map_x);
+        for (int s = 0; s < 2; ++s) {
+            if (SHARE) {
+                mbar_init(bar_full0 + 8 * s, (uint32_t)s == my_rank ? 2u : 1u);   // own: TMA thread + elected producer
+                mbar_init(bar_empty0 + 16 * s, 2);                                 // MMA commits of both CTAs
+                mbar_init(bar_empty0 + 16 * s + 8, 2);
+            } else {
+                mbar_init(bar_full0 + 8 * s, NWG + 1);
+                mbar_init(bar_empty0 + 16 * s, 1);
+                mbar_init(bar_empty0 + 16 * s + 8, 1);
+            }
+            mbar_init(bar_pfull0 + 8 * s, 1);
+            mbar_init(bar_pempty0 + 8 * s, NWG);
+            mbar_init(bar_tfull0 + 8 * s, 1);
+            mbar_init(bar_tempty0 + 8 * s, NEPI);
+        }
+        fence_barrier_init();
+    }
+    if (warp == WARP_MMA) tmem_alloc(smem_u32(tmem_slot), (uint32_t)P.tmem_cols);
+    tc_fence_before();
+    if (SHARE) cluster_sync_all(); else __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int tiles_mine = ((int)P.n_mtiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int total_g = tiles_mine * nkb;       // K-blocks this CTA's MMA consumes
+    // own K-blocks (the ones this CTA produces): SHARE: g = 2j + rank ; else g = j
+    const int n_own = SHARE ? (total_g - (int)my_rank + 1) / 2 : total_g;
+
+    if (warp < WARP_EPI0) {
+        // ======================= depthwise producers (two warpgroups) =======================
+        reg_inc<REGS_PROD>();
+        const ConvParams& c = P.c;
+        const int w = warp >> 2;                       // warpgroup 0 | 1 -> patch buffer w, own K-blocks j = w, w+2, ...
+        const int tw = tid & (NWG - 1);
+        const int cp = tw & 15;                        // channel pair inside the 32-channel K-block
+        const int blk = tw >> 4;                       // 4x4 pixel block inside the 128-pixel tile
+        constexpr int XB = TW / 4;
+        const int strip = blk / XB, xb = blk - strip * XB;
+        const int fn = (strip * 4) / SP.ry, ry = (strip * 4) - fn * SP.ry;
+        const int prr = SP.ry + 2 * PAD;               // patch rows per frame
+        const float* pbase = reinterpret_cast<const float*>(patch0 + (size_t)w * SP.patch_stride) +
+                             ((size_t)((fn * prr + ry) * PC + xb * 4)) * SBK + cp * 2;
+        const int row0 = strip * 4 * TW + xb * 4;      // tile-local pixel of output (o = 0, q = 0)
+        const float lowb = c.pre_relu ? 0.f : -3.402823466e38f;
+        const uint32_t pfull = bar_pfull0 + 8 * w, pempty = bar_pempty0 + 8 * w;
+        for (int j = w; j < n_own; j += 2) {
+            const int g = SHARE ? 2 * j + (int)my_rank : j;
+            const int ti = g / nkb, kb = g - ti * nkb;
+            const int ch = kb * SBK + cp * 2;
+            float2 wt[KS][KS];
+            const float* wp = c.w_dw + ch;
+#pragma unroll
+            for (int a = 0; a < KS; ++a)
+#pragma unroll
+                for (int b = 0; b < KS; ++b)
+                    wt[a][b] = __ldg(reinterpret_cast<const float2*>(wp + (size_t)(a * KS + b) * c.Cin));
+            float2 acc[4][4];
+#pragma unroll
+            for (int o = 0; o < 4; ++o)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[o][q] = make_float2(0.f, 0.f);
+
+            mbar_wait(pfull, (uint32_t)((j >> 1) & 1));
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+                float2 in[NR];
+#pragma unroll
+                for (int q = 0; q < NR; ++q) {
+                    float2 v = *reinterpret_cast<const float2*>(pbase + (r * PC + q) * SBK);
+                    in[q] = make_float2(fmaxf(v.x, lowb), fmaxf(v.y, lowb));
+                }
+#pragma unroll
+                for (int o = 0; o < 4; ++o) {
+                    const int ky = r - o;          // compile-time after unrolling
+                    if (ky >= 0 && ky < KS) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+#pragma unroll
+                            for (int kx = 0; kx < KS; ++kx) acc[o][q] = __ffma2_rn(wt[ky][kx], in[q + kx], acc[o][q]);
+                    }
+                }
+            }
+            mbar_arrive(pempty);                       // patch buffer may be refilled
+
+            const int s = g & 1;
+            const uint32_t it = (uint32_t)(g >> 1);
+            wait_stage_free(bar_empty0, s, it);
+            uint8_t* a_hi = smem + (size_t)s * stage_bytes;
+            uint8_t* a_lo = a_hi + A_BYTES;
+#pragma unroll
+            for (int o = 0; o < 4; ++o)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    uint32_t hi, lo;
+                    split2(acc[o][q].x, acc[o][q].y, hi, lo);
+                    const uint32_t off = swz64(row0 + o * TW + q, cp * 2);
+                    *reinterpret_cast<uint32_t*>(a_hi + off) = hi;
+                    if (want_lo) *reinterpret_cast<uint32_t*>(a_lo + off) = lo;
+                }
+            fence_proxy_async();
+            if (SHARE) {
+                asm volatile("bar.sync %0, %1;" ::"r"(1 + w), "r"(NWG) : "memory");
+                if (tw == 0) {
+                    mbar_arrive(bar_full0 + 8 * s);
+                    const uint32_t peer = my_rank ^ 1u;
+                    const uint32_t peer_full = mapa_peer(bar_full0 + 8 * s, peer);
+                    bulk_s2peer(mapa_peer(smem_u32(a_hi), peer), smem_u32(a_hi), A_BYTES, peer_full);
+                    if (want_lo) bulk_s2peer(mapa_peer(smem_u32(a_lo), peer), smem_u32(a_lo), A_BYTES, peer_full);
+                }
+            } else {
+                mbar_arrive(bar_full0 + 8 * s);
+            }
+        }
+    } else if (warp < WARP_TMA) {
+        // ======================= epilogue =======================
+        reg_inc<REGS_EPI>();
+        run_epilogue(P, epi_stage, tmem_base, bar_tfull0, bar_tempty0, n0, warp, lane);
+    } else {
+        reg_dec<REGS_CTRL>();
+        if (warp == WARP_TMA) {
+            // ======================= weight tiles via TMA =======================
+            if (lane == 0) {
+                const uint32_t tx = (uint32_t)(want_lo ? 2 : 1) * (uint32_t)b_bytes;
+                const uint32_t tx_a = (uint32_t)(want_lo ? 2 : 1) * (uint32_t)A_BYTES;
+                for (int g = 0; g < total_g; ++g) {
+                    const int ti = g / nkb, kb = g - ti * nkb;
+                    const int s = g & 1;
+                    const uint32_t it = (uint32_t)(g >> 1);
+                    wait_stage_free(bar_empty0, s, it);
+                    const uint32_t full = bar_full0 + 8 * s;
+                    mbar_arrive_expect_tx(full, tx + ((SHARE && (uint32_t)s != my_rank) ? tx_a : 0u));
+                    const uint32_t b_hi = smem_u32(smem + (size_t)s * stage_bytes + 2 * A_BYTES);
+                    const uint32_t b_lo = b_hi + (uint32_t)b_bytes;
+                    for (int sub = 0; sub < P.nsub; ++sub) {
+                        tma_load_2d(b_hi + (uint32_t)(sub * P.nw * 64), &map_hi, kb * SBK, n0 + sub * P.nw, full);
+                        if (want_lo)
+                            tma_load_2d(b_lo + (uint32_t)(sub * P.nw * 64), &map_lo, kb * SBK, n0 + sub * P.nw, full);
+                    }
+                }
+            }
+        } else if (warp == WARP_PATCH) {
+            // ======================= input patches via 4-D TMA =======================
+            if (lane == 0) {
+                const ConvParams& c = P.c;
+                for (int j = 0; j < n_own; ++j) {
+                    const int g = SHARE ? 2 * j + (int)my_rank : j;
+                    const int ti = g / nkb, kb = g - ti * nkb;
+                    const int t = blockIdx.x + ti * gridDim.x;
+                    const int w = j & 1;
+                    mbar_wait(bar_pempty0 + 8 * w, (uint32_t)(((j >> 1) & 1) ^ 1));
+                    const int grow = (t * BM) / TW;                 // global row index (n*H + y) of the tile's first row
+                    const int nf = grow / c.H, y0 = grow - nf * c.H;
+                    const uint32_t pf = bar_pfull0 + 8 * w;
+                    mbar_arrive_expect_tx(pf, (uint32_t)SP.patch_bytes);
+                    tma_load_4d(smem_u32(patch0 + (size_t)w * SP.patch_stride), &map_x, kb * SBK, -PAD, y0 - PAD, nf, pf);
+                }
+            }
+        } else if (warp == WARP_MMA) {
+            // ======================= MMA issue (one thread) =======================
+            if (lane == 0) {
+                int g = 0;
+                for (int ti = 0; ti < tiles_mine; ++ti) {
+                    const int acc = ti % P.nacc;
+                    const uint32_t acc_it = (uint32_t)(ti / P.nacc);
+                    mbar_wait(bar_tempty0 + 8 * acc, (acc_it & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t dacc = tmem_base + (uint32_t)(acc * P.acc_stride);
+                    for (int kb = 0; kb < nkb; ++kb, ++g) {
+                        const int s = g & 1;
+                        const uint32_t it = (uint32_t)(g >> 1);
+                        mbar_wait(bar_full0 + 8 * s, it & 1);
+                        tc_fence_after();
+                        const uint32_t a_hi = smem_u32(smem + (size_t)s * stage_bytes);
+                        const uint32_t a_lo = a_hi + A_BYTES;
+                        const uint32_t b_hi = a_hi + 2 * A_BYTES;
+                        const uint32_t b_lo = b_hi + (uint32_t)b_bytes;
+                        for (int sub = 0; sub < P.nsub; ++sub) {
+                            const uint32_t d = dacc + (uint32_t)(sub * P.nw);
+                            const uint32_t bo = (uint32_t)(sub * P.nw * 64);
+#pragma unroll
+                            for (int k = 0; k < SBK / 16; ++k) {
+                                const uint32_t ko = (uint32_t)(k * 32);      // 16 bf16 = 32 B along the swizzle row
+                                const uint32_t acc0 = (kb > 0 || k > 0) ? 1u : 0u;
+                                umma_bf16(d, make_desc64(a_hi + ko), make_desc64(b_hi + bo + ko), P.idesc, acc0);
+                                if (want_lo) {
+                                    umma_bf16(d, make_desc64(a_lo + ko), make_desc64(b_hi + bo + ko), P.idesc, 1u);
+                                    umma_bf16(d, make_desc64(a_hi + ko), make_desc64(b_lo + bo + ko), P.idesc, 1u);
+                                }
+                            }
+                        }
+                        if (SHARE) umma_commit_pair(bar_empty0 + 16 * s + 8 * (it & 1));
+                        else umma_commit(bar_empty0 + 16 * s + 8 * (it & 1));
+                    }
+                    umma_commit(bar_tfull0 + 8 * acc);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    if (SHARE) cluster_sync_all(); else __syncthreads();
+    if (warp == WARP_MMA) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
+    }
+}
+
+static bool make_map_b64(CUtensorMap* map, const void* base, int k_pad, int rows, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)k_pad, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)k_pad * 2};
+    cuuint32_t box[2] = {(cuuint32_t)SBK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// NHWC fp32 activations as a 4-D tensor (C, W, H, N); box = (32 ch, W + 2*PAD, rows + 2*PAD, frames)
+static bool make_map_x(CUtensorMap* map, const ConvParams& p, int pc, int prr, int fn) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return false;
+    cuuint64_t dims[4] = {(cuuint64_t)p.Cin, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.N};
+    cuuint64_t strides[3] = {(cuuint64_t)p.ldx * 4, (cuuint64_t)p.W * p.ldx * 4, (cuuint64_t)p.H * p.W * p.ldx * 4};
+    cuuint32_t box[4] = {(cuuint32_t)SBK, (cuuint32_t)pc, (cuuint32_t)prr, (cuuint32_t)fn};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(p.x), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace tcs
+
+// Shapes the TMA-staged kernel takes (everything else stays on conv_tc.cu's register-sliding producer).
+bool dh_sep_tma_supported(const dh_ctx* ctx, const ConvParams& p, const dh_packed_w* packed) {
+    if (!ctx->sep_tma) return false;
+    if (!packed || !packed->hi || !packed->lo) return false;
+    if (!(p.kh == p.kw && (p.kh == 3 || p.kh == 5)) || p.sh != 1 || p.sw != 1) return false;
+    if (p.Ho != p.H || p.Wo != p.W) return false;
+    if (p.pre_scale) return false;                       // BN prologue: padding would not be zero after the affine
+    if (!(p.W == 32 || p.W == 16 || p.W == 8)) return false;
+    const int tr = tc::BM / p.W;
+    if (tr <= p.H ? (p.H % tr) != 0 : (tr % p.H) != 0) return false;
+    if ((p.Cin % tcs::SBK) != 0 || (p.ldx & 3)) return false;
+    if ((reinterpret_cast<uintptr_t>(p.x) & 15) || (reinterpret_cast<uintptr_t>(p.w_dw) & 7)) return false;
+    if (packed->cout_pad != dh_tc_cout_pad(p.Cout) || packed->k < p.Cin) return false;
+    if (dh_tc_cout_pad(p.Cout) > 2 * tc::MAX_BN_CTA) return false;
+    return true;
+}
+
+int dh_launch_sep_tma(dh_ctx* ctx, const ConvParams& p, const dh_packed_w* packed, int precision, cudaStream_t s) {
+    using namespace tc;
+    using namespace tcs;
+    SepParams SP;
+    TcParams& P = SP.t;
+    P.c = p;
+    P.c.K = p.Cin;
+    P.k_pad = packed->k;
+    P.n_kblocks = p.Cin / SBK;
+    int gy;
+    tile_n(p.Cout, &P.bn_cta, &gy, &P.nsub, &P.nw);
+    P.precision = (precision == 1) ? 1 : 3;
+    P.ks = p.kh;
+    P.acc_stride = (P.bn_cta + 31) / 32 * 32;
+    P.nacc = (2 * P.acc_stride <= 512) ? 2 : 1;
+    int tm = 32;
+    while (tm < P.nacc * P.acc_stride) tm <<= 1;
+    P.tmem_cols = tm;
+    P.n_mtiles = (p.M + BM - 1) / BM;
+    P.stages = 2;
+    P.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.nw >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    const int pad = p.kh / 2;
+    const int tr = BM / p.W;
+    SP.ry = tr <= p.H ? tr : p.H;
+    SP.fn = tr <= p.H ? 1 : tr / p.H;
+    const int pc = p.W + 2 * pad, prr = SP.ry + 2 * pad;
+    SP.patch_bytes = SBK * 4 * pc * prr * SP.fn;
+    SP.patch_stride = (SP.patch_bytes + 1023) / 1024 * 1024;
+    const int stage_bytes = 2 * A_BYTES + 2 * P.bn_cta * 64;
+    const size_t smem = (size_t)2 * stage_bytes + 2 * (size_t)SP.patch_stride + EPI_STAGE_BYTES + 256 + 1024;
+    if (smem > 227 * 1024) {
+        dh_set_error("dh_launch_sep_tma: tile does not fit shared memory");
+        return -1;
+    }
+    CUtensorMap map_hi, map_lo, map_x;
+    if (!make_map_b64(&map_hi, packed->hi, packed->k, packed->cout_pad, P.nw) ||
+        !make_map_b64(&map_lo, packed->lo, packed->k, packed->cout_pad, P.nw) ||
+        !make_map_x(&map_x, p, pc, prr, SP.fn)) {
+        dh_set_error("dh_launch_sep_tma: cuTensorMapEncodeTiled failed");
+        return -1;
+    }
+    int gx = ctx->num_sms / gy;
+    if (gx < 1) gx = 1;
+    if (gx > P.n_mtiles) gx = P.n_mtiles;
+    dim3 grid(gx, gy);
+    const bool share = gy == 2;
+    cudaError_t e = cudaSuccess;
+#define DH_SEP_LAUNCH(KS_, TW_)                                                                                  \
+    do {                                                                                                         \
+        if (share) {                                                                                             \
+            e = cudaFuncSetAttribute(sep_tma_kernel<KS_, TW_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            if (e == cudaSuccess) {                                                                              \
+                cudaLaunchConfig_t cfg = {};                                                                     \
+                cfg.gridDim = grid; cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;  \
+                cudaLaunchAttribute at[1];                                                                       \
+                at[0].id = cudaLaunchAttributeClusterDimension;                                                  \
+                at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 2; at[0].val.clusterDim.z = 1;              \
+                cfg.attrs = at; cfg.numAttrs = 1;                                                                \
+                e = cudaLaunchKernelEx(&cfg, sep_tma_kernel<KS_, TW_, true>, SP, map_hi, map_lo, map_x);         \
+            }                                                                                                    \
+        } else {                                                                                                 \
+            e = cudaFuncSetAttribute(sep_tma_kernel<KS_, TW_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            if (e == cudaSuccess) sep_tma_kernel<KS_, TW_, false><<<grid, NTHREADS, smem, s>>>(SP, map_hi, map_lo, map_x); \
+        }                                                                                                        \
+    } while (0)
+    if (p.kh == 5) {
+        if (p.W == 32) DH_SEP_LAUNCH(5, 32); else if (p.W == 16) DH_SEP_LAUNCH(5, 16); else DH_SEP_LAUNCH(5, 8);
+    } else {
+        if (p.W == 32) DH_SEP_LAUNCH(3, 32); else if (p.W == 16) DH_SEP_LAUNCH(3, 16); else DH_SEP_LAUNCH(3, 8);
+    }
+#undef DH_SEP_LAUNCH
+    if (e != cudaSuccess) {
+        dh_set_error("dh_launch_sep_tma: launch setup failed: %s", cudaGetErrorString(e));
+        return (int)e;
+    }
+    return 0;
+}

@@ -1,0 +1,324 @@
+// Shared pieces of the tcgen05 convolution kernels (conv_tc.cu, conv_sep.cu): constants, launch
+// parameters, PTX wrappers (mbarrier, TMA, tcgen05, cluster/DSMEM, setmaxnreg), UMMA descriptors,
+// the bf16 hi/lo split, the fused epilogue and the host-side tensor-map / N-tiling helpers.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include "common.cuh"
+#include "conv_params.cuh"
+
+namespace tc {
+
+
+constexpr int BM = 128;
+constexpr int BK = 64;                 // bf16 per K-block = one 128-byte swizzle row
+constexpr int NPROD = 256;             // A producers: warps 0..7 (two warpgroups)
+constexpr int NEPI = 128;              // epilogue: warps 8..11 (one warpgroup; warp % 4 = TMEM lane quarter)
+constexpr int WARP_EPI0 = 8, WARP_TMA = 12, WARP_MMA = 13;
+constexpr int NTHREADS = 512;          // 4 warpgroups; the last one holds the TMA + MMA threads
+constexpr int EPI_STAGE_BYTES = 4 * 32 * 128;   // per epilogue warp: 32 rows x 32 fp32, XOR-swizzled
+// register budget (setmaxnreg): 256*168 + 128*136 + 128*40 = 65536
+constexpr int REGS_PROD = 168, REGS_EPI = 136, REGS_CTRL = 40;
+constexpr int A_TILE_BYTES = BM * 128; // 16 KB per (hi | lo)
+constexpr int MAX_STAGES = 4;
+constexpr int MAX_BN_CTA = 288;
+
+struct TcParams {
+    ConvParams c;
+    int n_kblocks;
+    int bn_cta, nsub, nw;   // bn_cta = nsub * nw, nw = MMA N (multiple of 16, <= 256)
+    int stages;
+    int precision;          // 1 | 3
+    int tmem_cols;          // power of two >= bn_cta
+    uint32_t idesc;
+    int ks;                 // separable: depthwise kernel size (3 | 5); 0 = dense
+    int k_pad;
+    int n_mtiles;           // ceil(M / 128); CTA (x, y) loops over tiles x, x + gridDim.x, ...
+    int nacc, acc_stride;   // TMEM accumulator ring: 1 or 2 buffers of acc_stride columns
+};
+
+// ---------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"(bar), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], bf16 x bf16 -> fp32
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
+        " tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// ---- 2-CTA cluster helpers (A-tile sharing between the two N-half CTAs of one pixel tile) ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t mapa_peer(uint32_t local_addr, uint32_t peer) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(peer));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// local shared memory -> peer CTA's shared memory, completion counted on the PEER's mbarrier
+__device__ __forceinline__ void bulk_s2peer(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t bar_cluster) {
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_cluster), "r"(src_cta), "r"(bytes), "r"(bar_cluster)
+                 : "memory");
+}
+// tcgen05.commit arriving on the same mbarrier offset in both CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3)
+                 : "memory");
+}
+template <int R> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
+template <int R> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, 128-byte swizzle UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor):
+// start>>4 [0,14) | LBO>>4 [16,30) (unused for swizzled K-major, 1) | SBO>>4 [32,46) = 1024 B
+// (8 rows x 128 B per swizzle atom) | version 1 [46,48) | layout SWIZZLE_128B = 2 [61,64).
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+           (2ull << 61);
+}
+
+// fp32 -> (hi, lo) bf16 split, round-to-nearest-even: x ~= hi + lo to ~16 mantissa bits.
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    float ra = a - __low2float(h), rb = b - __high2float(h);
+    __nv_bfloat162 l = __floats2bfloat162_rn(ra, rb);
+    hi = *reinterpret_cast<uint32_t*>(&h);
+    lo = *reinterpret_cast<uint32_t*>(&l);
+}
+
+// byte offset of element (row, k) inside a [rows][64 bf16] 128B-swizzled K-major tile
+__device__ __forceinline__ uint32_t swz(int row, int k) {
+    return (uint32_t)(row * 128 + ((((k >> 3) ^ (row & 7)) << 4) | ((k & 7) << 1)));
+}
+
+
+// Epilogue warps (one warpgroup; warp & 3 = TMEM lane quarter): loop over this CTA's tiles,
+// TMEM -> registers (lane = pixel row) -> per-warp XOR-swizzled smem transpose -> lane = 4
+// consecutive output channels: every global access is a coalesced 128-byte row segment;
+// BN affine / ReLU / residual adds are fused here.
+__device__ __forceinline__ void run_epilogue(const TcParams& P, uint8_t* epi_stage, uint32_t tmem_base,
+                                             uint32_t bar_tfull0, uint32_t bar_tempty0, int n0, int warp,
+                                             int lane) {
+    const ConvParams& c = P.c;
+    const int q = warp & 3;
+    float* tile = reinterpret_cast<float*>(epi_stage) + q * (32 * 32);
+    const int nch32 = (P.bn_cta + 31) >> 5;               // 32-column chunks (last may be 16 wide)
+    const bool vec_ok = ((c.ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(c.out) & 15) == 0) &&
+                        (!c.res0 || (((c.ldr0 & 3) == 0) && ((reinterpret_cast<uintptr_t>(c.res0) & 15) == 0))) &&
+                        (!c.res1 || (((c.ldr1 & 3) == 0) && ((reinterpret_cast<uintptr_t>(c.res1) & 15) == 0))) &&
+                        ((c.Cout & 3) == 0) &&
+                        (!c.post_scale || (((reinterpret_cast<uintptr_t>(c.post_scale) & 15) == 0) &&
+                                           ((reinterpret_cast<uintptr_t>(c.post_shift) & 15) == 0)));
+    int ti = 0;
+    for (int t = blockIdx.x; t < P.n_mtiles; t += gridDim.x, ++ti) {
+        const int acc = ti % P.nacc;
+        const uint32_t acc_it = (uint32_t)(ti / P.nacc);
+        const int mbase = t * BM + q * 32;
+        // while the MMAs of this tile run: pull this warp's residual rows into L2
+        if (c.res0 || c.res1) {
+            const int m = mbase + lane;
+            if (m < c.M) {
+                const int cols = min(P.bn_cta, c.Cout - n0);
+                for (int cb = 0; cb < cols; cb += 32) {
+                    if (c.res0) asm volatile("prefetch.global.L2 [%0];" ::"l"(c.res0 + (size_t)m * c.ldr0 + n0 + cb));
+                    if (c.res1) asm volatile("prefetch.global.L2 [%0];" ::"l"(c.res1 + (size_t)m * c.ldr1 + n0 + cb));
+                }
+            }
+        }
+        mbar_wait(bar_tfull0 + 8 * acc, acc_it & 1);
+        tc_fence_after();
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * P.acc_stride);
+        for (int ck = 0; ck < nch32; ++ck) {
+            const int col0 = ck * 32;
+            const int width = min(32, P.bn_cta - col0);        // 32 or 16
+            {
+                float v[32];
+                tmem_ld16(trow + (uint32_t)col0, v);
+                if (width == 32) tmem_ld16(trow + (uint32_t)(col0 + 16), v + 16);
+                if (ck == nch32 - 1) {                          // accumulator fully read -> MMA may reuse it
+                    tc_fence_before();
+                    mbar_arrive(bar_tempty0 + 8 * acc);
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (j * 4 < width)
+                        *reinterpret_cast<float4*>(tile + lane * 32 + ((j ^ (lane & 7)) << 2)) =
+                            make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+            __syncwarp();
+            if (vec_ok) {
+                // lane = (row r = lane/8 + 4*i, 4 columns c4 = 4*(lane%8)): 4 rows x 128 B per instruction
+                const int b4 = lane & 7;
+                const int co = n0 + col0 + b4 * 4;
+                const bool cok = b4 * 4 < width && co < c.Cout;
+                float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (cok && c.post_scale) {
+                    sc = __ldg(reinterpret_cast<const float4*>(c.post_scale + co));
+                    sh = __ldg(reinterpret_cast<const float4*>(c.post_shift + co));
+                }
+                float4 ra[8], rb[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int m = mbase + (lane >> 3) + 4 * i;
+                    ra[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    rb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (cok && m < c.M) {
+                        if (c.res0) ra[i] = __ldg(reinterpret_cast<const float4*>(c.res0 + (size_t)m * c.ldr0 + co));
+                        if (c.res1) rb[i] = __ldg(reinterpret_cast<const float4*>(c.res1 + (size_t)m * c.ldr1 + co));
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int r = (lane >> 3) + 4 * i;
+                    const int m = mbase + r;
+                    if (cok && m < c.M) {
+                        float4 tt = *reinterpret_cast<const float4*>(tile + r * 32 + ((b4 ^ (r & 7)) << 2));
+                        tt.x = fmaf(tt.x, sc.x, sh.x); tt.y = fmaf(tt.y, sc.y, sh.y);
+                        tt.z = fmaf(tt.z, sc.z, sh.z); tt.w = fmaf(tt.w, sc.w, sh.w);
+                        if (c.post_relu) {
+                            tt.x = fmaxf(tt.x, 0.f); tt.y = fmaxf(tt.y, 0.f);
+                            tt.z = fmaxf(tt.z, 0.f); tt.w = fmaxf(tt.w, 0.f);
+                        }
+                        tt.x += ra[i].x + rb[i].x; tt.y += ra[i].y + rb[i].y;
+                        tt.z += ra[i].z + rb[i].z; tt.w += ra[i].w + rb[i].w;
+                        *reinterpret_cast<float4*>(c.out + (size_t)m * c.ldo + co) = tt;
+                    }
+                }
+            } else {
+                const int co = n0 + col0 + lane;
+                const bool cok = lane < width && co < c.Cout;
+                float sc = 1.f, sh = 0.f;
+                if (cok && c.post_scale) {
+                    sc = __ldg(c.post_scale + co);
+                    sh = __ldg(c.post_shift + co);
+                }
+#pragma unroll 8
+                for (int r = 0; r < 32; ++r) {
+                    const int m = mbase + r;
+                    if (cok && m < c.M) {
+                        float tt = fmaf(tile[r * 32 + ((((lane >> 2) ^ (r & 7)) << 2) | (lane & 3))], sc, sh);
+                        if (c.post_relu) tt = fmaxf(tt, 0.f);
+                        if (c.res0) tt += __ldg(c.res0 + (size_t)m * c.ldr0 + co);
+                        if (c.res1) tt += __ldg(c.res1 + (size_t)m * c.ldr1 + co);
+                        c.out[(size_t)m * c.ldo + co] = tt;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static inline EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+static inline bool make_map(CUtensorMap* map, const void* base, int k_pad, int rows, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)k_pad, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)k_pad * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+// N tiling rule shared with the host-side weight packer (dh_tc_cout_pad).
+static inline void tile_n(int cout, int* bn_cta, int* gy, int* nsub, int* nw) {
+    int cp = (cout + 15) / 16 * 16;
+    int g = (cp + MAX_BN_CTA - 1) / MAX_BN_CTA;
+    int bn = ((cp + g - 1) / g + 15) / 16 * 16;
+    int ns = 1;
+    if (bn > 256) {
+        bn = (bn + 31) / 32 * 32;
+        ns = 2;
+    }
+    *bn_cta = bn; *gy = g; *nsub = ns; *nw = bn / ns;
+}
+
+}  // namespace tc

@@ -96,12 +96,30 @@ SEP_CASES = [
     (2, 16, 16, 384, 384, 5, 'bn_act'),
     (2, 8, 8, 480, 480, 5, 'bn_act'),
     (8, 4, 4, 576, 576, 5, 'bn_act'),
+    (2, 16, 16, 64, 96, 3, 'plain'),                # TMA-staged kernel without ReLU prologue
+    (5, 8, 8, 96, 80, 5, 'act_bn_res'),             # 8x8 maps: two frames per tile, odd frame count
 ]
+
+
+def _tma_eligible(case):
+    n, h, w, cin, cout, k, mode = case
+    return mode != 'bn_act' and w in (32, 16, 8) and cin % 32 == 0
 
 
 @pytest.mark.parametrize('case', SEP_CASES)
 @pytest.mark.parametrize('precision', [3, 1])
-def test_sepconv_tc(dev, case, precision):
+@pytest.mark.parametrize('kernel', ['tma', 'reg'])
+def test_sepconv_tc(dev, case, precision, kernel):
+    """kernel = 'tma': conv_sep.cu (TMA-staged patch, path 2) where it applies; 'reg': conv_tc.cu's
+    register-sliding producer (path 1)."""
+    _ffi.check(dev.lib.dh_set_option(dev.ctx.handle, b'sep_tma', 1 if kernel == 'tma' else 0))
+    try:
+        _run_sepconv(dev, case, precision, 2 if (kernel == 'tma' and _tma_eligible(case)) else 1)
+    finally:
+        _ffi.check(dev.lib.dh_set_option(dev.ctx.handle, b'sep_tma', 1))
+
+
+def _run_sepconv(dev, case, precision, expect_path):
     n, h, w, cin, cout, k, mode = case
     rng = np.random.default_rng(zlib.crc32(repr(case).encode()))
     x = rng.standard_normal((n, h, w, cin))
@@ -129,7 +147,7 @@ def test_sepconv_tc(dev, case, precision):
     xv, ov = dev.view(dev.put(x)), dev.view(out)
     dev.call('dh_sepconv2d_f32', C.byref(xv), dev.put(dw).data_ptr(), dev.put(pw).data_ptr(), C.byref(pk),
              C.byref(d), C.byref(ov))
-    assert dev.lib.dh_last_conv_path(dev.ctx.handle) == 1, 'tensor-core path was not taken'
+    assert dev.lib.dh_last_conv_path(dev.ctx.handle) == expect_path, 'unexpected kernel path'
     e = _err(out.cpu().numpy(), ref)
     assert e <= (TOL3 if precision == 3 else TOL1), e
 
@@ -160,6 +178,8 @@ def test_sepconv_cluster_share_matches(dev, share):
     try:
         for case in [(3, 32, 32, 576, 576, 5, 'act_bn_res'), (2, 16, 16, 288, 576, 5, 'act_bn_res'),
                      (1, 32, 32, 384, 576, 3, 'act_bn_res'), (5, 8, 8, 128, 576, 5, 'bn_act')]:
-            test_sepconv_tc(dev, case, 3)
+            _ffi.check(dev.lib.dh_set_option(dev.ctx.handle, b'sep_tma', 0))      # exercise conv_tc.cu's SHARE path
+            _run_sepconv(dev, case, 3, 1)
     finally:
         _ffi.check(dev.lib.dh_set_option(dev.ctx.handle, b'share_a', 1))
+        _ffi.check(dev.lib.dh_set_option(dev.ctx.handle, b'sep_tma', 1))
