@@ -33,6 +33,7 @@ struct SepParams {
     int patch_stride;       // bytes between the two patch buffers (>= patch_bytes, 1024-aligned)
     int patch_bytes;
     int ry, fn;             // tile rows per frame, frames per tile
+    int dbg;                // ablation bits (tools/ only): 1 no depthwise math, 2 no patch TMA, 8 no DSMEM push, 16 no weight TMA
 };
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
@@ -67,7 +68,8 @@ sep_tma_kernel(const __grid_constant__ SepParams SP, const __grid_constant__ CUt
     constexpr int NR = 4 + KS - 1;            // input rows / cols per 4x4 block
     const TcParams& P = SP.t;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment as an OFFSET (not a uintptr_t round-trip) so that accesses stay in the shared state space
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const bool want_lo = P.precision == 3;
@@ -76,15 +78,15 @@ sep_tma_kernel(const __grid_constant__ SepParams SP, const __grid_constant__ CUt
     uint8_t* patch0 = smem + 2 * stage_bytes;
     uint8_t* epi_stage = patch0 + 2 * SP.patch_stride;
     uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage + EPI_STAGE_BYTES);
-    // bars: full[2] | empty[2 stages][2] | pfull[2] | pempty[2] | tfull[2] | tempty[2]
+    // bars: full[2] | empty[2 stages][2] | pfull[2] | pempty[2] | tfull[MAX_SLOTS] | tempty[MAX_SLOTS]
     // empty[s][u & 1] is signalled when use u of stage s has been consumed by the MMAs.  Two barriers per
     // stage, alternating by use: in the cluster variant the two producer warpgroups write the SAME stage on
     // alternate uses, so with one barrier each warpgroup would skip every other phase -- and an mbarrier
     // parity wait is only meaningful one phase ahead.  With two, every waiter sees consecutive phases.
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10 + 2 * MAX_SLOTS);
     const uint32_t bar_full0 = smem_u32(bars), bar_empty0 = smem_u32(bars + 2), bar_pfull0 = smem_u32(bars + 6),
                    bar_pempty0 = smem_u32(bars + 8), bar_tfull0 = smem_u32(bars + 10),
-                   bar_tempty0 = smem_u32(bars + 12);
+                   bar_tempty0 = smem_u32(bars + 10 + MAX_SLOTS);
     const int n0 = blockIdx.y * P.bn_cta;
     const int nkb = P.n_kblocks;
     const uint32_t my_rank = SHARE ? cluster_ctarank() : 0u;
@@ -105,8 +107,10 @@ sep_tma_kernel(const __grid_constant__ SepParams SP, const __grid_constant__ CUt
             }
             mbar_init(bar_pfull0 + 8 * s, 1);
             mbar_init(bar_pempty0 + 8 * s, NWG);
-            mbar_init(bar_tfull0 + 8 * s, 1);
-            mbar_init(bar_tempty0 + 8 * s, NEPI);
+        }
+        for (int a = 0; a < MAX_SLOTS; ++a) {
+            mbar_init(bar_tfull0 + 8 * a, 1);
+            mbar_init(bar_tempty0 + 8 * a, NEPI);
         }
         fence_barrier_init();
     }
@@ -155,7 +159,8 @@ sep_tma_kernel(const __grid_constant__ SepParams SP, const __grid_constant__ CUt
 #pragma unroll
                 for (int q = 0; q < 4; ++q) acc[o][q] = make_float2(0.f, 0.f);
 
-            mbar_wait(pfull, (uint32_t)((j >> 1) & 1));
+            if (!(SP.dbg & 2)) mbar_wait(pfull, (uint32_t)((j >> 1) & 1));
+            if (!(SP.dbg & 1))
 #pragma unroll
             for (int r = 0; r < NR; ++r) {
                 float2 in[NR];
@@ -175,7 +180,7 @@ sep_tma_kernel(const __grid_constant__ SepParams SP, const __grid_constant__ CUt
                     }
                 }
             }
-            mbar_arrive(pempty);                       // patch buffer may be refilled
+            if (!(SP.dbg & 2)) mbar_arrive(pempty);    // patch buffer may be refilled
 
             const int s = g & 1;
             const uint32_t it = (uint32_t)(g >> 1);
@@ -199,8 +204,10 @@ sep_tma_kernel(const __grid_constant__ SepParams SP, const __grid_constant__ CUt
                     mbar_arrive(bar_full0 + 8 * s);
                     const uint32_t peer = my_rank ^ 1u;
                     const uint32_t peer_full = mapa_peer(bar_full0 + 8 * s, peer);
-                    bulk_s2peer(mapa_peer(smem_u32(a_hi), peer), smem_u32(a_hi), A_BYTES, peer_full);
-                    if (want_lo) bulk_s2peer(mapa_peer(smem_u32(a_lo), peer), smem_u32(a_lo), A_BYTES, peer_full);
+                    if (!(SP.dbg & 8)) {
+                        bulk_s2peer(mapa_peer(smem_u32(a_hi), peer), smem_u32(a_hi), A_BYTES, peer_full);
+                        if (want_lo) bulk_s2peer(mapa_peer(smem_u32(a_lo), peer), smem_u32(a_lo), A_BYTES, peer_full);
+                    }
                 }
             } else {
                 mbar_arrive(bar_full0 + 8 * s);
@@ -215,8 +222,8 @@ sep_tma_kernel(const __grid_constant__ SepParams SP, const __grid_constant__ CUt
         if (warp == WARP_TMA) {
             // ======================= weight tiles via TMA =======================
             if (lane == 0) {
-                const uint32_t tx = (uint32_t)(want_lo ? 2 : 1) * (uint32_t)b_bytes;
-                const uint32_t tx_a = (uint32_t)(want_lo ? 2 : 1) * (uint32_t)A_BYTES;
+                const uint32_t tx = (SP.dbg & 16) ? 0u : (uint32_t)(want_lo ? 2 : 1) * (uint32_t)b_bytes;
+                const uint32_t tx_a = (SP.dbg & 8) ? 0u : (uint32_t)(want_lo ? 2 : 1) * (uint32_t)A_BYTES;
                 for (int g = 0; g < total_g; ++g) {
                     const int ti = g / nkb, kb = g - ti * nkb;
                     const int s = g & 1;
@@ -226,6 +233,7 @@ sep_tma_kernel(const __grid_constant__ SepParams SP, const __grid_constant__ CUt
                     mbar_arrive_expect_tx(full, tx + ((SHARE && (uint32_t)s != my_rank) ? tx_a : 0u));
                     const uint32_t b_hi = smem_u32(smem + (size_t)s * stage_bytes + 2 * A_BYTES);
                     const uint32_t b_lo = b_hi + (uint32_t)b_bytes;
+                    if (!(SP.dbg & 16))
                     for (int sub = 0; sub < P.nsub; ++sub) {
                         tma_load_2d(b_hi + (uint32_t)(sub * P.nw * 64), &map_hi, kb * SBK, n0 + sub * P.nw, full);
                         if (want_lo)
@@ -235,7 +243,7 @@ sep_tma_kernel(const __grid_constant__ SepParams SP, const __grid_constant__ CUt
             }
         } else if (warp == WARP_PATCH) {
             // ======================= input patches via 4-D TMA =======================
-            if (lane == 0) {
+            if (lane == 0 && !(SP.dbg & 2)) {
                 const ConvParams& c = P.c;
                 for (int j = 0; j < n_own; ++j) {
                     const int g = SHARE ? 2 * j + (int)my_rank : j;
@@ -251,43 +259,69 @@ sep_tma_kernel(const __grid_constant__ SepParams SP, const __grid_constant__ CUt
                 }
             }
         } else if (warp == WARP_MMA) {
-            // ======================= MMA issue (one thread) =======================
-            if (lane == 0) {
-                int g = 0;
-                for (int ti = 0; ti < tiles_mine; ++ti) {
-                    const int acc = ti % P.nacc;
-                    const uint32_t acc_it = (uint32_t)(ti / P.nacc);
-                    mbar_wait(bar_tempty0 + 8 * acc, (acc_it & 1) ^ 1);
-                    tc_fence_after();
-                    const uint32_t dacc = tmem_base + (uint32_t)(acc * P.acc_stride);
-                    for (int kb = 0; kb < nkb; ++kb, ++g) {
-                        const int s = g & 1;
-                        const uint32_t it = (uint32_t)(g >> 1);
-                        mbar_wait(bar_full0 + 8 * s, it & 1);
-                        tc_fence_after();
-                        const uint32_t a_hi = smem_u32(smem + (size_t)s * stage_bytes);
-                        const uint32_t a_lo = a_hi + A_BYTES;
-                        const uint32_t b_hi = a_hi + 2 * A_BYTES;
-                        const uint32_t b_lo = b_hi + (uint32_t)b_bytes;
-                        for (int sub = 0; sub < P.nsub; ++sub) {
-                            const uint32_t d = dacc + (uint32_t)(sub * P.nw);
-                            const uint32_t bo = (uint32_t)(sub * P.nw * 64);
+            // ======================= MMA issue =======================
+            // The whole warp runs the loop (uniform control flow and operands); one elected lane issues.
+            // Descriptors differ only in the 14-bit start-address field, so they are base + (offset >> 4).
+            const bool leader = elect_one();
+            const uint64_t dbase = make_desc64(smem_u32(smem));
+            const uint32_t st16 = (uint32_t)stage_bytes >> 4, alo16 = A_BYTES >> 4, b16 = (2 * A_BYTES) >> 4,
+                           blo16 = (uint32_t)b_bytes >> 4, sub16 = (uint32_t)(P.nw * 64) >> 4;
+            uint32_t u = 0;                                    // accumulator use counter (tile * nsub + sub)
+            int g = 0;
+            for (int ti = 0; ti < tiles_mine; ++ti) {
+                uint32_t dsub[MAX_NSUB];
 #pragma unroll
-                            for (int k = 0; k < SBK / 16; ++k) {
-                                const uint32_t ko = (uint32_t)(k * 32);      // 16 bf16 = 32 B along the swizzle row
-                                const uint32_t acc0 = (kb > 0 || k > 0) ? 1u : 0u;
-                                umma_bf16(d, make_desc64(a_hi + ko), make_desc64(b_hi + bo + ko), P.idesc, acc0);
-                                if (want_lo) {
-                                    umma_bf16(d, make_desc64(a_lo + ko), make_desc64(b_hi + bo + ko), P.idesc, 1u);
-                                    umma_bf16(d, make_desc64(a_hi + ko), make_desc64(b_lo + bo + ko), P.idesc, 1u);
+                for (int sub = 0; sub < MAX_NSUB; ++sub) {
+                    dsub[sub] = 0;
+                    if (sub < P.nsub) {
+                        const uint32_t uu = u + (uint32_t)sub;
+                        const uint32_t slot = uu % (uint32_t)P.nslots;
+                        dsub[sub] = tmem_base + slot * (uint32_t)P.slot_stride;
+                    }
+                }
+                for (int kb = 0; kb < nkb; ++kb, ++g) {
+                    const int s = g & 1;
+                    const uint32_t it = (uint32_t)(g >> 1);
+                    if (!(P.dbg & 128)) mbar_wait(bar_full0 + 8 * s, it & 1);
+                    if (kb == 0) {                               // the epilogue must have drained the slots
+#pragma unroll
+                        for (int sub = 0; sub < MAX_NSUB; ++sub)
+                            if (sub < P.nsub) {
+                                const uint32_t uu = u + (uint32_t)sub;
+                                mbar_wait(bar_tempty0 + 8 * (uu % (uint32_t)P.nslots),
+                                          ((uu / (uint32_t)P.nslots) & 1) ^ 1);
+                            }
+                    }
+                    tc_fence_after();
+                    if (leader) {
+                        const uint64_t da = dbase + (uint64_t)((uint32_t)s * st16);
+#pragma unroll
+                        for (int sub = 0; sub < MAX_NSUB; ++sub) {
+                            if (sub < P.nsub) {
+                                const uint64_t db = da + (uint64_t)(b16 + (uint32_t)sub * sub16);
+#pragma unroll
+                                for (int k = 0; k < SBK / 16; ++k) {
+                                    const uint32_t acc0 = (kb > 0 || k > 0) ? 1u : 0u;
+                                    umma_bf16(dsub[sub], da + 2 * k, db + 2 * k, P.idesc, acc0);
+                                    if (want_lo) {
+                                        umma_bf16(dsub[sub], da + alo16 + 2 * k, db + 2 * k, P.idesc, 1u);
+                                        umma_bf16(dsub[sub], da + 2 * k, db + blo16 + 2 * k, P.idesc, 1u);
+                                    }
                                 }
                             }
                         }
                         if (SHARE) umma_commit_pair(bar_empty0 + 16 * s + 8 * (it & 1));
                         else umma_commit(bar_empty0 + 16 * s + 8 * (it & 1));
                     }
-                    umma_commit(bar_tfull0 + 8 * acc);
+                    __syncwarp();
                 }
+                if (leader) {
+#pragma unroll
+                    for (int sub = 0; sub < MAX_NSUB; ++sub)
+                        if (sub < P.nsub) umma_commit(bar_tfull0 + 8 * ((u + (uint32_t)sub) % (uint32_t)P.nslots));
+                }
+                __syncwarp();
+                u += (uint32_t)P.nsub;
             }
         }
     }
@@ -356,11 +390,7 @@ int dh_launch_sep_tma(dh_ctx* ctx, const ConvParams& p, const dh_packed_w* packe
     tile_n(p.Cout, &P.bn_cta, &gy, &P.nsub, &P.nw);
     P.precision = (precision == 1) ? 1 : 3;
     P.ks = p.kh;
-    P.acc_stride = (P.bn_cta + 31) / 32 * 32;
-    P.nacc = (2 * P.acc_stride <= 512) ? 2 : 1;
-    int tm = 32;
-    while (tm < P.nacc * P.acc_stride) tm <<= 1;
-    P.tmem_cols = tm;
+    plan_tmem(P);
     P.n_mtiles = (p.M + BM - 1) / BM;
     P.stages = 2;
     P.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.nw >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
@@ -371,6 +401,8 @@ int dh_launch_sep_tma(dh_ctx* ctx, const ConvParams& p, const dh_packed_w* packe
     const int pc = p.W + 2 * pad, prr = SP.ry + 2 * pad;
     SP.patch_bytes = SBK * 4 * pc * prr * SP.fn;
     SP.patch_stride = (SP.patch_bytes + 1023) / 1024 * 1024;
+    SP.dbg = ctx->dbg;
+    P.dbg = ctx->dbg;
     const int stage_bytes = 2 * A_BYTES + 2 * P.bn_cta * 64;
     const size_t smem = (size_t)2 * stage_bytes + 2 * (size_t)SP.patch_stride + EPI_STAGE_BYTES + 256 + 1024;
     if (smem > 227 * 1024) {
@@ -388,7 +420,7 @@ int dh_launch_sep_tma(dh_ctx* ctx, const ConvParams& p, const dh_packed_w* packe
     if (gx < 1) gx = 1;
     if (gx > P.n_mtiles) gx = P.n_mtiles;
     dim3 grid(gx, gy);
-    const bool share = gy == 2;
+    const bool share = gy == 2 && ctx->share_a;
     cudaError_t e = cudaSuccess;
 #define DH_SEP_LAUNCH(KS_, TW_)                                                                                  \
     do {                                                                                                         \

@@ -238,7 +238,8 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUtensorMap map_hi,
                const __grid_constant__ CUtensorMap map_lo) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment as an OFFSET (not a uintptr_t round-trip) so that accesses stay in the shared state space
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const bool want_lo = P.precision == 3;
@@ -246,10 +247,10 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
     const int stage_bytes = 2 * A_TILE_BYTES + 2 * b_tile_bytes;
     uint8_t* epi_stage = smem + (size_t)P.stages * stage_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage + EPI_STAGE_BYTES);
-    // bars: full[MAX_STAGES] | empty[MAX_STAGES] | tmem_full[2] | tmem_empty[2] ; then the TMEM base word
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
+    // bars: full[MAX_STAGES] | empty[MAX_STAGES] | tmem_full[MAX_SLOTS] | tmem_empty[MAX_SLOTS] ; then the TMEM base word
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 2 * MAX_SLOTS);
     const uint32_t bar_full0 = smem_u32(bars), bar_empty0 = smem_u32(bars + MAX_STAGES),
-                   bar_tfull0 = smem_u32(bars + 2 * MAX_STAGES), bar_tempty0 = smem_u32(bars + 2 * MAX_STAGES + 2);
+                   bar_tfull0 = smem_u32(bars + 2 * MAX_STAGES), bar_tempty0 = smem_u32(bars + 2 * MAX_STAGES + MAX_SLOTS);
     const int n0 = blockIdx.y * P.bn_cta;
     const int nkb = P.n_kblocks;
 
@@ -267,7 +268,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
                 mbar_init(bar_empty0 + 8 * s, 1);
             }
         }
-        for (int a = 0; a < 2; ++a) {
+        for (int a = 0; a < MAX_SLOTS; ++a) {
             mbar_init(bar_tfull0 + 8 * a, 1);
             mbar_init(bar_tempty0 + 8 * a, NEPI);
         }
@@ -353,43 +354,66 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
                 }
             }
         } else if (warp == WARP_MMA) {
-            // ======================= MMA issue (one thread) =======================
-            if (lane == 0) {
-                int g = 0, ti = 0;
-                for (int t = blockIdx.x; t < P.n_mtiles; t += gridDim.x, ++ti) {
-                    const int acc = ti % P.nacc;
-                    const uint32_t acc_it = (uint32_t)(ti / P.nacc);
-                    mbar_wait(bar_tempty0 + 8 * acc, (acc_it & 1) ^ 1);      // epilogue drained this accumulator
-                    tc_fence_after();
-                    const uint32_t dacc = tmem_base + (uint32_t)(acc * P.acc_stride);
-                    for (int kb = 0; kb < nkb; ++kb, ++g) {
-                        const int s = g % P.stages;
-                        const uint32_t it = (uint32_t)(g / P.stages);
-                        mbar_wait(bar_full0 + 8 * s, it & 1);
-                        tc_fence_after();
-                        const uint32_t a_hi = smem_u32(smem + (size_t)s * stage_bytes);
-                        const uint32_t a_lo = a_hi + A_TILE_BYTES;
-                        const uint32_t b_hi = a_hi + 2 * A_TILE_BYTES;
-                        const uint32_t b_lo = b_hi + (uint32_t)b_tile_bytes;
-                        for (int sub = 0; sub < P.nsub; ++sub) {
-                            const uint32_t d = dacc + (uint32_t)(sub * P.nw);
-                            const uint32_t bo = (uint32_t)(sub * P.nw * 128);
+            // ======================= MMA issue =======================
+            // The whole warp runs the loop (uniform control flow and operands); one elected lane issues.
+            // Descriptors differ only in the 14-bit start-address field, so they are base + (offset >> 4).
+            const bool leader = elect_one();
+            const uint64_t dbase = make_desc(smem_u32(smem));
+            const uint32_t st16 = (uint32_t)stage_bytes >> 4, alo16 = A_TILE_BYTES >> 4, b16 = (2 * A_TILE_BYTES) >> 4,
+                           blo16 = (uint32_t)b_tile_bytes >> 4, sub16 = (uint32_t)(P.nw * 128) >> 4;
+            uint32_t u = 0;                                    // accumulator use counter (tile * nsub + sub)
+            int s = 0;
+            uint32_t it = 0;                                   // use count of stage s
+            for (int t = blockIdx.x; t < P.n_mtiles; t += gridDim.x) {
+                uint32_t dsub[MAX_NSUB];
 #pragma unroll
-                            for (int k = 0; k < BK / 16; ++k) {
-                                const uint32_t ko = (uint32_t)(k * 32);      // 16 bf16 = 32 B along the swizzle row
-                                const uint32_t acc0 = (kb > 0 || k > 0) ? 1u : 0u;
-                                umma_bf16(d, make_desc(a_hi + ko), make_desc(b_hi + bo + ko), P.idesc, acc0);
-                                if (want_lo) {
-                                    umma_bf16(d, make_desc(a_lo + ko), make_desc(b_hi + bo + ko), P.idesc, 1u);
-                                    umma_bf16(d, make_desc(a_hi + ko), make_desc(b_lo + bo + ko), P.idesc, 1u);
+                for (int sub = 0; sub < MAX_NSUB; ++sub) {
+                    dsub[sub] = 0;
+                    if (sub < P.nsub)
+                        dsub[sub] = tmem_base + ((u + (uint32_t)sub) % (uint32_t)P.nslots) * (uint32_t)P.slot_stride;
+                }
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(bar_full0 + 8 * s, it & 1);
+                    if (kb == 0) {                               // the epilogue must have drained the slots
+#pragma unroll
+                        for (int sub = 0; sub < MAX_NSUB; ++sub)
+                            if (sub < P.nsub) {
+                                const uint32_t uu = u + (uint32_t)sub;
+                                mbar_wait(bar_tempty0 + 8 * (uu % (uint32_t)P.nslots),
+                                          ((uu / (uint32_t)P.nslots) & 1) ^ 1);
+                            }
+                    }
+                    tc_fence_after();
+                    if (leader) {
+                        const uint64_t da = dbase + (uint64_t)((uint32_t)s * st16);
+#pragma unroll
+                        for (int sub = 0; sub < MAX_NSUB; ++sub) {
+                            if (sub < P.nsub) {
+                                const uint64_t db = da + (uint64_t)(b16 + (uint32_t)sub * sub16);
+#pragma unroll
+                                for (int k = 0; k < BK / 16; ++k) {      // 16 bf16 = 32 B along the swizzle row
+                                    const uint32_t acc0 = (kb > 0 || k > 0) ? 1u : 0u;
+                                    umma_bf16(dsub[sub], da + 2 * k, db + 2 * k, P.idesc, acc0);
+                                    if (want_lo) {
+                                        umma_bf16(dsub[sub], da + alo16 + 2 * k, db + 2 * k, P.idesc, 1u);
+                                        umma_bf16(dsub[sub], da + 2 * k, db + blo16 + 2 * k, P.idesc, 1u);
+                                    }
                                 }
                             }
                         }
                         if (SHARE) umma_commit_pair(bar_empty0 + 8 * s);   // both CTAs must release the stage
                         else umma_commit(bar_empty0 + 8 * s);              // frees this smem stage when the MMAs retire
                     }
-                    umma_commit(bar_tfull0 + 8 * acc);                     // accumulator complete -> epilogue
+                    __syncwarp();
+                    if (++s == P.stages) { s = 0; ++it; }
                 }
+                if (leader) {                                   // accumulator complete -> epilogue
+#pragma unroll
+                    for (int sub = 0; sub < MAX_NSUB; ++sub)
+                        if (sub < P.nsub) umma_commit(bar_tfull0 + 8 * ((u + (uint32_t)sub) % (uint32_t)P.nslots));
+                }
+                __syncwarp();
+                u += (uint32_t)P.nsub;
             }
         }
     }
@@ -447,11 +471,8 @@ int dh_launch_conv_tc(dh_ctx* ctx, const ConvParams& p, const dh_packed_w* packe
     tile_n(p.Cout, &P.bn_cta, &gy, &P.nsub, &P.nw);
     P.precision = (precision == 1) ? 1 : 3;
     P.ks = separable ? p.kh : 0;
-    P.acc_stride = (P.bn_cta + 31) / 32 * 32;
-    P.nacc = (2 * P.acc_stride <= 512) ? 2 : 1;
-    int tm = 32;
-    while (tm < P.nacc * P.acc_stride) tm <<= 1;
-    P.tmem_cols = tm;
+    plan_tmem(P);
+    P.dbg = ctx->dbg;
     P.n_mtiles = (p.M + BM - 1) / BM;
     // cute::UMMA::InstrDescriptor: c_format F32 [4,6)=1, a/b_format BF16 [7,10)/[10,13)=1, K-major A and B,
     // n_dim = N>>3 at [17,23), m_dim = M>>4 at [24,29)

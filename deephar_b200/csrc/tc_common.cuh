@@ -34,7 +34,9 @@ struct TcParams {
     int ks;                 // separable: depthwise kernel size (3 | 5); 0 = dense
     int k_pad;
     int n_mtiles;           // ceil(M / 128); CTA (x, y) loops over tiles x, x + gridDim.x, ...
-    int nacc, acc_stride;   // TMEM accumulator ring: 1 or 2 buffers of acc_stride columns
+    int nslots, slot_stride; // TMEM accumulator slots (see run_epilogue): nslots x slot_stride columns
+    int dbg;                // ablation bits (tools/ only; results are wrong when set): 64 epilogue only hands
+                            // the slots back, 128 MMAs do not wait for operands
 };
 
 // ---------------------------------------------------------------------------
@@ -92,6 +94,12 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
         " tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+// one lane of a converged warp (the compiler keeps tcgen05 operands in uniform registers under this predicate)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -159,120 +167,224 @@ __device__ __forceinline__ uint32_t swz(int row, int k) {
 }
 
 
+// TMEM accumulator slots.  A tile's accumulator is nsub sub-tiles of nw columns; sub-tile `sub` of this
+// CTA's tile number ti is "use" u = ti * nsub + sub and lives in slot u % nslots (slot_stride columns each),
+// guarded by tfull[slot] / tempty[slot].  With nslots > nsub the MMAs of tile ti+1 start in the spare
+// slot(s) while the epilogue still drains tile ti; the epilogue frees slots in the order the MMAs need them.
+constexpr int MAX_SLOTS = 8;
+constexpr int MAX_NSUB = 3;
+
+struct ResRows { float4 v[8]; };
+
+__device__ __forceinline__ void sts128(uint32_t a, float x, float y, float z, float w) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+    return v;
+}
+
+// residual rows of one 32-column chunk: lane = (row lane/8 + 4 i, columns 4 (lane%8) ..+3)
+template <bool FULL>
+__device__ __forceinline__ void epi_load_res(ResRows& r, const float* p, size_t ld4, int m0, int M, bool on) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        r.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (on && (FULL || m0 + 4 * i < M)) r.v[i] = __ldg(reinterpret_cast<const float4*>(p + i * ld4));
+    }
+}
+
 // Epilogue warps (one warpgroup; warp & 3 = TMEM lane quarter): loop over this CTA's tiles,
 // TMEM -> registers (lane = pixel row) -> per-warp XOR-swizzled smem transpose -> lane = 4
 // consecutive output channels: every global access is a coalesced 128-byte row segment;
-// BN affine / ReLU / residual adds are fused here.
+// BN affine / ReLU / residual adds are fused here.  The first residual is software-pipelined one
+// 32-column chunk ahead (its global-load latency would otherwise serialise the drain of the accumulator).
+// This loop is a single-warp serial instruction stream on the critical path of every tile, so it is
+// written for a short stream: shared-space addresses, hoisted row pointers, one predicate per lane.
+template <bool FULL>
+__device__ __forceinline__ void epilogue_tile(const TcParams& P, uint32_t tile_s, uint32_t tmem_base,
+                                              uint32_t bar_tfull0, uint32_t bar_tempty0, int n0, int q, int lane,
+                                              int mbase, uint32_t u0, bool vec_ok) {
+    const ConvParams& c = P.c;
+    const int nch = (P.nw + 31) >> 5;                     // 32-column chunks per sub-tile (last may be 16 wide)
+    const int b4 = lane & 7, r0 = lane >> 3;
+    const int m0 = mbase + r0;
+    const size_t ldo4 = (size_t)c.ldo * 4, ldr04 = (size_t)c.ldr0 * 4, ldr14 = (size_t)c.ldr1 * 4;
+    const uint32_t st_a = tile_s + (uint32_t)lane * 128u;                       // transpose: write row = lane
+    const uint32_t ld_a0 = tile_s + (uint32_t)(r0 * 128 + ((b4 ^ r0) << 4));    // read rows r0, r0 + 8, ...
+    const uint32_t ld_a1 = tile_s + (uint32_t)((r0 + 4) * 128 + ((b4 ^ (r0 + 4)) << 4));   // rows r0 + 4, r0 + 12, ...
+    const bool pipe = vec_ok && c.res0 != nullptr;
+    float* out_row = c.out + (size_t)m0 * c.ldo;
+    const float* res0_row = c.res0 ? c.res0 + (size_t)m0 * c.ldr0 : nullptr;
+    const float* res1_row = c.res1 ? c.res1 + (size_t)m0 * c.ldr1 : nullptr;
+    const float* post_scale = c.post_scale;
+    const float* post_shift = c.post_shift;
+    const bool has_post = c.post_scale != nullptr, has1 = c.res1 != nullptr, relu = c.post_relu != 0;
+    const int M = c.M;
+
+    // chunk iterator (sub, ck) -> output column of this lane
+    auto lane_co = [&](int sub, int ck, bool& cok) __attribute__((always_inline)) {
+        const int col0 = ck * 32;
+        const int co = n0 + sub * P.nw + col0 + b4 * 4;
+        cok = (b4 * 4 < P.nw - col0) && (co < c.Cout);
+        return co;
+    };
+    auto stage_a = [&](int sub, int ck) __attribute__((always_inline)) {
+        const int col0 = ck * 32;
+        const int width = min(32, P.nw - col0);            // 32 or 16
+        const uint32_t u = u0 + (uint32_t)sub;
+        const uint32_t slot = u % (uint32_t)P.nslots;
+        if (ck == 0) {
+            mbar_wait(bar_tfull0 + 8 * slot, (u / (uint32_t)P.nslots) & 1);
+            tc_fence_after();
+        }
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + slot * (uint32_t)P.slot_stride;
+        if (P.dbg & 64) {
+            if (ck == nch - 1) {
+                tc_fence_before();
+                mbar_arrive(bar_tempty0 + 8 * slot);
+            }
+            return;
+        }
+        {
+            float v[32];
+            tmem_ld16(trow + (uint32_t)col0, v);
+            if (width == 32) tmem_ld16(trow + (uint32_t)(col0 + 16), v + 16);
+            if (ck == nch - 1) {                            // sub-tile fully read -> MMA may reuse the slot
+                tc_fence_before();
+                mbar_arrive(bar_tempty0 + 8 * slot);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (j * 4 < width)
+                    sts128(st_a + (uint32_t)((j ^ (lane & 7)) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+        __syncwarp();
+    };
+    // rows of chunk (sub, ck); as each residual row is consumed, the same register is refilled with that row
+    // of the NEXT chunk (nco / nok), so one 8 x float4 buffer gives a full chunk period of load latency
+    auto stage_b = [&](int sub, int ck, ResRows& ra, int nco, bool nok) __attribute__((always_inline)) {
+        const int col0 = ck * 32;
+        const int width = min(32, P.nw - col0);
+        if (P.dbg & 64) return;
+        if (vec_ok) {
+            // lane = (row r = lane/8 + 4*i, 4 columns c4 = 4*(lane%8)): 4 rows x 128 B per instruction
+            bool cok;
+            const int co = lane_co(sub, ck, cok);
+            if (cok) {
+                float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (has_post) {
+                    sc = __ldg(reinterpret_cast<const float4*>(post_scale + co));
+                    sh = __ldg(reinterpret_cast<const float4*>(post_shift + co));
+                }
+                float* op = out_row + co;
+                const float* r1p = res1_row + co;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (FULL || m0 + 4 * i < M) {
+                        float4 tt = lds128(((i & 1) ? ld_a1 : ld_a0) + (uint32_t)((i >> 1) * 1024));
+                        tt.x = fmaf(tt.x, sc.x, sh.x); tt.y = fmaf(tt.y, sc.y, sh.y);
+                        tt.z = fmaf(tt.z, sc.z, sh.z); tt.w = fmaf(tt.w, sc.w, sh.w);
+                        if (relu) {
+                            tt.x = fmaxf(tt.x, 0.f); tt.y = fmaxf(tt.y, 0.f);
+                            tt.z = fmaxf(tt.z, 0.f); tt.w = fmaxf(tt.w, 0.f);
+                        }
+                        tt.x += ra.v[i].x; tt.y += ra.v[i].y; tt.z += ra.v[i].z; tt.w += ra.v[i].w;
+                        if (has1) {
+                            const float4 rb = __ldg(reinterpret_cast<const float4*>(r1p + i * ldr14));
+                            tt.x += rb.x; tt.y += rb.y; tt.z += rb.z; tt.w += rb.w;
+                        }
+                        *reinterpret_cast<float4*>(op + i * ldo4) = tt;
+                    }
+                }
+            }
+            if (nok) {
+                const float* nres = res0_row + nco;
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if (FULL || m0 + 4 * i < M) ra.v[i] = __ldg(reinterpret_cast<const float4*>(nres + i * ldr04));
+            }
+        } else {
+            const int co = n0 + sub * P.nw + col0 + lane;
+            const bool cok = lane < width && co < c.Cout;
+            float sc = 1.f, sh = 0.f;
+            if (cok && c.post_scale) {
+                sc = __ldg(c.post_scale + co);
+                sh = __ldg(c.post_shift + co);
+            }
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) {
+                const int m = mbase + r;
+                float tv;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(tv)
+                             : "r"(tile_s + (uint32_t)((r * 32 + ((((lane >> 2) ^ (r & 7)) << 2) | (lane & 3))) * 4)) : "memory");
+                if (cok && m < c.M) {
+                    float tt = fmaf(tv, sc, sh);
+                    if (c.post_relu) tt = fmaxf(tt, 0.f);
+                    if (c.res0) tt += __ldg(c.res0 + (size_t)m * c.ldr0 + co);
+                    if (c.res1) tt += __ldg(c.res1 + (size_t)m * c.ldr1 + co);
+                    c.out[(size_t)m * c.ldo + co] = tt;
+                }
+            }
+        }
+        __syncwarp();
+    };
+
+    ResRows ra;
+    {
+        bool cok;
+        const int co = lane_co(0, 0, cok);
+        epi_load_res<FULL>(ra, res0_row + co, ldr04, m0, c.M, pipe && cok);
+    }
+    int sub = 0, ck = 0;
+    const int nchunks = P.nsub * nch;
+    for (int e = 0; e < nchunks; ++e) {
+        int sub1 = sub, ck1 = ck + 1;
+        if (ck1 == nch) { ck1 = 0; ++sub1; }
+        bool nok = false;
+        int nco = 0;
+        if (e + 1 < nchunks) nco = lane_co(sub1, ck1, nok);
+        stage_a(sub, ck);
+        stage_b(sub, ck, ra, nco, nok && pipe);
+        sub = sub1; ck = ck1;
+    }
+}
+
 __device__ __forceinline__ void run_epilogue(const TcParams& P, uint8_t* epi_stage, uint32_t tmem_base,
                                              uint32_t bar_tfull0, uint32_t bar_tempty0, int n0, int warp,
                                              int lane) {
     const ConvParams& c = P.c;
     const int q = warp & 3;
-    float* tile = reinterpret_cast<float*>(epi_stage) + q * (32 * 32);
-    const int nch32 = (P.bn_cta + 31) >> 5;               // 32-column chunks (last may be 16 wide)
+    const uint32_t tile_s = smem_u32(epi_stage) + (uint32_t)q * (32 * 32 * 4);
     const bool vec_ok = ((c.ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(c.out) & 15) == 0) &&
                         (!c.res0 || (((c.ldr0 & 3) == 0) && ((reinterpret_cast<uintptr_t>(c.res0) & 15) == 0))) &&
                         (!c.res1 || (((c.ldr1 & 3) == 0) && ((reinterpret_cast<uintptr_t>(c.res1) & 15) == 0))) &&
                         ((c.Cout & 3) == 0) &&
                         (!c.post_scale || (((reinterpret_cast<uintptr_t>(c.post_scale) & 15) == 0) &&
                                            ((reinterpret_cast<uintptr_t>(c.post_shift) & 15) == 0)));
-    int ti = 0;
-    for (int t = blockIdx.x; t < P.n_mtiles; t += gridDim.x, ++ti) {
-        const int acc = ti % P.nacc;
-        const uint32_t acc_it = (uint32_t)(ti / P.nacc);
+    uint32_t u = 0;
+    for (int t = blockIdx.x; t < P.n_mtiles; t += gridDim.x, u += (uint32_t)P.nsub) {
         const int mbase = t * BM + q * 32;
-        // while the MMAs of this tile run: pull this warp's residual rows into L2
+        // pull the residual rows of the NEXT tile into L2 while this one is drained (the loads of this tile
+        // were prefetched one tile ago; the first tile relies on the chunk-ahead register pipeline)
         if (c.res0 || c.res1) {
-            const int m = mbase + lane;
-            if (m < c.M) {
-                const int cols = min(P.bn_cta, c.Cout - n0);
-                for (int cb = 0; cb < cols; cb += 32) {
-                    if (c.res0) asm volatile("prefetch.global.L2 [%0];" ::"l"(c.res0 + (size_t)m * c.ldr0 + n0 + cb));
-                    if (c.res1) asm volatile("prefetch.global.L2 [%0];" ::"l"(c.res1 + (size_t)m * c.ldr1 + n0 + cb));
+            const int tn = (t == (int)blockIdx.x) ? t : t + (int)gridDim.x;
+            for (int tt = tn; tt <= t + (int)gridDim.x && tt < P.n_mtiles; tt += gridDim.x) {
+                const int m = tt * BM + q * 32 + lane;
+                if (m < c.M) {
+                    const int cols = min(P.bn_cta, c.Cout - n0);
+                    for (int cb = 0; cb < cols; cb += 32) {
+                        if (c.res0) asm volatile("prefetch.global.L2 [%0];" ::"l"(c.res0 + (size_t)m * c.ldr0 + n0 + cb));
+                        if (c.res1) asm volatile("prefetch.global.L2 [%0];" ::"l"(c.res1 + (size_t)m * c.ldr1 + n0 + cb));
+                    }
                 }
             }
         }
-        mbar_wait(bar_tfull0 + 8 * acc, acc_it & 1);
-        tc_fence_after();
-        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * P.acc_stride);
-        for (int ck = 0; ck < nch32; ++ck) {
-            const int col0 = ck * 32;
-            const int width = min(32, P.bn_cta - col0);        // 32 or 16
-            {
-                float v[32];
-                tmem_ld16(trow + (uint32_t)col0, v);
-                if (width == 32) tmem_ld16(trow + (uint32_t)(col0 + 16), v + 16);
-                if (ck == nch32 - 1) {                          // accumulator fully read -> MMA may reuse it
-                    tc_fence_before();
-                    mbar_arrive(bar_tempty0 + 8 * acc);
-                }
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    if (j * 4 < width)
-                        *reinterpret_cast<float4*>(tile + lane * 32 + ((j ^ (lane & 7)) << 2)) =
-                            make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            }
-            __syncwarp();
-            if (vec_ok) {
-                // lane = (row r = lane/8 + 4*i, 4 columns c4 = 4*(lane%8)): 4 rows x 128 B per instruction
-                const int b4 = lane & 7;
-                const int co = n0 + col0 + b4 * 4;
-                const bool cok = b4 * 4 < width && co < c.Cout;
-                float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (cok && c.post_scale) {
-                    sc = __ldg(reinterpret_cast<const float4*>(c.post_scale + co));
-                    sh = __ldg(reinterpret_cast<const float4*>(c.post_shift + co));
-                }
-                float4 ra[8], rb[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int m = mbase + (lane >> 3) + 4 * i;
-                    ra[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    rb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (cok && m < c.M) {
-                        if (c.res0) ra[i] = __ldg(reinterpret_cast<const float4*>(c.res0 + (size_t)m * c.ldr0 + co));
-                        if (c.res1) rb[i] = __ldg(reinterpret_cast<const float4*>(c.res1 + (size_t)m * c.ldr1 + co));
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int r = (lane >> 3) + 4 * i;
-                    const int m = mbase + r;
-                    if (cok && m < c.M) {
-                        float4 tt = *reinterpret_cast<const float4*>(tile + r * 32 + ((b4 ^ (r & 7)) << 2));
-                        tt.x = fmaf(tt.x, sc.x, sh.x); tt.y = fmaf(tt.y, sc.y, sh.y);
-                        tt.z = fmaf(tt.z, sc.z, sh.z); tt.w = fmaf(tt.w, sc.w, sh.w);
-                        if (c.post_relu) {
-                            tt.x = fmaxf(tt.x, 0.f); tt.y = fmaxf(tt.y, 0.f);
-                            tt.z = fmaxf(tt.z, 0.f); tt.w = fmaxf(tt.w, 0.f);
-                        }
-                        tt.x += ra[i].x + rb[i].x; tt.y += ra[i].y + rb[i].y;
-                        tt.z += ra[i].z + rb[i].z; tt.w += ra[i].w + rb[i].w;
-                        *reinterpret_cast<float4*>(c.out + (size_t)m * c.ldo + co) = tt;
-                    }
-                }
-            } else {
-                const int co = n0 + col0 + lane;
-                const bool cok = lane < width && co < c.Cout;
-                float sc = 1.f, sh = 0.f;
-                if (cok && c.post_scale) {
-                    sc = __ldg(c.post_scale + co);
-                    sh = __ldg(c.post_shift + co);
-                }
-#pragma unroll 8
-                for (int r = 0; r < 32; ++r) {
-                    const int m = mbase + r;
-                    if (cok && m < c.M) {
-                        float tt = fmaf(tile[r * 32 + ((((lane >> 2) ^ (r & 7)) << 2) | (lane & 3))], sc, sh);
-                        if (c.post_relu) tt = fmaxf(tt, 0.f);
-                        if (c.res0) tt += __ldg(c.res0 + (size_t)m * c.ldr0 + co);
-                        if (c.res1) tt += __ldg(c.res1 + (size_t)m * c.ldr1 + co);
-                        c.out[(size_t)m * c.ldo + co] = tt;
-                    }
-                }
-            }
-            __syncwarp();
-        }
+        if (mbase + 32 <= c.M)
+            epilogue_tile<true>(P, tile_s, tmem_base, bar_tfull0, bar_tempty0, n0, q, lane, mbase, u, vec_ok);
+        else
+            epilogue_tile<false>(P, tile_s, tmem_base, bar_tfull0, bar_tempty0, n0, q, lane, mbase, u, vec_ok);
     }
 }
 
@@ -306,6 +418,18 @@ static inline bool make_map(CUtensorMap* map, const void* base, int k_pad, int r
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
+}
+
+// TMEM plan: as many nw-column slots as fit 512 columns (at most two tiles' worth).
+static inline void plan_tmem(TcParams& P) {
+    P.slot_stride = (P.nw + 31) / 32 * 32;
+    int ns = 512 / P.slot_stride;
+    if (ns > 2 * P.nsub) ns = 2 * P.nsub;
+    if (ns > 8) ns = 8;
+    P.nslots = ns;
+    int tm = 32;
+    while (tm < P.nslots * P.slot_stride) tm <<= 1;
+    P.tmem_cols = tm;
 }
 
 // N tiling rule shared with the host-side weight packer (dh_tc_cout_pad).

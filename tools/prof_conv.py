@@ -17,6 +17,10 @@ n, h, w, cin, cout, k = [int(a) for a in sys.argv[2:8]]
 precision = int(sys.argv[8]) if len(sys.argv) > 8 else 3
 reps = int(sys.argv[9]) if len(sys.argv) > 9 else 5
 dev = Dev(torch)
+if os.environ.get('DH_DBG'):
+    dev.lib.dh_set_option(dev.ctx.handle, b'dbg', int(os.environ['DH_DBG']))
+if os.environ.get('DH_SHARE'):
+    dev.lib.dh_set_option(dev.ctx.handle, b'share_a', int(os.environ['DH_SHARE']))
 rng = np.random.default_rng(0)
 x = dev.put(rng.standard_normal((n, h, w, cin)))
 r0 = dev.put(rng.standard_normal((n, h, w, cout)))
