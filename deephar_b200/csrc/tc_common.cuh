@@ -16,12 +16,15 @@ constexpr int NPROD = 256;             // A producers: warps 0..7 (two warpgroup
 constexpr int NEPI = 128;              // epilogue: warps 8..11 (one warpgroup; warp % 4 = TMEM lane quarter)
 constexpr int WARP_EPI0 = 8, WARP_TMA = 12, WARP_MMA = 13;
 constexpr int NTHREADS = 512;          // 4 warpgroups; the last one holds the TMA + MMA threads
-constexpr int EPI_STAGE_BYTES = 4 * 32 * 128;   // per epilogue warp: 32 rows x 32 fp32, XOR-swizzled
-// register budget (setmaxnreg): 256*168 + 128*136 + 128*40 = 65536
-constexpr int REGS_PROD = 168, REGS_EPI = 136, REGS_CTRL = 40;
+constexpr int MAX_BN_CTA = 288;
+constexpr int EPI_TILE_BYTES = 4 * 32 * 128;    // per epilogue warp: 32 rows x 32 fp32, XOR-swizzled
+// + this CTA's BN scale | shift columns (read per chunk with LDS: a global load there would share a
+// scoreboard with the in-flight residual loads and drain them early)
+constexpr int EPI_STAGE_BYTES = EPI_TILE_BYTES + 2 * MAX_BN_CTA * 4;
+// register budget (setmaxnreg): 256*168 + 128*144 + 128*32 = 65536
+constexpr int REGS_PROD = 168, REGS_EPI = 144, REGS_CTRL = 32;
 constexpr int A_TILE_BYTES = BM * 128; // 16 KB per (hi | lo)
 constexpr int MAX_STAGES = 4;
-constexpr int MAX_BN_CTA = 288;
 
 struct TcParams {
     ConvParams c;
@@ -144,6 +147,24 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 32 consecutive columns of this warp's 32 lanes: two x16 loads in flight, one wait
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr + 16));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // K-major, 128-byte swizzle UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor):
 // start>>4 [0,14) | LBO>>4 [16,30) (unused for swizzled K-major, 1) | SBO>>4 [32,46) = 1024 B
 // (8 rows x 128 B per swizzle atom) | version 1 [46,48) | layout SWIZZLE_128B = 2 [61,64).
@@ -202,152 +223,155 @@ __device__ __forceinline__ void epi_load_res(ResRows& r, const float* p, size_t 
 // 32-column chunk ahead (its global-load latency would otherwise serialise the drain of the accumulator).
 // This loop is a single-warp serial instruction stream on the critical path of every tile, so it is
 // written for a short stream: shared-space addresses, hoisted row pointers, one predicate per lane.
-template <bool FULL>
+// (Pinning loop invariants in registers with an asm mov -- so that the compiler cannot rematerialise them
+// with LDC / S2R, which share scoreboards with the in-flight residual loads -- was tried and measured
+// slower: the extra live registers cost more than the early scoreboard waits.)
+__device__ __forceinline__ int pin(int x) { return x; }
+__device__ __forceinline__ uint32_t pin(uint32_t x) { return x; }
+
+template <bool FULL, bool RES1>
 __device__ __forceinline__ void epilogue_tile(const TcParams& P, uint32_t tile_s, uint32_t tmem_base,
                                               uint32_t bar_tfull0, uint32_t bar_tempty0, int n0, int q, int lane,
-                                              int mbase, uint32_t u0, bool vec_ok) {
+                                              int mbase, uint32_t u0, bool vec_ok, uint32_t aff_s) {
     const ConvParams& c = P.c;
-    const int nch = (P.nw + 31) >> 5;                     // 32-column chunks per sub-tile (last may be 16 wide)
+    const int nw = pin(P.nw), nsub = pin(P.nsub);
+    const int nch = pin((nw + 31) >> 5);                  // 32-column chunks per sub-tile (last may be 16 wide)
+    const int wlast = pin(nw - (nch - 1) * 32);           // width of the last chunk: 32 or 16
+    lane = pin(lane);
+    n0 = pin(n0);
     const int b4 = lane & 7, r0 = lane >> 3;
     const int m0 = mbase + r0;
+    const int M = pin(c.M), Cout = pin(c.Cout);
     const size_t ldo4 = (size_t)c.ldo * 4, ldr04 = (size_t)c.ldr0 * 4, ldr14 = (size_t)c.ldr1 * 4;
-    const uint32_t st_a = tile_s + (uint32_t)lane * 128u;                       // transpose: write row = lane
-    const uint32_t ld_a0 = tile_s + (uint32_t)(r0 * 128 + ((b4 ^ r0) << 4));    // read rows r0, r0 + 8, ...
-    const uint32_t ld_a1 = tile_s + (uint32_t)((r0 + 4) * 128 + ((b4 ^ (r0 + 4)) << 4));   // rows r0 + 4, r0 + 12, ...
-    const bool pipe = vec_ok && c.res0 != nullptr;
+    const uint32_t st_a = pin(tile_s + (uint32_t)lane * 128u);                  // transpose: write row = lane
+    const uint32_t ld_a0 = pin(tile_s + (uint32_t)(r0 * 128 + ((b4 ^ r0) << 4)));   // read rows r0, r0 + 8, ...
+    const uint32_t ld_a1 = pin(tile_s + (uint32_t)((r0 + 4) * 128 + ((b4 ^ (r0 + 4)) << 4)));   // rows r0 + 4, ...
     float* out_row = c.out + (size_t)m0 * c.ldo;
     const float* res0_row = c.res0 ? c.res0 + (size_t)m0 * c.ldr0 : nullptr;
     const float* res1_row = c.res1 ? c.res1 + (size_t)m0 * c.ldr1 : nullptr;
     const float* post_scale = c.post_scale;
     const float* post_shift = c.post_shift;
-    const bool has_post = c.post_scale != nullptr, has1 = c.res1 != nullptr, relu = c.post_relu != 0;
-    const int M = c.M;
+    const bool has_post = c.post_scale != nullptr, relu = c.post_relu != 0;
+    const bool pipe0 = vec_ok && c.res0 != nullptr, pipe1 = vec_ok && c.res1 != nullptr;
 
-    // chunk iterator (sub, ck) -> output column of this lane
-    auto lane_co = [&](int sub, int ck, bool& cok) __attribute__((always_inline)) {
-        const int col0 = ck * 32;
-        const int co = n0 + sub * P.nw + col0 + b4 * 4;
-        cok = (b4 * 4 < P.nw - col0) && (co < c.Cout);
-        return co;
-    };
-    auto stage_a = [&](int sub, int ck) __attribute__((always_inline)) {
-        const int col0 = ck * 32;
-        const int width = min(32, P.nw - col0);            // 32 or 16
+    ResRows ra, rb;
+    int co = n0 + b4 * 4;                                  // this lane's first output column of the current chunk
+    {
+        const bool cok = co < Cout;                        // chunk 0 is at least 16 wide: b4 * 4 < 32 always; 16-wide: b4 < 4
+        const bool ok0 = cok && (b4 * 4 < (nch == 1 ? wlast : 32));
+        epi_load_res<FULL>(ra, res0_row + co, ldr04, m0, M, pipe0 && ok0);
+        epi_load_res<FULL>(rb, res1_row + co, ldr14, m0, M, pipe1 && ok0);
+    }
+    for (int sub = 0; sub < nsub; ++sub) {
         const uint32_t u = u0 + (uint32_t)sub;
         const uint32_t slot = u % (uint32_t)P.nslots;
-        if (ck == 0) {
-            mbar_wait(bar_tfull0 + 8 * slot, (u / (uint32_t)P.nslots) & 1);
-            tc_fence_after();
-        }
+        mbar_wait(bar_tfull0 + 8 * slot, (u / (uint32_t)P.nslots) & 1);
+        tc_fence_after();
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + slot * (uint32_t)P.slot_stride;
         if (P.dbg & 64) {
-            if (ck == nch - 1) {
-                tc_fence_before();
-                mbar_arrive(bar_tempty0 + 8 * slot);
-            }
-            return;
+            tc_fence_before();
+            mbar_arrive(bar_tempty0 + 8 * slot);
+            continue;
         }
-        {
-            float v[32];
-            tmem_ld16(trow + (uint32_t)col0, v);
-            if (width == 32) tmem_ld16(trow + (uint32_t)(col0 + 16), v + 16);
-            if (ck == nch - 1) {                            // sub-tile fully read -> MMA may reuse the slot
-                tc_fence_before();
-                mbar_arrive(bar_tempty0 + 8 * slot);
+        co = n0 + sub * nw + b4 * 4;
+        for (int ck = 0; ck < nch; ++ck, co += 32) {
+            const bool last = ck == nch - 1;
+            const int width = last ? wlast : 32;
+            const bool cok = (b4 * 4 < width) && (co < Cout);
+            // next chunk of this tile (for the residual pipeline)
+            const bool more = !last || (sub + 1 < nsub);
+            const int nco = last ? n0 + (sub + 1) * nw + b4 * 4 : co + 32;
+            const int nwidth = last ? (nch == 1 ? wlast : 32) : (ck + 1 == nch - 1 ? wlast : 32);
+            const bool nok = more && (b4 * 4 < nwidth) && (nco < Cout);
+            // BN affine of this chunk's columns from the CTA's shared-memory copy
+            float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (vec_ok && has_post && cok) {
+                sc = lds128(aff_s + (uint32_t)(co - n0) * 4u);
+                sh = lds128(aff_s + (uint32_t)(MAX_BN_CTA + co - n0) * 4u);
             }
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (j * 4 < width)
-                    sts128(st_a + (uint32_t)((j ^ (lane & 7)) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        }
-        __syncwarp();
-    };
-    // rows of chunk (sub, ck); as each residual row is consumed, the same register is refilled with that row
-    // of the NEXT chunk (nco / nok), so one 8 x float4 buffer gives a full chunk period of load latency
-    auto stage_b = [&](int sub, int ck, ResRows& ra, int nco, bool nok) __attribute__((always_inline)) {
-        const int col0 = ck * 32;
-        const int width = min(32, P.nw - col0);
-        if (P.dbg & 64) return;
-        if (vec_ok) {
-            // lane = (row r = lane/8 + 4*i, 4 columns c4 = 4*(lane%8)): 4 rows x 128 B per instruction
-            bool cok;
-            const int co = lane_co(sub, ck, cok);
-            if (cok) {
-                float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (has_post) {
-                    sc = __ldg(reinterpret_cast<const float4*>(post_scale + co));
-                    sh = __ldg(reinterpret_cast<const float4*>(post_shift + co));
+            {
+                float v[32];
+                if (width == 32) tmem_ld32(trow + (uint32_t)(ck * 32), v);
+                else tmem_ld16(trow + (uint32_t)(ck * 32), v);
+                if (last) {                                     // sub-tile fully read -> MMA may reuse the slot
+                    tc_fence_before();
+                    mbar_arrive(bar_tempty0 + 8 * slot);
                 }
-                float* op = out_row + co;
-                const float* r1p = res1_row + co;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    if (FULL || m0 + 4 * i < M) {
-                        float4 tt = lds128(((i & 1) ? ld_a1 : ld_a0) + (uint32_t)((i >> 1) * 1024));
-                        tt.x = fmaf(tt.x, sc.x, sh.x); tt.y = fmaf(tt.y, sc.y, sh.y);
-                        tt.z = fmaf(tt.z, sc.z, sh.z); tt.w = fmaf(tt.w, sc.w, sh.w);
-                        if (relu) {
-                            tt.x = fmaxf(tt.x, 0.f); tt.y = fmaxf(tt.y, 0.f);
-                            tt.z = fmaxf(tt.z, 0.f); tt.w = fmaxf(tt.w, 0.f);
+                for (int j = 0; j < 8; ++j)
+                    if (j * 4 < width)
+                        sts128(st_a + (uint32_t)((j ^ (lane & 7)) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+            __syncwarp();
+            if (vec_ok) {
+                // lane = (row r = lane/8 + 4*i, 4 columns c4 = 4*(lane%8)): 4 rows x 128 B per instruction.
+                // As each residual row is consumed its register is refilled with that row of the NEXT chunk,
+                // so one 8 x float4 buffer per residual gives a full chunk period of load latency.
+                if (cok) {
+                    float* op = out_row + co;
+                    const float2 sc01 = make_float2(sc.x, sc.y), sc23 = make_float2(sc.z, sc.w);
+                    const float2 sh01 = make_float2(sh.x, sh.y), sh23 = make_float2(sh.z, sh.w);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        if (FULL || m0 + 4 * i < M) {
+                            const float4 t4 = lds128(((i & 1) ? ld_a1 : ld_a0) + (uint32_t)((i >> 1) * 1024));
+                            float2 a = make_float2(t4.x, t4.y), b = make_float2(t4.z, t4.w);
+                            if (has_post) { a = __ffma2_rn(a, sc01, sh01); b = __ffma2_rn(b, sc23, sh23); }
+                            if (relu) {
+                                a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f);
+                                b.x = fmaxf(b.x, 0.f); b.y = fmaxf(b.y, 0.f);
+                            }
+                            if (pipe0) {
+                                a = __fadd2_rn(a, make_float2(ra.v[i].x, ra.v[i].y));
+                                b = __fadd2_rn(b, make_float2(ra.v[i].z, ra.v[i].w));
+                            }
+                            if (pipe1) {
+                                a = __fadd2_rn(a, make_float2(rb.v[i].x, rb.v[i].y));
+                                b = __fadd2_rn(b, make_float2(rb.v[i].z, rb.v[i].w));
+                            }
+                            *reinterpret_cast<float4*>(op + i * ldo4) = make_float4(a.x, a.y, b.x, b.y);
                         }
-                        tt.x += ra.v[i].x; tt.y += ra.v[i].y; tt.z += ra.v[i].z; tt.w += ra.v[i].w;
-                        if (has1) {
-                            const float4 rb = __ldg(reinterpret_cast<const float4*>(r1p + i * ldr14));
-                            tt.x += rb.x; tt.y += rb.y; tt.z += rb.z; tt.w += rb.w;
-                        }
-                        *reinterpret_cast<float4*>(op + i * ldo4) = tt;
+                    }
+                }
+                if (nok) {
+                    if (pipe0) {
+                        const float* nres = res0_row + nco;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            if (FULL || m0 + 4 * i < M) ra.v[i] = __ldg(reinterpret_cast<const float4*>(nres + i * ldr04));
+                    }
+                    if (pipe1) {
+                        const float* nres1 = res1_row + nco;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            if (FULL || m0 + 4 * i < M) rb.v[i] = __ldg(reinterpret_cast<const float4*>(nres1 + i * ldr14));
+                    }
+                }
+            } else {
+                const int cos = n0 + sub * nw + ck * 32 + lane;
+                const bool coks = lane < width && cos < Cout;
+                float scs = 1.f, shs = 0.f;
+                if (coks && has_post) {
+                    scs = __ldg(post_scale + cos);
+                    shs = __ldg(post_shift + cos);
+                }
+#pragma unroll 8
+                for (int r = 0; r < 32; ++r) {
+                    const int m = mbase + r;
+                    float tv;
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(tv)
+                                 : "r"(tile_s + (uint32_t)((r * 32 + ((((lane >> 2) ^ (r & 7)) << 2) | (lane & 3))) * 4)) : "memory");
+                    if (coks && m < M) {
+                        float tt = fmaf(tv, scs, shs);
+                        if (relu) tt = fmaxf(tt, 0.f);
+                        if (c.res0) tt += __ldg(c.res0 + (size_t)m * c.ldr0 + cos);
+                        if (c.res1) tt += __ldg(c.res1 + (size_t)m * c.ldr1 + cos);
+                        c.out[(size_t)m * c.ldo + cos] = tt;
                     }
                 }
             }
-            if (nok) {
-                const float* nres = res0_row + nco;
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    if (FULL || m0 + 4 * i < M) ra.v[i] = __ldg(reinterpret_cast<const float4*>(nres + i * ldr04));
-            }
-        } else {
-            const int co = n0 + sub * P.nw + col0 + lane;
-            const bool cok = lane < width && co < c.Cout;
-            float sc = 1.f, sh = 0.f;
-            if (cok && c.post_scale) {
-                sc = __ldg(c.post_scale + co);
-                sh = __ldg(c.post_shift + co);
-            }
-#pragma unroll 8
-            for (int r = 0; r < 32; ++r) {
-                const int m = mbase + r;
-                float tv;
-                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(tv)
-                             : "r"(tile_s + (uint32_t)((r * 32 + ((((lane >> 2) ^ (r & 7)) << 2) | (lane & 3))) * 4)) : "memory");
-                if (cok && m < c.M) {
-                    float tt = fmaf(tv, sc, sh);
-                    if (c.post_relu) tt = fmaxf(tt, 0.f);
-                    if (c.res0) tt += __ldg(c.res0 + (size_t)m * c.ldr0 + co);
-                    if (c.res1) tt += __ldg(c.res1 + (size_t)m * c.ldr1 + co);
-                    c.out[(size_t)m * c.ldo + co] = tt;
-                }
-            }
+            __syncwarp();
         }
-        __syncwarp();
-    };
-
-    ResRows ra;
-    {
-        bool cok;
-        const int co = lane_co(0, 0, cok);
-        epi_load_res<FULL>(ra, res0_row + co, ldr04, m0, c.M, pipe && cok);
-    }
-    int sub = 0, ck = 0;
-    const int nchunks = P.nsub * nch;
-    for (int e = 0; e < nchunks; ++e) {
-        int sub1 = sub, ck1 = ck + 1;
-        if (ck1 == nch) { ck1 = 0; ++sub1; }
-        bool nok = false;
-        int nco = 0;
-        if (e + 1 < nchunks) nco = lane_co(sub1, ck1, nok);
-        stage_a(sub, ck);
-        stage_b(sub, ck, ra, nco, nok && pipe);
-        sub = sub1; ck = ck1;
     }
 }
 
@@ -363,6 +387,17 @@ __device__ __forceinline__ void run_epilogue(const TcParams& P, uint8_t* epi_sta
                         ((c.Cout & 3) == 0) &&
                         (!c.post_scale || (((reinterpret_cast<uintptr_t>(c.post_scale) & 15) == 0) &&
                                            ((reinterpret_cast<uintptr_t>(c.post_shift) & 15) == 0)));
+    // this CTA's BN columns -> shared memory (epilogue warps only: named barrier 3)
+    const uint32_t aff_s = smem_u32(epi_stage) + EPI_TILE_BYTES;
+    if (c.post_scale) {
+        float* aff = reinterpret_cast<float*>(epi_stage + EPI_TILE_BYTES);
+        for (int i = (warp & 3) * 32 + lane; i < P.bn_cta; i += NEPI) {
+            const bool in = n0 + i < c.Cout;
+            aff[i] = in ? __ldg(c.post_scale + n0 + i) : 1.f;
+            aff[MAX_BN_CTA + i] = in ? __ldg(c.post_shift + n0 + i) : 0.f;
+        }
+    }
+    asm volatile("bar.sync 3, %0;" ::"r"(NEPI) : "memory");
     uint32_t u = 0;
     for (int t = blockIdx.x; t < P.n_mtiles; t += gridDim.x, u += (uint32_t)P.nsub) {
         const int mbase = t * BM + q * 32;
@@ -382,9 +417,9 @@ __device__ __forceinline__ void run_epilogue(const TcParams& P, uint8_t* epi_sta
             }
         }
         if (mbase + 32 <= c.M)
-            epilogue_tile<true>(P, tile_s, tmem_base, bar_tfull0, bar_tempty0, n0, q, lane, mbase, u, vec_ok);
+            epilogue_tile<true, true>(P, tile_s, tmem_base, bar_tfull0, bar_tempty0, n0, q, lane, mbase, u, vec_ok, aff_s);
         else
-            epilogue_tile<false>(P, tile_s, tmem_base, bar_tfull0, bar_tempty0, n0, q, lane, mbase, u, vec_ok);
+            epilogue_tile<false, true>(P, tile_s, tmem_base, bar_tfull0, bar_tempty0, n0, q, lane, mbase, u, vec_ok, aff_s);
     }
 }
 

@@ -24,9 +24,11 @@ if os.environ.get('DH_SHARE'):
 rng = np.random.default_rng(0)
 x = dev.put(rng.standard_normal((n, h, w, cin)))
 r0 = dev.put(rng.standard_normal((n, h, w, cout)))
+r1 = dev.put(rng.standard_normal((n, h, w, cout)))
 out = dev.empty(n, h, w, cout)
 post = (rng.uniform(0.5, 1.5, cout), rng.standard_normal(cout))
-d = conv_desc(dev, (k, k), pre_relu=True, post=post, res=[dev.view(r0)], precision=precision)
+d = conv_desc(dev, (k, k), pre_relu=True, post=post, res=[] if os.environ.get('DH_NORES') else ([dev.view(r0), dev.view(r1)] if os.environ.get('DH_RES2') else [dev.view(r0)]),
+              precision=precision)
 xv, ov = dev.view(x), dev.view(out)
 if kind == 'sep':
     dw = dev.put(rng.standard_normal((k, k, cin, 1)) / k)
