@@ -27,6 +27,7 @@ constexpr int SBK = 32;                    // channels (bf16 K elements) per K-b
 constexpr int A_BYTES = BM * 64;           // 8 KB per (hi | lo)
 constexpr int NWG = 128;                   // threads per producer warpgroup
 constexpr int WARP_PATCH = 14;
+constexpr int NA = 3;                      // A-tile ring depth (the weight ring stays 2 deep)
 
 struct SepParams {
     TcParams t;
@@ -74,19 +75,23 @@ sep_tma_kernel(const __grid_constant__ SepParams SP, const __grid_constant__ CUt
     const int warp = tid >> 5, lane = tid & 31;
     const bool want_lo = P.precision == 3;
     const int b_bytes = P.bn_cta * 64;                       // per (hi | lo)
-    const int stage_bytes = 2 * A_BYTES + 2 * b_bytes;
-    uint8_t* patch0 = smem + 2 * stage_bytes;
+    // smem: A ring [NA][hi | lo] | weight ring [2][hi | lo] | patches [2] | epilogue staging | barriers
+    uint8_t* b_ring = smem + NA * 2 * A_BYTES;
+    uint8_t* patch0 = b_ring + 2 * 2 * b_bytes;
     uint8_t* epi_stage = patch0 + 2 * SP.patch_stride;
     uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage + EPI_STAGE_BYTES);
-    // bars: full[2] | empty[2 stages][2] | pfull[2] | pempty[2] | tfull[MAX_SLOTS] | tempty[MAX_SLOTS]
-    // empty[s][u & 1] is signalled when use u of stage s has been consumed by the MMAs.  Two barriers per
-    // stage, alternating by use: in the cluster variant the two producer warpgroups write the SAME stage on
-    // alternate uses, so with one barrier each warpgroup would skip every other phase -- and an mbarrier
-    // parity wait is only meaningful one phase ahead.  With two, every waiter sees consecutive phases.
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10 + 2 * MAX_SLOTS);
-    const uint32_t bar_full0 = smem_u32(bars), bar_empty0 = smem_u32(bars + 2), bar_pfull0 = smem_u32(bars + 6),
-                   bar_pempty0 = smem_u32(bars + 8), bar_tfull0 = smem_u32(bars + 10),
-                   bar_tempty0 = smem_u32(bars + 10 + MAX_SLOTS);
+    // bars: fullA[NA] | emptyA[NA][2] | fullB[2] | emptyB[2] | pfull[2] | pempty[2] | tfull[MAX_SLOTS] | tempty[MAX_SLOTS]
+    // K-block g uses A stage g % NA (use g / NA) and weight stage g & 1 (use g >> 1).  In the cluster variant
+    // K-block g is produced by CTA g & 1, so consecutive own productions land in different A stages and the
+    // store of one does not have to wait for the MMAs of the previous one.
+    // emptyA[s][u & 1] is signalled when use u of stage s has been consumed by the MMAs (of both CTAs).  Two
+    // barriers per stage, alternating by use, so that every waiter sees consecutive phases of its barrier.
+    constexpr int NB_A = NA + 2 * NA;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NB_A + 8 + 2 * MAX_SLOTS);
+    const uint32_t bar_full0 = smem_u32(bars), bar_empty0 = smem_u32(bars + NA), bar_fullb0 = smem_u32(bars + NB_A),
+                   bar_emptyb0 = smem_u32(bars + NB_A + 2), bar_pfull0 = smem_u32(bars + NB_A + 4),
+                   bar_pempty0 = smem_u32(bars + NB_A + 6), bar_tfull0 = smem_u32(bars + NB_A + 8),
+                   bar_tempty0 = smem_u32(bars + NB_A + 8 + MAX_SLOTS);
     const int n0 = blockIdx.y * P.bn_cta;
     const int nkb = P.n_kblocks;
     const uint32_t my_rank = SHARE ? cluster_ctarank() : 0u;
@@ -95,16 +100,16 @@ sep_tma_kernel(const __grid_constant__ SepParams SP, const __grid_constant__ CUt
         tma_prefetch_desc(&map_hi);
         if (want_lo) tma_prefetch_desc(&map_lo);
         tma_prefetch_desc(&map_x);
+        for (int s = 0; s < NA; ++s) {
+            // fullA: SHARE: one arrival per use -- the elected producer thread (own K-block) or the TMA thread's
+            // arrive.expect_tx for the A bytes the peer pushes; else every producer thread of the warpgroup
+            mbar_init(bar_full0 + 8 * s, SHARE ? 1u : (uint32_t)NWG);
+            mbar_init(bar_empty0 + 16 * s, SHARE ? 2u : 1u);                       // MMA commits (of both CTAs)
+            mbar_init(bar_empty0 + 16 * s + 8, SHARE ? 2u : 1u);
+        }
         for (int s = 0; s < 2; ++s) {
-            if (SHARE) {
-                mbar_init(bar_full0 + 8 * s, (uint32_t)s == my_rank ? 2u : 1u);   // own: TMA thread + elected producer
-                mbar_init(bar_empty0 + 16 * s, 2);                                 // MMA commits of both CTAs
-                mbar_init(bar_empty0 + 16 * s + 8, 2);
-            } else {
-                mbar_init(bar_full0 + 8 * s, NWG + 1);
-                mbar_init(bar_empty0 + 16 * s, 1);
-                mbar_init(bar_empty0 + 16 * s + 8, 1);
-            }
+            mbar_init(bar_fullb0 + 8 * s, 1);
+            mbar_init(bar_emptyb0 + 8 * s, 1);
             mbar_init(bar_pfull0 + 8 * s, 1);
             mbar_init(bar_pempty0 + 8 * s, NWG);
         }
@@ -182,10 +187,10 @@ sep_tma_kernel(const __grid_constant__ SepParams SP, const __grid_constant__ CUt
             }
             if (!(SP.dbg & 2)) mbar_arrive(pempty);    // patch buffer may be refilled
 
-            const int s = g & 1;
-            const uint32_t it = (uint32_t)(g >> 1);
+            const int s = g % NA;
+            const uint32_t it = (uint32_t)(g / NA);
             wait_stage_free(bar_empty0, s, it);
-            uint8_t* a_hi = smem + (size_t)s * stage_bytes;
+            uint8_t* a_hi = smem + (size_t)s * (2 * A_BYTES);
             uint8_t* a_lo = a_hi + A_BYTES;
 #pragma unroll
             for (int o = 0; o < 4; ++o)
@@ -226,18 +231,25 @@ sep_tma_kernel(const __grid_constant__ SepParams SP, const __grid_constant__ CUt
                 const uint32_t tx_a = (SP.dbg & 8) ? 0u : (uint32_t)(want_lo ? 2 : 1) * (uint32_t)A_BYTES;
                 for (int g = 0; g < total_g; ++g) {
                     const int ti = g / nkb, kb = g - ti * nkb;
-                    const int s = g & 1;
-                    const uint32_t it = (uint32_t)(g >> 1);
-                    wait_stage_free(bar_empty0, s, it);
-                    const uint32_t full = bar_full0 + 8 * s;
-                    mbar_arrive_expect_tx(full, tx + ((SHARE && (uint32_t)s != my_rank) ? tx_a : 0u));
-                    const uint32_t b_hi = smem_u32(smem + (size_t)s * stage_bytes + 2 * A_BYTES);
+                    const int sb = g & 1;
+                    const uint32_t itb = (uint32_t)(g >> 1);
+                    if (itb >= 1) mbar_wait(bar_emptyb0 + 8 * sb, (itb - 1) & 1);
+                    const uint32_t full = bar_fullb0 + 8 * sb;
+                    mbar_arrive_expect_tx(full, tx);
+                    const uint32_t b_hi = smem_u32(b_ring + (size_t)sb * (2 * b_bytes));
                     const uint32_t b_lo = b_hi + (uint32_t)b_bytes;
                     if (!(SP.dbg & 16))
                     for (int sub = 0; sub < P.nsub; ++sub) {
                         tma_load_2d(b_hi + (uint32_t)(sub * P.nw * 64), &map_hi, kb * SBK, n0 + sub * P.nw, full);
                         if (want_lo)
                             tma_load_2d(b_lo + (uint32_t)(sub * P.nw * 64), &map_lo, kb * SBK, n0 + sub * P.nw, full);
+                    }
+                    if (SHARE && (uint32_t)(g & 1) != my_rank) {
+                        // the peer produces this K-block: arm our fullA for the bytes it will push (the previous
+                        // use of the stage has been consumed by both CTAs, so the barrier is in the right phase)
+                        const int sa = g % NA;
+                        wait_stage_free(bar_empty0, sa, (uint32_t)(g / NA));
+                        mbar_arrive_expect_tx(bar_full0 + 8 * sa, tx_a);
                     }
                 }
             }
@@ -264,7 +276,8 @@ sep_tma_kernel(const __grid_constant__ SepParams SP, const __grid_constant__ CUt
             // Descriptors differ only in the 14-bit start-address field, so they are base + (offset >> 4).
             const bool leader = elect_one();
             const uint64_t dbase = make_desc64(smem_u32(smem));
-            const uint32_t st16 = (uint32_t)stage_bytes >> 4, alo16 = A_BYTES >> 4, b16 = (2 * A_BYTES) >> 4,
+            const uint64_t dbase_b = make_desc64(smem_u32(b_ring));
+            const uint32_t sta16 = (2 * A_BYTES) >> 4, stb16 = (uint32_t)(2 * b_bytes) >> 4, alo16 = A_BYTES >> 4,
                            blo16 = (uint32_t)b_bytes >> 4, sub16 = (uint32_t)(P.nw * 64) >> 4;
             uint32_t u = 0;                                    // accumulator use counter (tile * nsub + sub)
             int g = 0;
@@ -280,9 +293,10 @@ sep_tma_kernel(const __grid_constant__ SepParams SP, const __grid_constant__ CUt
                     }
                 }
                 for (int kb = 0; kb < nkb; ++kb, ++g) {
-                    const int s = g & 1;
-                    const uint32_t it = (uint32_t)(g >> 1);
+                    const int s = g % NA, sb = g & 1;
+                    const uint32_t it = (uint32_t)(g / NA);
                     if (!(P.dbg & 128)) mbar_wait(bar_full0 + 8 * s, it & 1);
+                    mbar_wait(bar_fullb0 + 8 * sb, (uint32_t)(g >> 1) & 1);
                     if (kb == 0) {                               // the epilogue must have drained the slots
 #pragma unroll
                         for (int sub = 0; sub < MAX_NSUB; ++sub)
@@ -294,11 +308,11 @@ sep_tma_kernel(const __grid_constant__ SepParams SP, const __grid_constant__ CUt
                     }
                     tc_fence_after();
                     if (leader) {
-                        const uint64_t da = dbase + (uint64_t)((uint32_t)s * st16);
+                        const uint64_t da = dbase + (uint64_t)((uint32_t)s * sta16);
 #pragma unroll
                         for (int sub = 0; sub < MAX_NSUB; ++sub) {
                             if (sub < P.nsub) {
-                                const uint64_t db = da + (uint64_t)(b16 + (uint32_t)sub * sub16);
+                                const uint64_t db = dbase_b + (uint64_t)((uint32_t)sb * stb16 + (uint32_t)sub * sub16);
 #pragma unroll
                                 for (int k = 0; k < SBK / 16; ++k) {
                                     const uint32_t acc0 = (kb > 0 || k > 0) ? 1u : 0u;
@@ -312,6 +326,7 @@ sep_tma_kernel(const __grid_constant__ SepParams SP, const __grid_constant__ CUt
                         }
                         if (SHARE) umma_commit_pair(bar_empty0 + 16 * s + 8 * (it & 1));
                         else umma_commit(bar_empty0 + 16 * s + 8 * (it & 1));
+                        umma_commit(bar_emptyb0 + 8 * sb);
                     }
                     __syncwarp();
                 }
@@ -403,8 +418,8 @@ int dh_launch_sep_tma(dh_ctx* ctx, const ConvParams& p, const dh_packed_w* packe
     SP.patch_stride = (SP.patch_bytes + 1023) / 1024 * 1024;
     SP.dbg = ctx->dbg;
     P.dbg = ctx->dbg;
-    const int stage_bytes = 2 * A_BYTES + 2 * P.bn_cta * 64;
-    const size_t smem = (size_t)2 * stage_bytes + 2 * (size_t)SP.patch_stride + EPI_STAGE_BYTES + 256 + 1024;
+    const size_t smem = (size_t)NA * 2 * A_BYTES + (size_t)2 * 2 * P.bn_cta * 64 + 2 * (size_t)SP.patch_stride +
+                        EPI_STAGE_BYTES + 512 + 1024;
     if (smem > 227 * 1024) {
         dh_set_error("dh_launch_sep_tma: tile does not fit shared memory");
         return -1;
