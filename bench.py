@@ -182,7 +182,7 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--micro-batch', type=int, default=128, help='frames per forward call')
+    ap.add_argument('--micro-batch', type=int, default=256, help='frames per forward call')
     ap.add_argument('--workload', default='reception2d', choices=['reception2d', 'spnet_penn', 'spnet_ntu'],
                     help='reception2d = BASELINE configs[1] model (headline); spnet_* = configs[3]/[4] models')
     ap.add_argument('--no-cpu-baseline', action='store_true')

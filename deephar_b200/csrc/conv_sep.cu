@@ -45,6 +45,11 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
         : "memory");
 }
 
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global [%0, {%1, %2, %3, %4}];"
+                 ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
 // K-major, 64-byte swizzle UMMA descriptor: SBO = 512 B (8 rows x 64 B), layout SWIZZLE_64B = 4.
 __device__ __forceinline__ uint64_t make_desc64(uint32_t smem_addr) {
     return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) |
@@ -257,14 +262,25 @@ sep_tma_kernel(const __grid_constant__ SepParams SP, const __grid_constant__ CUt
             // ======================= input patches via 4-D TMA =======================
             if (lane == 0 && !(SP.dbg & 2)) {
                 const ConvParams& c = P.c;
-                for (int j = 0; j < n_own; ++j) {
+                auto coords = [&](int j, int& kb, int& nf, int& y0) {
                     const int g = SHARE ? 2 * j + (int)my_rank : j;
-                    const int ti = g / nkb, kb = g - ti * nkb;
+                    const int ti = g / nkb;
+                    kb = g - ti * nkb;
                     const int t = blockIdx.x + ti * gridDim.x;
-                    const int w = j & 1;
-                    mbar_wait(bar_pempty0 + 8 * w, (uint32_t)(((j >> 1) & 1) ^ 1));
                     const int grow = (t * BM) / TW;                 // global row index (n*H + y) of the tile's first row
-                    const int nf = grow / c.H, y0 = grow - nf * c.H;
+                    nf = grow / c.H;
+                    y0 = grow - nf * c.H;
+                };
+                for (int j = 0; j < n_own; ++j) {
+                    int kb, nf, y0;
+                    coords(j, kb, nf, y0);
+                    const int w = j & 1;
+                    if ((SP.dbg & 1024) && j + 2 < n_own) {         // pull the patch after next into L2
+                        int kb2, nf2, y2;
+                        coords(j + 2, kb2, nf2, y2);
+                        tma_prefetch_4d(&map_x, kb2 * SBK, -PAD, y2 - PAD, nf2);
+                    }
+                    mbar_wait(bar_pempty0 + 8 * w, (uint32_t)(((j >> 1) & 1) ^ 1));
                     const uint32_t pf = bar_pfull0 + 8 * w;
                     mbar_arrive_expect_tx(pf, (uint32_t)SP.patch_bytes);
                     tma_load_4d(smem_u32(patch0 + (size_t)w * SP.patch_stride), &map_x, kb * SBK, -PAD, y0 - PAD, nf, pf);

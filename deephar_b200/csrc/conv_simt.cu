@@ -220,7 +220,86 @@ int dh_fill_conv_params(ConvParams* p, const dh_view* x, const dh_conv_desc* d, 
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Direct convolution for a tiny reduction (the 3x3x3 first conv of the stem, K = 27,
+// models/reception.py:61-66).  An implicit-GEMM tile would waste half its K and N; here 4 threads
+// share one output pixel (8 output channels each): the K inputs of the pixel sit in registers, the
+// [K][Cout] weights and the BN affine in shared memory (broadcast float4 reads), and the 4 threads of
+// a pixel write 128 contiguous bytes -> a warp stores 1 KB rows.  No prologue, no residuals.
+// ---------------------------------------------------------------------------------------------
+constexpr int SK_MAX = 32;        // max K
+constexpr int SK_NT = 256;        // threads per block = 64 pixels x 4 channel groups (Cout = 32) ...
+
+template <int CG, int KH, int KW, int CIN>   // CG = Cout / 8 channel groups per pixel (4 | 8); compile-time taps
+__global__ void __launch_bounds__(SK_NT) conv_smallk_kernel(const ConvParams p) {
+    __shared__ __align__(16) float w_s[SK_MAX * 8 * CG];
+    __shared__ __align__(16) float sc_s[8 * CG], sh_s[8 * CG];
+    const int K = p.K, Cout = 8 * CG;
+    for (int i = threadIdx.x; i < K * Cout; i += SK_NT) w_s[i] = __ldg(p.w + i);
+    for (int i = threadIdx.x; i < Cout; i += SK_NT) {
+        sc_s[i] = p.post_scale ? __ldg(p.post_scale + i) : 1.f;
+        sh_s[i] = p.post_shift ? __ldg(p.post_shift + i) : 0.f;
+    }
+    __syncthreads();
+    const int cg = threadIdx.x % CG;
+    constexpr int PPB = SK_NT / CG;                       // pixels per block iteration
+    for (int m = blockIdx.x * PPB + threadIdx.x / CG; m < p.M; m += gridDim.x * PPB) {
+        const int ox = m % p.Wo, t = m / p.Wo, oy = t % p.Ho, n = t / p.Ho;
+        const int iy0 = oy * p.sh - p.pt, ix0 = ox * p.sw - p.pl;
+        const float* xb = p.x + (size_t)n * p.H * p.W * p.ldx;
+        float in[KH * KW * CIN];
+#pragma unroll
+        for (int ky = 0; ky < KH; ++ky) {
+            const int iy = iy0 + ky;
+#pragma unroll
+            for (int kx = 0; kx < KW; ++kx) {
+                const int ix = ix0 + kx;
+                const bool ok = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+                const float* px = xb + ((size_t)iy * p.W + ix) * p.ldx;
+#pragma unroll
+                for (int ci = 0; ci < CIN; ++ci) in[(ky * KW + kx) * CIN + ci] = ok ? __ldg(px + ci) : 0.f;
+            }
+        }
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < KH * KW * CIN; ++kk) {
+            {
+                const float4 w0 = *reinterpret_cast<const float4*>(w_s + kk * Cout + cg * 8);
+                const float4 w1 = *reinterpret_cast<const float4*>(w_s + kk * Cout + cg * 8 + 4);
+                acc[0] = fmaf(in[kk], w0.x, acc[0]); acc[1] = fmaf(in[kk], w0.y, acc[1]);
+                acc[2] = fmaf(in[kk], w0.z, acc[2]); acc[3] = fmaf(in[kk], w0.w, acc[3]);
+                acc[4] = fmaf(in[kk], w1.x, acc[4]); acc[5] = fmaf(in[kk], w1.y, acc[5]);
+                acc[6] = fmaf(in[kk], w1.z, acc[6]); acc[7] = fmaf(in[kk], w1.w, acc[7]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            acc[j] = fmaf(acc[j], sc_s[cg * 8 + j], sh_s[cg * 8 + j]);
+            if (p.post_relu) acc[j] = fmaxf(acc[j], 0.f);
+        }
+        float* op = p.out + (size_t)m * p.ldo + cg * 8;
+        *reinterpret_cast<float4*>(op) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        *reinterpret_cast<float4*>(op + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+}
+
+static bool smallk_ok(const ConvParams& p) {
+    return p.kh == 3 && p.kw == 3 && p.Cin == 3 && p.K == 27 && (p.Cout == 32 || p.Cout == 64) && !p.pre_scale && !p.pre_relu && !p.res0 && !p.res1 &&
+           (p.ldo & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0;
+}
+
 void dh_launch_conv_simt(const ConvParams& p, cudaStream_t s) {
+    if (smallk_ok(p)) {
+        const int cgn = p.Cout / 8;
+        const int ppb = SK_NT / cgn;
+        int blocks = (p.M + ppb - 1) / ppb;
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        if (cgn == 4) conv_smallk_kernel<4, 3, 3, 3><<<blocks, SK_NT, 0, s>>>(p);
+        else conv_smallk_kernel<8, 3, 3, 3><<<blocks, SK_NT, 0, s>>>(p);
+        return;
+    }
     dim3 grid((p.M + BM - 1) / BM, (p.Cout + BN - 1) / BN);
     conv_simt_kernel<<<grid, NT, 0, s>>>(p);
 }
