@@ -176,6 +176,15 @@ def softargmax_microbench(torch, model, peaks):
             'frac': gbs / peaks['hbm_gbs'], 'us_per_launch': ms * 1000.0, 'peak_source': peaks['source']}
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE `ncu --set full` capture of the dominant kernel (committed
+# under profiles/), per frame; the capture is a 128-frame launch, the bench launch is micro_batch frames.
+NCU_TRAFFIC = {
+    'sepconv 32x32x576->32x32x576 k5x5': {
+        'bytes_per_frame': (855.118336e6 + 270.342912e6) / 128,
+        'source': 'profiles/r1_septma_final.ncu-rep (128-frame launch: 855.1 MB read + 270.3 MB written), scaled per frame'},
+}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -299,7 +308,9 @@ def main():
     tf = top['flops'] / (top['ms'] / top['launches'] / 1000.0) / 1e12 if top['flops'] else 0.0
     roofline = {
         'kernel': top['label'], 'bound': 'tensor', 'achieved': tf, 'peak': peaks['bf16_tflops_sustained'],
-        'unit': 'TFLOP/s', 'frac': tf / peaks['bf16_tflops_sustained'], 'traffic': None,
+        'unit': 'TFLOP/s', 'frac': tf / peaks['bf16_tflops_sustained'],
+        'traffic': NCU_TRAFFIC.get(top['label'], {}).get('bytes_per_frame', 0) * step_items * (1 if args.workload == 'reception2d' else FRAMES) or None,
+        'traffic_source': NCU_TRAFFIC.get(top['label'], {}).get('source'),
         'share_of_step': top['ms'] / total_ms, 'us_per_launch': 1000.0 * top['ms'] / top['launches'],
         'peak_source': peaks['source'] + ' bf16 dense (sustained); kernel math: ' + model.math_mode(),
         'whole_forward_tflops': conv_flops * n_frames / (ms_step / 1000.0) / 1e12,
