@@ -47,6 +47,7 @@ extern "C" int dh_ctx_create(dh_ctx** out, int device) {
     c->share_a = 1;
     c->sep_tma = 1;
     c->dbg = 0;
+    c->pw_smallk = 1;
     *out = c;
     return 0;
 }
@@ -68,6 +69,7 @@ extern "C" int dh_set_option(dh_ctx* ctx, const char* name, int value) {
     if (!strcmp(name, "share_a")) { ctx->share_a = value; return 0; }
     if (!strcmp(name, "sep_tma")) { ctx->sep_tma = value; return 0; }
     if (!strcmp(name, "dbg")) { ctx->dbg = value; return 0; }
+    if (!strcmp(name, "pw_smallk")) { ctx->pw_smallk = value; return 0; }
     dh_set_error("dh_set_option: unknown option %s", name);
     return -1;
 }

@@ -14,6 +14,7 @@ struct dh_ctx {
     int last_conv_path;   // 0 = CUDA-core kernels, 1 = tcgen05 kernel (test / bench introspection)
     int share_a;          // 1 = cluster pairs share the separable A tile (default), 0 = independent CTAs
     int sep_tma;          // 1 = TMA-staged separable kernel (conv_sep.cu) where it applies (default)
+    int pw_smallk;        // 1 = CUDA-core kernel for wide 1x1 convs with Cin <= 64 (conv_simt.cu) (default)
     int dbg;              // ablation bits for tools/ (0 in production; results are WRONG when set)
 };
 

@@ -12,6 +12,12 @@ extern "C" int dh_conv2d_f32(dh_ctx* ctx, const dh_view* x, const float* w_hwio,
     if (rc) return rc;
     p.w = w_hwio;
     cudaStream_t s = (cudaStream_t)stream;
+    if (ctx->pw_smallk && dh_pw_smallk_supported(p)) {
+        rc = dh_launch_pw_smallk(p, ctx->num_sms, ctx->dbg & 3, s);
+        if (rc) return rc;
+        ctx->last_conv_path = 3;
+        DH_LAUNCH_EPILOGUE(ctx, 1);
+    }
     if (packed && packed->hi && dh_tc_supported(p, packed, false)) {
         rc = dh_launch_conv_tc(ctx, p, packed, false, d->precision, s);
         if (rc) return rc;

@@ -290,6 +290,155 @@ static bool smallk_ok(const ConvParams& p) {
            (p.ldo & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Pointwise (1x1, stride 1) convolution with a SMALL reduction (Cin <= 64) and a wide output: the
+// fReMap layers (48 -> 576 heat-map re-injection, models/reception.py:156-164 + the block-end add of
+// :194-196).  Such a layer is all epilogue -- 48 MACs per output but three 302 MB streams (two
+// residuals in, one out per 128 frames) -- so it runs on CUDA cores in exact fp32 with every thread
+// taking part in the memory traffic: per 64-pixel tile the [Cin][Cout] weights, the BN vectors and the
+// (prologue-applied) input tile sit in shared memory; warp = 8 pixels, lane = 4 consecutive output
+// channels (x ceil(Cout/128) passes); the 16 residual float4 loads of a pass are issued BEFORE its
+// k-loop (64 KB in flight per SM), packed FFMA2 accumulate, 512-byte coalesced rows out.
+// ---------------------------------------------------------------------------------------------
+template <int PW_PX, int PW_NT, bool PRE1>   // pixels per warp, threads per CTA, prefetch the 2nd residual too
+__global__ void __launch_bounds__(PW_NT, 1) conv_pw_smallk_kernel(const ConvParams p) {
+    constexpr int PW_TILE = (PW_NT / 32) * PW_PX;
+    extern __shared__ __align__(16) float pw_smem[];
+    const int K = p.Cin, Cout = p.Cout, CQ = Cout >> 2, K4 = K >> 2;
+    float* w_s = pw_smem;                       // [K][Cout]
+    float* sc_s = w_s + K * Cout;               // [Cout]
+    float* sh_s = sc_s + Cout;                  // [Cout]
+    float* ps_s = sh_s + Cout;                  // [K] prologue scale
+    float* pb_s = ps_s + K;                     // [K] prologue shift
+    float* h_s = pb_s + K;                      // [PW_TILE][K]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < K * CQ; i += PW_NT)
+        reinterpret_cast<float4*>(w_s)[i] = __ldg(reinterpret_cast<const float4*>(p.w) + i);
+    for (int i = tid; i < Cout; i += PW_NT) {
+        sc_s[i] = p.post_scale ? __ldg(p.post_scale + i) : 1.f;
+        sh_s[i] = p.post_shift ? __ldg(p.post_shift + i) : 0.f;
+    }
+    for (int i = tid; i < K; i += PW_NT) {
+        ps_s[i] = p.pre_scale ? __ldg(p.pre_scale + i) : 1.f;
+        pb_s[i] = p.pre_shift ? __ldg(p.pre_shift + i) : 0.f;
+    }
+    const float lowb = p.pre_relu ? 0.f : -3.402823466e38f;
+    const int ntiles = (p.M + PW_TILE - 1) / PW_TILE;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int m0 = tile * PW_TILE;
+        __syncthreads();                         // previous tile's readers are done (and the tables are written)
+        for (int i = tid; i < PW_TILE * K4; i += PW_NT) {
+            const int row = i / K4, c4 = i - row * K4;
+            const int m = m0 + row;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m < p.M) {
+                v = __ldg(reinterpret_cast<const float4*>(p.x + (size_t)m * p.ldx + c4 * 4));
+                const float4 a = *reinterpret_cast<const float4*>(ps_s + c4 * 4);
+                const float4 b = *reinterpret_cast<const float4*>(pb_s + c4 * 4);
+                v.x = fmaxf(fmaf(v.x, a.x, b.x), lowb); v.y = fmaxf(fmaf(v.y, a.y, b.y), lowb);
+                v.z = fmaxf(fmaf(v.z, a.z, b.z), lowb); v.w = fmaxf(fmaf(v.w, a.w, b.w), lowb);
+            }
+            reinterpret_cast<float4*>(h_s)[i] = v;
+        }
+        __syncthreads();
+        const int mw = m0 + warp * PW_PX;        // this warp's first pixel
+        const float* hw = h_s + warp * PW_PX * K;
+        for (int cq = lane; cq < CQ; cq += 32) {
+            const int co = cq * 4;
+            float4 r0[PW_PX], r1[PW_PX];
+#pragma unroll
+            for (int q = 0; q < PW_PX; ++q) {
+                r0[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                r1[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (mw + q < p.M) {
+                    if (p.res0) r0[q] = __ldg(reinterpret_cast<const float4*>(p.res0 + (size_t)(mw + q) * p.ldr0 + co));
+                    if (PRE1 && p.res1) r1[q] = __ldg(reinterpret_cast<const float4*>(p.res1 + (size_t)(mw + q) * p.ldr1 + co));
+                }
+            }
+            float2 a01[PW_PX], a23[PW_PX];
+#pragma unroll
+            for (int q = 0; q < PW_PX; ++q) { a01[q] = make_float2(0.f, 0.f); a23[q] = make_float2(0.f, 0.f); }
+            for (int k = 0; k < K; k += 4) {
+                const float4 w0 = *reinterpret_cast<const float4*>(w_s + (k + 0) * Cout + co);
+                const float4 w1 = *reinterpret_cast<const float4*>(w_s + (k + 1) * Cout + co);
+                const float4 w2 = *reinterpret_cast<const float4*>(w_s + (k + 2) * Cout + co);
+                const float4 w3 = *reinterpret_cast<const float4*>(w_s + (k + 3) * Cout + co);
+#pragma unroll
+                for (int q = 0; q < PW_PX; ++q) {
+                    const float4 h = *reinterpret_cast<const float4*>(hw + q * K + k);     // broadcast
+                    a01[q] = __ffma2_rn(make_float2(h.x, h.x), make_float2(w0.x, w0.y), a01[q]);
+                    a23[q] = __ffma2_rn(make_float2(h.x, h.x), make_float2(w0.z, w0.w), a23[q]);
+                    a01[q] = __ffma2_rn(make_float2(h.y, h.y), make_float2(w1.x, w1.y), a01[q]);
+                    a23[q] = __ffma2_rn(make_float2(h.y, h.y), make_float2(w1.z, w1.w), a23[q]);
+                    a01[q] = __ffma2_rn(make_float2(h.z, h.z), make_float2(w2.x, w2.y), a01[q]);
+                    a23[q] = __ffma2_rn(make_float2(h.z, h.z), make_float2(w2.z, w2.w), a23[q]);
+                    a01[q] = __ffma2_rn(make_float2(h.w, h.w), make_float2(w3.x, w3.y), a01[q]);
+                    a23[q] = __ffma2_rn(make_float2(h.w, h.w), make_float2(w3.z, w3.w), a23[q]);
+                }
+            }
+            const float4 sc = *reinterpret_cast<const float4*>(sc_s + co);
+            const float4 sh = *reinterpret_cast<const float4*>(sh_s + co);
+            if (!PRE1 && p.res1) {
+#pragma unroll
+                for (int q = 0; q < PW_PX; ++q)
+                    if (mw + q < p.M) r1[q] = __ldg(reinterpret_cast<const float4*>(p.res1 + (size_t)(mw + q) * p.ldr1 + co));
+            }
+#pragma unroll
+            for (int q = 0; q < PW_PX; ++q) {
+                if (mw + q < p.M) {
+                    float4 t;
+                    t.x = fmaf(a01[q].x, sc.x, sh.x); t.y = fmaf(a01[q].y, sc.y, sh.y);
+                    t.z = fmaf(a23[q].x, sc.z, sh.z); t.w = fmaf(a23[q].y, sc.w, sh.w);
+                    if (p.post_relu) {
+                        t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f);
+                    }
+                    t.x += r0[q].x + r1[q].x; t.y += r0[q].y + r1[q].y;
+                    t.z += r0[q].z + r1[q].z; t.w += r0[q].w + r1[q].w;
+                    *reinterpret_cast<float4*>(p.out + (size_t)(mw + q) * p.ldo + co) = t;
+                }
+            }
+        }
+    }
+}
+
+static size_t pw_smallk_smem(const ConvParams& p, int tile) {
+    return sizeof(float) * ((size_t)p.Cin * p.Cout + 2 * (size_t)p.Cout + 2 * (size_t)p.Cin + (size_t)tile * p.Cin);
+}
+
+bool dh_pw_smallk_supported(const ConvParams& p) {
+    auto a16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    if (!(p.kh == 1 && p.kw == 1 && p.sh == 1 && p.sw == 1)) return false;
+    if (p.Cin > 64 || (p.Cin & 3) || (p.Cout & 3) || p.Cout < 128) return false;       // wide outputs only
+    if ((p.ldx & 3) || (p.ldo & 3) || !a16(p.x) || !a16(p.out) || !a16(p.w)) return false;
+    if (p.res0 && ((p.ldr0 & 3) || !a16(p.res0))) return false;
+    if (p.res1 && ((p.ldr1 & 3) || !a16(p.res1))) return false;
+    return pw_smallk_smem(p, 96) <= 200 * 1024;
+}
+
+template <int PX, int NT, bool PRE1>
+static int pw_launch(const ConvParams& p, int num_sms, cudaStream_t s) {
+    constexpr int tile = (NT / 32) * PX;
+    const size_t smem = pw_smallk_smem(p, tile);
+    cudaError_t e = cudaFuncSetAttribute(conv_pw_smallk_kernel<PX, NT, PRE1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+        dh_set_error("dh_launch_pw_smallk: %s", cudaGetErrorString(e));
+        return (int)e;
+    }
+    int blocks = (p.M + tile - 1) / tile;
+    if (blocks > num_sms) blocks = num_sms;
+    conv_pw_smallk_kernel<PX, NT, PRE1><<<blocks, NT, smem, s>>>(p);
+    return 0;
+}
+
+int dh_launch_pw_smallk(const ConvParams& p, int num_sms, int variant, cudaStream_t s) {
+    switch (variant) {
+        case 1: return pw_launch<8, 384, false>(p, num_sms, s);
+        case 2: return pw_launch<4, 512, true>(p, num_sms, s);
+        case 3: return pw_launch<4, 768, true>(p, num_sms, s);
+        default: return pw_launch<8, 256, true>(p, num_sms, s);
+    }
+}
+
 void dh_launch_conv_simt(const ConvParams& p, cudaStream_t s) {
     if (smallk_ok(p)) {
         const int cgn = p.Cout / 8;

@@ -86,6 +86,44 @@ def test_conv2d_channel_views(dev):
     assert np.all(got[..., :5] == 7.0) and np.all(got[..., 17:] == 7.0)
 
 
+PW_CASES = [
+    # N, H, W, Cin, Cout, n_res, prologue -- wide 1x1 convs with a small reduction (conv_pw_smallk_kernel)
+    (2, 32, 32, 48, 576, 2, True),       # fReMap + block-end add (reception.py:156-164, :194-196)
+    (1, 7, 5, 12, 272, 0, False),        # M tail (35 pixels), Cout not a multiple of 128
+    (3, 9, 9, 64, 128, 1, True),         # largest Cin, one residual
+    (1, 16, 16, 4, 576, 2, False),       # smallest Cin
+]
+
+
+@pytest.mark.parametrize('case', PW_CASES)
+def test_conv2d_pointwise_smallk(dev, case):
+    n, h, w, cin, cout, nres, prologue = case
+    rng = np.random.default_rng(zlib.crc32(repr(case).encode()))
+    x = rng.standard_normal((n, h, w, cin))
+    wt = rng.standard_normal((1, 1, cin, cout)) / np.sqrt(cin)
+    post = (rng.uniform(0.5, 1.5, cout), rng.standard_normal(cout) * 0.3)
+    pre = None
+    xin = x
+    if prologue:
+        pre = (rng.uniform(0.5, 1.5, cin), rng.standard_normal(cin) * 0.3)
+        xin = np.maximum(x * pre[0] + pre[1], 0)
+    ref = ops_np.conv2d(xin, wt) * post[0] + post[1]
+    # residuals are channel slices of wider buffers (ld != C), output is a slice of a concat buffer
+    rbig = [rng.standard_normal((n, h, w, cout + 8)) for _ in range(nres)]
+    for r in rbig:
+        ref = ref + r[..., 4:4 + cout]
+    res = [dev.view(dev.put(r), 4, 4 + cout) for r in rbig]
+    cat = dev.empty(n, h, w, cout + 12)
+    cat.fill_(3.0)
+    d = conv_desc(dev, (1, 1), pre_relu=prologue, pre=pre, post=post, res=res)
+    xv, ov = dev.view(dev.put(x)), dev.view(cat, 8, 8 + cout)
+    dev.call('dh_conv2d_f32', C.byref(xv), dev.put(wt).data_ptr(), NULLP, C.byref(d), C.byref(ov))
+    assert dev.lib.dh_last_conv_path(dev.ctx.handle) == 3, 'pointwise small-K kernel was not taken'
+    got = cat.cpu().numpy()
+    _close(got[..., 8:8 + cout], ref)
+    assert np.all(got[..., :8] == 3.0) and np.all(got[..., 8 + cout:] == 3.0)
+
+
 SEP_CASES = [
     (2, 16, 16, 32, 48, (5, 5), (1, 1)),
     (1, 8, 8, 24, 24, (3, 3), (1, 1)),

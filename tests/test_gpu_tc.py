@@ -76,7 +76,13 @@ def test_conv_tc(dev, case, precision):
     d = conv_desc(dev, size, strides, 'same', pre_relu=fused, pre=pre, post=post, res=res, precision=precision)
     pk = _packed(dev, wt.reshape(-1, cout))
     xv, ov = dev.view(dev.put(x)), dev.view(out)
-    dev.call('dh_conv2d_f32', C.byref(xv), dev.put(wt).data_ptr(), C.byref(pk), C.byref(d), C.byref(ov))
+    # the wide / small-Cin 1x1 shapes would be served by the CUDA-core pointwise kernel (test_gpu_ops.py):
+    # switch it off so that this test keeps exercising the tensor-core kernel on them
+    _ffi.check(dev.lib.dh_set_option(dev.ctx.handle, b'pw_smallk', 0))
+    try:
+        dev.call('dh_conv2d_f32', C.byref(xv), dev.put(wt).data_ptr(), C.byref(pk), C.byref(d), C.byref(ov))
+    finally:
+        _ffi.check(dev.lib.dh_set_option(dev.ctx.handle, b'pw_smallk', 1))
     assert dev.lib.dh_last_conv_path(dev.ctx.handle) == 1, 'tensor-core path was not taken'
     e = _err(out.cpu().numpy(), ref)
     assert e <= (TOL3 if precision == 3 else TOL1), e
