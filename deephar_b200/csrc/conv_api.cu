@@ -13,7 +13,7 @@ extern "C" int dh_conv2d_f32(dh_ctx* ctx, const dh_view* x, const float* w_hwio,
     p.w = w_hwio;
     cudaStream_t s = (cudaStream_t)stream;
     if (ctx->pw_smallk && dh_pw_smallk_supported(p)) {
-        rc = dh_launch_pw_smallk(p, ctx->num_sms, ctx->dbg & 3, s);
+        rc = dh_launch_pw_smallk(p, ctx->num_sms, s);
         if (rc) return rc;
         ctx->last_conv_path = 3;
         DH_LAUNCH_EPILOGUE(ctx, 1);

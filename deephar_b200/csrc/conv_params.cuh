@@ -22,7 +22,7 @@ int dh_fill_conv_params(ConvParams* p, const dh_view* x, const dh_conv_desc* d, 
 void dh_launch_conv_simt(const ConvParams& p, cudaStream_t s);
 // wide pointwise conv with a small reduction (conv_simt.cu), exact fp32
 bool dh_pw_smallk_supported(const ConvParams& p);
-int dh_launch_pw_smallk(const ConvParams& p, int num_sms, int variant, cudaStream_t s);
+int dh_launch_pw_smallk(const ConvParams& p, int num_sms, cudaStream_t s);
 void dh_launch_depthwise_simt(const ConvParams& p, float* tmp, int num_sms, cudaStream_t s);
 
 // TMA-staged fused separable kernel (conv_sep.cu)

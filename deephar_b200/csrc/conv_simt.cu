@@ -296,11 +296,11 @@ static bool smallk_ok(const ConvParams& p) {
 // :194-196).  Such a layer is all epilogue -- 48 MACs per output but three 302 MB streams (two
 // residuals in, one out per 128 frames) -- so it runs on CUDA cores in exact fp32 with every thread
 // taking part in the memory traffic: per 64-pixel tile the [Cin][Cout] weights, the BN vectors and the
-// (prologue-applied) input tile sit in shared memory; warp = 8 pixels, lane = 4 consecutive output
-// channels (x ceil(Cout/128) passes); the 16 residual float4 loads of a pass are issued BEFORE its
+// (prologue-applied) input tile sit in shared memory; warp = PW_PX pixels, lane = 4 consecutive output
+// channels (x ceil(Cout/128) passes); the residual float4 loads of a pass are issued BEFORE its
 // k-loop (64 KB in flight per SM), packed FFMA2 accumulate, 512-byte coalesced rows out.
 // ---------------------------------------------------------------------------------------------
-template <int PW_PX, int PW_NT, bool PRE1>   // pixels per warp, threads per CTA, prefetch the 2nd residual too
+template <int PW_PX, int PW_NT, bool PRE1>   // pixels per warp, threads per CTA, prefetch the 2nd residual before the k-loop
 __global__ void __launch_bounds__(PW_NT, 1) conv_pw_smallk_kernel(const ConvParams p) {
     constexpr int PW_TILE = (PW_NT / 32) * PW_PX;
     extern __shared__ __align__(16) float pw_smem[];
@@ -412,7 +412,7 @@ bool dh_pw_smallk_supported(const ConvParams& p) {
     if ((p.ldx & 3) || (p.ldo & 3) || !a16(p.x) || !a16(p.out) || !a16(p.w)) return false;
     if (p.res0 && ((p.ldr0 & 3) || !a16(p.res0))) return false;
     if (p.res1 && ((p.ldr1 & 3) || !a16(p.res1))) return false;
-    return pw_smallk_smem(p, 96) <= 200 * 1024;
+    return pw_smallk_smem(p, 64) <= 200 * 1024;
 }
 
 template <int PX, int NT, bool PRE1>
@@ -430,13 +430,11 @@ static int pw_launch(const ConvParams& p, int num_sms, cudaStream_t s) {
     return 0;
 }
 
-int dh_launch_pw_smallk(const ConvParams& p, int num_sms, int variant, cudaStream_t s) {
-    switch (variant) {
-        case 1: return pw_launch<8, 384, false>(p, num_sms, s);
-        case 2: return pw_launch<4, 512, true>(p, num_sms, s);
-        case 3: return pw_launch<4, 768, true>(p, num_sms, s);
-        default: return pw_launch<8, 256, true>(p, num_sms, s);
-    }
+// Measured on the fReMap shape (128 frames, 48 -> 576, two residuals): 4 px x 512 threads 280 us,
+// 8 px x 256 threads 298 us, 8 px x 384 threads 300 us, 4 px x 768 threads 295 us -- the kernel is bound by the
+// fp32 FMA pipe (7.2 GFLOP at ~26 TFLOP/s), not by occupancy.
+int dh_launch_pw_smallk(const ConvParams& p, int num_sms, cudaStream_t s) {
+    return pw_launch<4, 512, true>(p, num_sms, s);
 }
 
 void dh_launch_conv_simt(const ConvParams& p, cudaStream_t s) {

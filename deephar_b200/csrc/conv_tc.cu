@@ -287,6 +287,37 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
         DenseRows rows;
         DenseRegs cur, nxt;
         int ti = 0;
+        if (MODE == 0 && !SHARE) {
+            // dense, one CTA per tile column: flat loop over (tile, K-block) items with the global loads
+            // running ONE ITEM AHEAD of the shared-memory stores -- also across tile boundaries, so that a
+            // short-K layer (stem 3x3 convs: 5 K-blocks, fReMap: 1) does not expose the load latency at
+            // the start of every tile.  The pixel decode (rows) belongs to the load side only.
+            int t_l = blockIdx.x, kb_l = 0;
+            if (t_l < P.n_mtiles) {
+                dense_rows_init(P.c, t_l * BM, tid, rows);
+                dense_load(P, rows, 0, tid, cur);
+                if (++kb_l == nkb) { kb_l = 0; t_l += gridDim.x; }
+            }
+            int s = 0;
+            uint32_t it = 0;
+            for (int t = blockIdx.x; t < P.n_mtiles; t += gridDim.x) {
+                for (int kb = 0; kb < nkb; ++kb) {
+                    const bool more = t_l < P.n_mtiles;
+                    if (more) {
+                        if (kb_l == 0) dense_rows_init(P.c, t_l * BM, tid, rows);
+                        dense_load(P, rows, kb_l, tid, nxt);
+                        if (++kb_l == nkb) { kb_l = 0; t_l += gridDim.x; }
+                    }
+                    mbar_wait(bar_empty0 + 8 * s, (it & 1) ^ 1);
+                    uint8_t* a_hi = smem + (size_t)s * stage_bytes;
+                    dense_store(P, cur, a_hi, a_hi + A_TILE_BYTES, tid, want_lo);
+                    if (more) cur = nxt;
+                    fence_proxy_async();
+                    mbar_arrive(bar_full0 + 8 * s);
+                    if (++s == P.stages) { s = 0; ++it; }
+                }
+            }
+        } else
         for (int t = blockIdx.x; t < P.n_mtiles; t += gridDim.x, ++ti) {
             const int m0 = t * BM;
             const int g0 = ti * nkb;
