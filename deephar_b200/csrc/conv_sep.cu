@@ -61,8 +61,8 @@ __device__ __forceinline__ uint32_t swz64(int row, int k) {
 }
 
 // use `it` (0,1,2,...) of stage s may start once use it-1 has been consumed
-__device__ __forceinline__ void wait_stage_free(uint32_t bar_empty0, int s, uint32_t it) {
-    if (it >= 1) mbar_wait(bar_empty0 + 16 * s + 8 * ((it - 1) & 1), ((it - 1) >> 1) & 1);
+__device__ __forceinline__ void wait_stage_free(uint32_t bar_empty0, int s, uint32_t it, uint32_t ns = 0) {
+    if (it >= 1) mbar_wait_relaxed(bar_empty0 + 16 * s + 8 * ((it - 1) & 1), ((it - 1) >> 1) & 1, ns);
 }
 
 template <int KS, int TW, bool SHARE>
@@ -169,7 +169,7 @@ sep_tma_kernel(const __grid_constant__ SepParams SP, const __grid_constant__ CUt
 #pragma unroll
                 for (int q = 0; q < 4; ++q) acc[o][q] = make_float2(0.f, 0.f);
 
-            if (!(SP.dbg & 2)) mbar_wait(pfull, (uint32_t)((j >> 1) & 1));
+            if (!(SP.dbg & 2)) mbar_wait_relaxed(pfull, (uint32_t)((j >> 1) & 1), (SP.dbg & 2048) ? 32u : 0u);
             if (!(SP.dbg & 1))
 #pragma unroll
             for (int r = 0; r < NR; ++r) {
@@ -194,7 +194,7 @@ sep_tma_kernel(const __grid_constant__ SepParams SP, const __grid_constant__ CUt
 
             const int s = g % NA;
             const uint32_t it = (uint32_t)(g / NA);
-            wait_stage_free(bar_empty0, s, it);
+            wait_stage_free(bar_empty0, s, it, (SP.dbg & 2048) ? 32u : 0u);
             uint8_t* a_hi = smem + (size_t)s * (2 * A_BYTES);
             uint8_t* a_lo = a_hi + A_BYTES;
 #pragma unroll
@@ -238,7 +238,7 @@ sep_tma_kernel(const __grid_constant__ SepParams SP, const __grid_constant__ CUt
                     const int ti = g / nkb, kb = g - ti * nkb;
                     const int sb = g & 1;
                     const uint32_t itb = (uint32_t)(g >> 1);
-                    if (itb >= 1) mbar_wait(bar_emptyb0 + 8 * sb, (itb - 1) & 1);
+                    if (itb >= 1) mbar_wait_relaxed(bar_emptyb0 + 8 * sb, (itb - 1) & 1, (SP.dbg & 2048) ? 64u : 0u);
                     const uint32_t full = bar_fullb0 + 8 * sb;
                     mbar_arrive_expect_tx(full, tx);
                     const uint32_t b_hi = smem_u32(b_ring + (size_t)sb * (2 * b_bytes));
@@ -280,7 +280,7 @@ sep_tma_kernel(const __grid_constant__ SepParams SP, const __grid_constant__ CUt
                         coords(j + 2, kb2, nf2, y2);
                         tma_prefetch_4d(&map_x, kb2 * SBK, -PAD, y2 - PAD, nf2);
                     }
-                    mbar_wait(bar_pempty0 + 8 * w, (uint32_t)(((j >> 1) & 1) ^ 1));
+                    mbar_wait_relaxed(bar_pempty0 + 8 * w, (uint32_t)(((j >> 1) & 1) ^ 1), (SP.dbg & 2048) ? 64u : 0u);
                     const uint32_t pf = bar_pfull0 + 8 * w;
                     mbar_arrive_expect_tx(pf, (uint32_t)SP.patch_bytes);
                     tma_load_4d(smem_u32(patch0 + (size_t)w * SP.patch_stride), &map_x, kb * SBK, -PAD, y0 - PAD, nf, pf);

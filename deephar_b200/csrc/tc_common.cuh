@@ -67,6 +67,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "memory");
     } while (!ok);
 }
+// same, for waits that are expected to be long (not on the MMA-issue critical path): sleep between polls so
+// that the spinning warp does not take issue slots from the warps doing the work
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, uint32_t ns) {
+    uint32_t ok;
+    for (;;) {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (ok) break;
+        if (ns) __nanosleep(ns);
+    }
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -265,7 +279,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& P, uint32_t tile_s
     for (int sub = 0; sub < nsub; ++sub) {
         const uint32_t u = u0 + (uint32_t)sub;
         const uint32_t slot = u % (uint32_t)P.nslots;
-        mbar_wait(bar_tfull0 + 8 * slot, (u / (uint32_t)P.nslots) & 1);
+        mbar_wait_relaxed(bar_tfull0 + 8 * slot, (u / (uint32_t)P.nslots) & 1, (P.dbg & 2048) ? 64u : 0u);
         tc_fence_after();
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + slot * (uint32_t)P.slot_stride;
         if (P.dbg & 64) {
