@@ -1,3 +1,2 @@
-for d in 0 2048; do echo "dbg=$d"; DH_DBG=$d timeout 120 python tools/prof_conv.py sep 128 32 32 576 576 5 3 10; done
-for d in 0 2048; do echo "dbg=$d"; DH_DBG=$d timeout 120 python tools/prof_conv.py sep 128 16 16 288 288 5 3 10; done
-for d in 0 2048; do echo "dbg=$d"; DH_DBG=$d timeout 120 python tools/prof_conv.py conv 128 32 32 576 576 1 3 10; done
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 900 -c 300 --csv --log-file gpurun_out/r1_launches_bench.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/launches.log 2>&1
+tail -n 1 gpurun_out/r1_launches_bench.csv | cut -c1-120
