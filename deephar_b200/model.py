@@ -39,6 +39,21 @@ class Model(object):
         self.plan = compile_graph(graph)
         self.calib_key = calib_key
         self.weight_specs = list(graph.weight_specs)
+        # Weights of layers the builders create but whose outputs never reach a model output (e.g. the
+        # re-injection convs after the LAST prediction block, spnet.py:249-262).  keras.Model drops such
+        # layers, so the reference's checkpoints do not contain them: they are optional when loading.
+        live = set()
+        stack = [t.node for t in graph.outputs]
+        seen = set()
+        while stack:
+            nd = stack.pop()
+            if nd is None or nd.id in seen:
+                continue
+            seen.add(nd.id)
+            if 'name' in nd.attrs:
+                live.add(nd.attrs['name'])
+            stack.extend(t.node for t in nd.inputs)
+        self.optional_weights = [n for n, _ in self.weight_specs if n.rsplit('/', 1)[0] not in live]
         self._host_weights = None
         self._dev = None            # device-side weight arena (torch tensor) + pointer table
         self._ptr = {}
@@ -90,8 +105,12 @@ class Model(object):
     def set_weights(self, table):
         """table: {name: array} in the Keras layouts listed by `weight_specs`."""
         host = {}
+        optional = set(self.optional_weights)
         for name, shape in self.weight_specs:
             if name not in table:
+                if name in optional:                    # dead layer: absent from reference checkpoints
+                    host[name] = np.zeros(shape, dtype=np.float32)
+                    continue
                 raise KeyError('missing weight %s %s' % (name, shape))
             a = np.asarray(table[name], dtype=np.float32)
             if tuple(a.shape) != tuple(shape):

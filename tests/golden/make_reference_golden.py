@@ -1,0 +1,149 @@
+"""Generate golden vectors by EXECUTING THE REFERENCE'S OWN MODEL BUILDERS (runs only where
+/root/reference exists; the fixtures it writes are what the tests read).
+
+    python tests/golden/make_reference_golden.py            # writes tests/golden/ref_*.npz
+
+keras / tensorflow are not installable here, so the reference code (deephar/models/reception.py, spnet.py,
+action.py, blocks.py, common.py, layers.py, activations.py -- imported unmodified from /root/reference) runs on
+tests/golden/keras_shim: an eager float64 stand-in for the Keras 2.1.4 functional API (README there).  For
+every case the script
+  1. builds the reference model and lists its weights as Keras would save them
+     ("<sub-model>/<layer>/<weight>", auto-names from Keras's per-class counters), separating the constants
+     the reference code itself assigns with set_weights (soft-argmax grids, aggregation matrix);
+  2. builds the product model (deephar_b200) for the same arguments, checks that its weight_specs minus
+     `optional_weights` are exactly the reference's trainable weights (names AND shapes), fills the reference
+     model with the product's synthetic weights BY NAME;
+  3. runs the reference graph on seeded inputs and stores inputs' seed, outputs and the weight list.
+tests/test_reference_golden.py then checks the oracle (both op sets) and, on the GPU, the product against these
+files.  What is and is not pinned by this: tests/golden/keras_shim/README.md.
+"""
+import os
+import sys
+import warnings
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REFERENCE = os.environ.get('DEEPHAR_REFERENCE', '/root/reference')
+sys.path.insert(0, os.path.join(HERE, 'keras_shim'))
+sys.path.insert(1, REFERENCE)
+sys.path.insert(2, ROOT)
+sys.path.insert(3, HERE)
+warnings.filterwarnings('ignore')
+
+import numpy as np  # noqa: E402
+
+np.seterr(all='ignore')
+
+import keras  # noqa: E402,F401  (the shim)
+from keras.engine import Model as KModel, reset_uids  # noqa: E402
+from keras.layers import TimeDistributed  # noqa: E402
+
+assert keras.__version__.endswith('shim')
+import deephar  # noqa: E402,F401  (the reference, unmodified)
+from deephar.config import ModelConfig as RefModelConfig  # noqa: E402
+from deephar.models import action as ref_action  # noqa: E402
+from deephar.models import reception as ref_reception  # noqa: E402
+from deephar.models import spnet as ref_spnet  # noqa: E402
+from deephar.utils.pose import pa16j2d as ref_pa16j2d, pa17j3d as ref_pa17j3d  # noqa: E402
+
+from deephar_b200 import action, reception, spnet  # noqa: E402
+from deephar_b200.config import ModelConfig, pa16j2d, pa17j3d  # noqa: E402
+from oracle import synth  # noqa: E402
+
+
+def fresh_process_state():
+    """Every reference script builds ONE model per process.  Emulate that between cases: reset Keras's
+    auto-name counters and the module-level counters the reference keeps in globals()
+    (spnet.py:210 act_cnt, layers.py:167 global_sam_cnt, :412 max_min_pool_cnt, :429 global_max_min_pool_cnt)."""
+    import deephar.layers as ref_layers
+    reset_uids()
+    ref_spnet.__dict__.pop('act_cnt', None)
+    for name in ('global_sam_cnt', 'max_min_pool_cnt', 'global_max_min_pool_cnt'):
+        ref_layers.__dict__.pop(name, None)
+
+
+def collect(model, prefix='', trainable=True, strip=()):
+    """Weights as keras.Model.save_weights groups them: nested models contribute '<model>/<layer>/<weight>'.
+    Returns [(name, weight, frozen)]: frozen = a constant the reference code assigned with set_weights on a layer
+    (or inside a model) it then marked non-trainable (soft-argmax grids, aggregation matrix) -- never in a
+    checkpoint's learned state.  `strip`: wrapper prefixes to drop (the merge model wraps the pose network's
+    sub-models in TimeDistributed layers named 'td_<name>', action.py:117-153)."""
+    out = []
+    for l in model.layers:
+        inner = l.layer if isinstance(l, TimeDistributed) else l
+        eff = trainable and getattr(l, 'trainable', True) and getattr(inner, 'trainable', True)
+        if isinstance(inner, KModel):
+            name = l.name
+            for pre in strip:
+                if name.startswith(pre):
+                    name = name[len(pre):]
+            sub = '' if name.startswith('Model') else name + '/'          # anonymous 'Model<N>' wrapper: transparent
+            out += collect(inner, prefix + sub, eff and getattr(inner, 'trainable', True), strip)
+        else:
+            for w in l.weights:
+                out.append((prefix + l.name + '/' + w['name'], w, w['fixed'] and not eff))
+    return out
+
+
+def pin(case, ref_model, prod_model, seed, x, strip=()):
+    ws = collect(ref_model, strip=strip)
+    names = [n for n, _, _ in ws]
+    assert len(set(names)) == len(names), 'duplicate weight names in the reference model'
+    trainable = {n: w for n, w, frozen in ws if not frozen}
+    specs = dict(prod_model.weight_specs)
+    live = {n: s for n, s in specs.items() if n not in set(prod_model.optional_weights)}
+    assert set(live) == set(trainable), (sorted(set(live) - set(trainable))[:5], sorted(set(trainable) - set(live))[:5])
+    for n, w in trainable.items():
+        assert tuple(w['value'].shape) == tuple(specs[n]), (n, w['value'].shape, specs[n])
+    prod_model.init_synthetic_weights(seed)
+    table = prod_model.get_weights()
+    for n, w in trainable.items():
+        w['value'] = np.asarray(table[n], dtype=np.float64)
+    outs = ref_model.predict(np.asarray(x, dtype=np.float64))
+    if not isinstance(outs, (list, tuple)):
+        outs = [outs]
+    path = os.path.join(HERE, 'ref_%s.npz' % case)
+    blob = {'out%d' % i: np.asarray(o, dtype=np.float64) for i, o in enumerate(outs)}
+    blob['weight_names'] = np.array(sorted(trainable))
+    blob['weight_shapes'] = np.array([repr(tuple(trainable[n]['value'].shape)) for n in sorted(trainable)])
+    blob['fixed_names'] = np.array(sorted(n for n, w, frozen in ws if frozen))
+    blob['optional_in_product'] = np.array(sorted(prod_model.optional_weights))
+    blob['seed'] = np.array(seed)
+    blob['x'] = np.asarray(x, dtype=np.float32)
+    np.savez_compressed(path, **blob)
+    print('%-28s %3d trainable + %2d fixed weights, %d outputs -> %s (%.0f KB)' % (
+        case, len(trainable), len(ws) - len(trainable), len(outs), os.path.basename(path), os.path.getsize(path) / 1024.0))
+
+
+def main():
+    from ref_cases import MERGE_CASE, RECEPTION_CASES, SPNET_CASES
+    # ---- ReceptionNet (CVPR'18) ----
+    for case, (shape, kw, seed, xs) in RECEPTION_CASES.items():
+        fresh_process_state()
+        ref = ref_reception.build(shape, **kw)
+        prod = reception.build(shape, **kw)
+        pin(case, ref, prod, seed, synth.synth_frames(2, shape[0], shape[1], seed=xs))
+
+    # ---- SPNet (TPAMI'20) ----
+    rng = np.random.default_rng(11)
+    layouts = {'pa16j2d': (ref_pa16j2d, pa16j2d), 'pa17j3d': (ref_pa17j3d, pa17j3d)}
+    for case, (shape, layout, kw, seed, batch) in SPNET_CASES.items():
+        fresh_process_state()
+        ref = ref_spnet.build(RefModelConfig(shape, layouts[layout][0], **kw))
+        prod = spnet.build(ModelConfig(shape, layouts[layout][1], **kw))
+        pin(case, ref, prod, seed, rng.uniform(-1.0, 1.0, (batch,) + shape))
+
+    # ---- CVPR'18 merge model (2-D pose + action) ----
+    fresh_process_state()
+    mc = MERGE_CASE
+    ref_pe = ref_reception.build(mc['input_shape'], **mc['reception'])
+    ref = ref_action.build_merge_model(ref_pe, mc['num_actions'], mc['input_shape'], mc['num_frames'], mc['num_joints'],
+                                       mc['num_blocks'], pose_dim=2)
+    prod_pe = reception.build(mc['input_shape'], **mc['reception'])
+    prod = action.build_merge_model(prod_pe, mc['num_actions'], mc['input_shape'], mc['num_frames'], mc['num_joints'],
+                                    mc['num_blocks'], pose_dim=2)
+    pin('merge_model', ref, prod, mc['seed'], rng.uniform(-1.0, 1.0, (1, mc['num_frames']) + mc['input_shape']), strip=('td_',))
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,25 @@
+"""Case table shared by make_reference_golden.py (which runs the REFERENCE builders on keras_shim) and
+tests/test_reference_golden.py (which checks the oracle and the product against the fixtures it wrote)."""
+
+RECEPTION_CASES = {
+    # case: (input shape, reception.build kwargs, weight seed, input seed)
+    'reception2d_ctx': ((64, 64, 3), dict(num_joints=16, dim=2, num_blocks=2, ksize=(5, 5), num_context_per_joint=2,
+                                          concat_pose_confidence=False), 1234, 1),
+    'reception2d_heatmaps': ((64, 64, 3), dict(num_joints=16, dim=2, num_blocks=2, ksize=(3, 3), export_heatmaps=True), 7, 22),
+    'reception3d': ((64, 64, 3), dict(num_joints=17, dim=3, num_blocks=2, ksize=(5, 5), concat_pose_confidence=False), 1234, 23),
+}
+
+SPNET_CASES = {
+    # case: (cfg input shape, pose layout name, ModelConfig kwargs, weight seed, batch)
+    'spnet_penn_like': ((2, 128, 128, 3), 'pa16j2d',
+                        dict(num_actions=[15], num_pyramids=2, action_pyramids=[1, 2], num_levels=4, pose_replica=True,
+                             num_pose_features=160, num_visual_features=160), 1234, 1),
+    'spnet_ntu_like': ((2, 128, 128, 3), 'pa17j3d',
+                       dict(num_actions=[60], num_pyramids=2, action_pyramids=[1, 2], num_levels=4, num_pose_features=192,
+                            num_visual_features=192), 1234, 1),
+    'spnet_pose_only': ((128, 128, 3), 'pa16j2d', dict(num_pyramids=2, action_pyramids=[], num_levels=4), 5, 2),
+}
+
+# CVPR'18 merge model (exp/pennaction/eval_penn_ar_pe_merge.py:42-62), small geometry
+MERGE_CASE = dict(input_shape=(64, 64, 3), num_frames=4, num_actions=15, num_joints=16, num_blocks=4, seed=3,
+                  reception=dict(num_joints=16, dim=2, num_blocks=4, num_context_per_joint=2, ksize=(5, 5)))
