@@ -240,26 +240,21 @@ __device__ __forceinline__ void epi_load_res(ResRows& r, const float* p, size_t 
 // (Pinning loop invariants in registers with an asm mov -- so that the compiler cannot rematerialise them
 // with LDC / S2R, which share scoreboards with the in-flight residual loads -- was tried and measured
 // slower: the extra live registers cost more than the early scoreboard waits.)
-__device__ __forceinline__ int pin(int x) { return x; }
-__device__ __forceinline__ uint32_t pin(uint32_t x) { return x; }
-
 template <bool FULL, bool RES1>
 __device__ __forceinline__ void epilogue_tile(const TcParams& P, uint32_t tile_s, uint32_t tmem_base,
                                               uint32_t bar_tfull0, uint32_t bar_tempty0, int n0, int q, int lane,
                                               int mbase, uint32_t u0, bool vec_ok, uint32_t aff_s) {
     const ConvParams& c = P.c;
-    const int nw = pin(P.nw), nsub = pin(P.nsub);
-    const int nch = pin((nw + 31) >> 5);                  // 32-column chunks per sub-tile (last may be 16 wide)
-    const int wlast = pin(nw - (nch - 1) * 32);           // width of the last chunk: 32 or 16
-    lane = pin(lane);
-    n0 = pin(n0);
+    const int nw = P.nw, nsub = P.nsub;
+    const int nch = (nw + 31) >> 5;                  // 32-column chunks per sub-tile (last may be 16 wide)
+    const int wlast = nw - (nch - 1) * 32;           // width of the last chunk: 32 or 16
     const int b4 = lane & 7, r0 = lane >> 3;
     const int m0 = mbase + r0;
-    const int M = pin(c.M), Cout = pin(c.Cout);
+    const int M = c.M, Cout = c.Cout;
     const size_t ldo4 = (size_t)c.ldo * 4, ldr04 = (size_t)c.ldr0 * 4, ldr14 = (size_t)c.ldr1 * 4;
-    const uint32_t st_a = pin(tile_s + (uint32_t)lane * 128u);                  // transpose: write row = lane
-    const uint32_t ld_a0 = pin(tile_s + (uint32_t)(r0 * 128 + ((b4 ^ r0) << 4)));   // read rows r0, r0 + 8, ...
-    const uint32_t ld_a1 = pin(tile_s + (uint32_t)((r0 + 4) * 128 + ((b4 ^ (r0 + 4)) << 4)));   // rows r0 + 4, ...
+    const uint32_t st_a = tile_s + (uint32_t)lane * 128u;                  // transpose: write row = lane
+    const uint32_t ld_a0 = tile_s + (uint32_t)(r0 * 128 + ((b4 ^ r0) << 4));   // read rows r0, r0 + 8, ...
+    const uint32_t ld_a1 = tile_s + (uint32_t)((r0 + 4) * 128 + ((b4 ^ (r0 + 4)) << 4));   // rows r0 + 4, ...
     float* out_row = c.out + (size_t)m0 * c.ldo;
     const float* res0_row = c.res0 ? c.res0 + (size_t)m0 * c.ldr0 : nullptr;
     const float* res1_row = c.res1 ? c.res1 + (size_t)m0 * c.ldr1 : nullptr;

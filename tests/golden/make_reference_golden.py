@@ -118,11 +118,13 @@ def pin(case, ref_model, prod_model, seed, x, strip=()):
 def main():
     from ref_cases import MERGE_CASE, RECEPTION_CASES, SPNET_CASES
     # ---- ReceptionNet (CVPR'18) ----
-    for case, (shape, kw, seed, xs) in RECEPTION_CASES.items():
+    for case, spec in RECEPTION_CASES.items():
+        shape, kw, seed, xs = spec[:4]
+        frames = spec[4] if len(spec) > 4 else 2
         fresh_process_state()
         ref = ref_reception.build(shape, **kw)
         prod = reception.build(shape, **kw)
-        pin(case, ref, prod, seed, synth.synth_frames(2, shape[0], shape[1], seed=xs))
+        pin(case, ref, prod, seed, synth.synth_frames(frames, shape[0], shape[1], seed=xs))
 
     # ---- SPNet (TPAMI'20) ----
     rng = np.random.default_rng(11)

@@ -2,11 +2,14 @@
 tests/test_reference_golden.py (which checks the oracle and the product against the fixtures it wrote)."""
 
 RECEPTION_CASES = {
-    # case: (input shape, reception.build kwargs, weight seed, input seed)
+    # case: (input shape, reception.build kwargs, weight seed, input seed[, frames])
     'reception2d_ctx': ((64, 64, 3), dict(num_joints=16, dim=2, num_blocks=2, ksize=(5, 5), num_context_per_joint=2,
                                           concat_pose_confidence=False), 1234, 1),
     'reception2d_heatmaps': ((64, 64, 3), dict(num_joints=16, dim=2, num_blocks=2, ksize=(3, 3), export_heatmaps=True), 7, 22),
     'reception3d': ((64, 64, 3), dict(num_joints=17, dim=3, num_blocks=2, ksize=(5, 5), concat_pose_confidence=False), 1234, 23),
+    # the BASELINE.json configs[1] model at full size (eval_penn_ar_pe_merge.py:51-53 / eval_mpii_singleperson.py:47), 1 frame
+    'reception2d_c1_fullsize': ((256, 256, 3), dict(num_joints=16, dim=2, num_blocks=8, ksize=(5, 5), num_context_per_joint=2,
+                                                    concat_pose_confidence=False), 1234, 31, 1),
 }
 
 SPNET_CASES = {

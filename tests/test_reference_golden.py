@@ -44,7 +44,7 @@ def _fixture(case):
 
 def _product(case):
     if case in RECEPTION_CASES:
-        shape, kw, seed, _ = RECEPTION_CASES[case]
+        shape, kw, seed = RECEPTION_CASES[case][:3]
         return reception.build(shape, **kw), seed
     if case in SPNET_CASES:
         shape, layout, kw, seed, _ = SPNET_CASES[case]
@@ -86,8 +86,9 @@ def test_oracle_matches_reference_graph(case):
     assert seed == int(z['seed'])
     table = m.init_synthetic_weights(seed).get_weights()      # host-side only: no device is touched
     x = z['x'].astype(np.float64)
-    big = case.startswith('spnet')
-    # numpy fp64 oracle on the small graphs, the torch-CPU fp32 op set on the 128x128 SPNets (CPU-suite time)
+    big = case.startswith('spnet') or case.endswith('fullsize')
+    # numpy fp64 oracle on the small graphs, the torch-CPU fp32 op set on the 128x128 SPNets and the full-size
+    # ReceptionNet (CPU-suite time)
     outs = _oracle(case, ops_torch if big else ops_np, table, x)
     assert len(outs) == len(ref_outs)
     # the merge model feeds the ill-conditioned context division (see below) into a second network: fp64
@@ -112,10 +113,12 @@ def test_product_matches_reference_graph(cuda, case):
     # that sum cancels are ill-conditioned in ANY precision -- bound them by the oracle's condition number and
     # exclude cond > 100 (must be < 2 % of joints), exactly as tests/test_gpu_reception.py does
     cond = None
-    if case == 'reception2d_ctx':
+    if case in RECEPTION_CASES and RECEPTION_CASES[case][1].get('num_context_per_joint') and \
+            not RECEPTION_CASES[case][1].get('concat_pose_confidence', True):
         dbg = {}
-        oracle_reception.forward(ops_np, m.get_weights(), z['x'].astype(np.float64), debug=dbg, **RECEPTION_CASES[case][1])
-        cond = dbg['ctx_cond']
+        oracle_reception.forward(ops_torch if case.endswith('fullsize') else ops_np, m.get_weights(),
+                                 z['x'].astype(np.float64), debug=dbg, **RECEPTION_CASES[case][1])
+        cond = [np.asarray(c, dtype=np.float64) for c in dbg['ctx_cond']]
     skipped = total = 0
     for i, (o, r) in enumerate(zip(outs, ref_outs)):
         assert o.shape == r.shape
