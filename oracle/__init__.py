@@ -11,7 +11,8 @@ PARITY -- what is pinned by the reference itself and what is not:
   (deephar/models/reception.py, spnet.py, action.py, blocks.py, common.py, layers.py, activations.py --
   unmodified, from /root/reference) and EXECUTES it on tests/golden/keras_shim, an eager float64 stand-in
   for the Keras 2.1.4 functional API.  The fixtures tests/golden/ref_*.npz (ReceptionNet 2-D ctx / heat-map
-  export / 3-D / full-size BASELINE configs[1] model, SPNet Penn-like / NTU-like / pose-only, CVPR'18 merge model) hold the reference models'
+  export / 3-D / full-size BASELINE configs[1] model, SPNet Penn-like / NTU-like / pose-only / full-resolution
+  configs[3] architecture, CVPR'18 merge model) hold the reference models'
   weight lists (Keras auto-names, shapes) and outputs; tests/test_reference_golden.py requires
   reception.py / spnet.py / action.py here to reproduce them to 1e-9 (fp64) and the product's weight_specs
   to be exactly the reference's learned weights.

@@ -21,6 +21,11 @@ SPNET_CASES = {
                        dict(num_actions=[60], num_pyramids=2, action_pyramids=[1, 2], num_levels=4, num_pose_features=192,
                             num_visual_features=192), 1234, 1),
     'spnet_pose_only': ((128, 128, 3), 'pa16j2d', dict(num_pyramids=2, action_pyramids=[], num_levels=4), 5, 2),
+    # the BASELINE.json configs[3] architecture (exp/pennaction/eval_penn_multitask.py:37-40) at full resolution; the clip
+    # is cut to 2 frames (the clip length only sets the temporal extent of the action head's input)
+    'spnet_penn_c4_t2': ((2, 256, 256, 3), 'pa16j2d',
+                         dict(num_actions=[15], num_pyramids=6, action_pyramids=[5, 6], num_levels=4, pose_replica=True,
+                              num_pose_features=160, num_visual_features=160), 1234, 1),
 }
 
 # CVPR'18 merge model (exp/pennaction/eval_penn_ar_pe_merge.py:42-62), small geometry
