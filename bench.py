@@ -134,8 +134,11 @@ def run_reference(args):
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1000.0 * dt / args.steps,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
         'data': 'synthetic',
-        'config': {'workload': 'reception2d_8blk_k5_j16 forward, 256x256x3, CPU port (keras/tensorflow not installed)',
-                   'global_batch_frames': per_step},
+        # same workload as the product arm; each step is a bounded sample of it (see cpu_baseline.sample)
+        'config': {'workload': 'reception2d_8blk_k5_j16 (BASELINE configs[1] model) x 32 clips x 16 frames',
+                   'global_batch_frames': CLIPS * FRAMES, 'sample_frames_per_step': per_step,
+                   'implementation': 'CPU port of the Keras graph (oracle/, torch-CPU fp32, all host threads); '
+                                     'keras 2.1.4 / tensorflow 1.6 are not installable in this image'},
         'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': fps, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
