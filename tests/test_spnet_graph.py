@@ -72,3 +72,25 @@ def test_pose_only_single_frame_model():
     m = spnet.build(cfg)
     assert m.output_shape == [(None, 16, 3)] * 6
     assert 'kron' not in [k.kind for k in m.plan.kops]
+
+
+def test_optional_weights_are_the_dead_layers_only():
+    """Layers the reference builds but keras.Model prunes (they feed no output) are absent from its checkpoints:
+    set_weights must accept a table without them and still insist on everything else (spnet.py:249-262)."""
+    import numpy as np
+    import pytest
+    from deephar_b200.weights import synthetic_weights
+    cfg = ModelConfig((2, 64, 64, 3), pa16j2d, num_actions=[15], num_pyramids=2, action_pyramids=[1, 2], num_levels=3,
+                      pose_replica=True, num_pose_features=32, num_visual_features=32)
+    m = spnet.build(cfg)
+    assert sorted(m.optional_weights) == ['act4_action_pred_conv3/kernel', 'up2_pb0_heatmaps_conv2/kernel',
+                                          'up2_pb0_heatmaps_fw_maps/kernel']
+    table = synthetic_weights(m.weight_specs, 1, {})
+    for n in m.optional_weights:
+        del table[n]
+    m.set_weights(table)                                   # checkpoint-like table: accepted
+    assert all(np.all(m.get_weights()[n] == 0) for n in m.optional_weights)
+    required = next(n for n, _ in m.weight_specs if n not in m.optional_weights)
+    del table[required]
+    with pytest.raises(KeyError):
+        m.set_weights(table)
