@@ -131,16 +131,36 @@ class Model(object):
         return self
 
     def load_weights(self, path, by_name=False):
-        """.npz written by save_weights (names = weight_specs).  Importing the released Keras
-        .h5 files is SURVEY.md 8(f) rank 1 (needs an HDF5 reader that is not in this image)."""
-        if str(path).endswith(('.h5', '.hdf5')):
-            raise NotImplementedError('Keras HDF5 import is not available (no h5py in the image); '
-                                      'convert to .npz with names from Model.weight_specs')
-        with np.load(path) as z:
-            self.set_weights({k: z[k] for k in z.files})
+        """keras.Model.load_weights: a Keras HDF5 weight file (`save_weights` / `save` output, read by
+        the pure-Python reader in hdf5.py / keras_h5.py -- the call every reference evaluator makes:
+        eval_mpii_singleperson.py:54, eval_h36m.py:53, eval_penn_multitask.py:76) or an .npz written by
+        `save_weights` here.  by_name=False requires every (non-optional) weight of the model to be in
+        the file; by_name=True loads the layers whose names match and keeps the rest."""
+        path = str(path)
+        if path.endswith(('.h5', '.hdf5', '.keras')):
+            from . import keras_h5
+            table, unused = keras_h5.load(path, self.weight_specs, self.optional_weights, by_name=by_name)
+            self.unused_file_weights = unused
+        else:
+            with np.load(path) as z:
+                table = {k: z[k] for k in z.files}
+            known = set(n for n, _ in self.weight_specs)
+            self.unused_file_weights = [k for k in table if k not in known]
+            table = {k: v for k, v in table.items() if k in known}
+        if by_name and self._host_weights is not None:
+            merged = dict(self._host_weights)
+            merged.update(table)
+            table = merged
+        self.set_weights(table)
 
     def save_weights(self, path):
-        np.savez(path, **self._host_weights)
+        """Keras-layout HDF5 for '*.h5' (loadable by keras.Model.load_weights of the reference), else .npz."""
+        path = str(path)
+        if path.endswith(('.h5', '.hdf5', '.keras')):
+            from . import keras_h5
+            keras_h5.save(path, self.weight_specs, self._host_weights)
+        else:
+            np.savez(path, **self._host_weights)
 
     # ---- engine --------------------------------------------------------------------
     def _torch(self):

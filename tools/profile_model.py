@@ -10,9 +10,11 @@ import bench  # noqa: E402
 
 wl = sys.argv[1] if len(sys.argv) > 1 else 'reception2d'
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 128
-if wl == 'reception2d':
+if wl in ('reception2d', 'reception3d'):
     from deephar_b200 import reception
-    m = reception.build((256, 256, 3), **bench.MODEL_KW).init_synthetic_weights(1234)
+    kw = bench.MODEL_KW if wl == 'reception2d' else dict(num_joints=17, dim=3, num_blocks=8, ksize=(5, 5),
+                                                          concat_pose_confidence=False)
+    m = reception.build((256, 256, 3), **kw).init_synthetic_weights(1234)
     x = torch.rand(n, 256, 256, 3, device='cuda') * 2 - 1
 else:
     from deephar_b200 import spnet
