@@ -48,6 +48,7 @@ SIGNATURES = {
     'dh_tc_cout_pad': (C.c_int, [C.c_int]),
     'dh_tc_k_pad': (C.c_int, [C.c_int]),
     'dh_last_conv_path': (C.c_int, [C.c_void_p]),
+    'dh_fallback_count': (C.c_int64, [C.c_void_p, C.c_int]),
     'dh_conv2d_f32': (C.c_int, [C.c_void_p, _VP, C.c_void_p, _PP, _DP, _VP, C.c_void_p]),
     'dh_sepconv2d_f32': (C.c_int, [C.c_void_p, _VP, C.c_void_p, C.c_void_p, _PP, _DP, _VP, C.c_void_p]),
     'dh_maxpool2d_f32': (C.c_int, [C.c_void_p, _VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _VP, C.c_void_p]),

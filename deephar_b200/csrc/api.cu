@@ -48,6 +48,8 @@ extern "C" int dh_ctx_create(dh_ctx** out, int device) {
     c->sep_tma = 1;
     c->dbg = 0;
     c->pw_smallk = 1;
+    c->dense_patch = 1;
+    c->fallbacks = 0;
     *out = c;
     return 0;
 }
@@ -70,11 +72,19 @@ extern "C" int dh_set_option(dh_ctx* ctx, const char* name, int value) {
     if (!strcmp(name, "sep_tma")) { ctx->sep_tma = value; return 0; }
     if (!strcmp(name, "dbg")) { ctx->dbg = value; return 0; }
     if (!strcmp(name, "pw_smallk")) { ctx->pw_smallk = value; return 0; }
+    if (!strcmp(name, "dense_patch")) { ctx->dense_patch = value; return 0; }
     dh_set_error("dh_set_option: unknown option %s", name);
     return -1;
 }
 
 extern "C" int dh_last_conv_path(dh_ctx* ctx) { return ctx ? ctx->last_conv_path : -1; }
+
+extern "C" int64_t dh_fallback_count(dh_ctx* ctx, int reset) {
+    if (!ctx) return -1;
+    int64_t v = ctx->fallbacks;
+    if (reset) ctx->fallbacks = 0;
+    return v;
+}
 
 extern "C" int dh_set_workspace(dh_ctx* ctx, void* ptr, int64_t bytes) {
     DH_CHECK_ARG(ctx != nullptr, "dh_set_workspace: ctx is NULL");

@@ -18,6 +18,12 @@ extern "C" int dh_conv2d_f32(dh_ctx* ctx, const dh_view* x, const float* w_hwio,
         ctx->last_conv_path = 3;
         DH_LAUNCH_EPILOGUE(ctx, 1);
     }
+    if (packed && packed->hi && dh_patch_supported(ctx, p, packed)) {
+        rc = dh_launch_patch(ctx, p, packed, d->precision, s);
+        if (rc) return rc;
+        ctx->last_conv_path = 4;
+        DH_LAUNCH_EPILOGUE(ctx, 1);
+    }
     if (packed && packed->hi && dh_tc_supported(p, packed, false)) {
         rc = dh_launch_conv_tc(ctx, p, packed, false, d->precision, s);
         if (rc) return rc;
@@ -25,6 +31,7 @@ extern "C" int dh_conv2d_f32(dh_ctx* ctx, const dh_view* x, const float* w_hwio,
         DH_LAUNCH_EPILOGUE(ctx, 1);
     }
     ctx->last_conv_path = 0;
+    ctx->fallbacks += 1;
     dh_launch_conv_simt(p, s);
     DH_LAUNCH_EPILOGUE(ctx, 1);
 }
@@ -54,6 +61,7 @@ extern "C" int dh_sepconv2d_f32(dh_ctx* ctx, const dh_view* x, const float* w_dw
         DH_LAUNCH_EPILOGUE(ctx, 1);
     }
     ctx->last_conv_path = 0;
+    ctx->fallbacks += 1;
     // Two-kernel CUDA-core path: depthwise (with the fused pre-ops) into the caller's
     // workspace, then the pointwise 1x1 as an implicit GEMM with the fused post-ops.
     int64_t need = (int64_t)p.M * p.Cin * (int64_t)sizeof(float);

@@ -29,6 +29,10 @@ void dh_launch_depthwise_simt(const ConvParams& p, float* tmp, int num_sms, cuda
 bool dh_sep_tma_supported(const dh_ctx* ctx, const ConvParams& p, const dh_packed_w* packed);
 int dh_launch_sep_tma(dh_ctx* ctx, const ConvParams& p, const dh_packed_w* packed, int precision, cudaStream_t s);
 
+// TMA-staged patch kernel for stride-1 Conv2D (conv_patch.cu)
+bool dh_patch_supported(const dh_ctx* ctx, const ConvParams& p, const dh_packed_w* packed);
+int dh_launch_patch(dh_ctx* ctx, const ConvParams& p, const dh_packed_w* packed, int precision, cudaStream_t s);
+
 // tensor-core path (conv_tc.cu). Returns true if it took the op.
 bool dh_tc_supported(const ConvParams& p, const dh_packed_w* packed, bool separable);
 int dh_launch_conv_tc(dh_ctx* ctx, const ConvParams& p, const dh_packed_w* packed, bool separable,

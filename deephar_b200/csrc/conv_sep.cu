@@ -23,7 +23,6 @@
 namespace tcs {
 using namespace tc;
 
-constexpr int SBK = 32;                    // channels (bf16 K elements) per K-block = one 64-byte swizzle row
 constexpr int A_BYTES = BM * 64;           // 8 KB per (hi | lo)
 constexpr int NWG = 128;                   // threads per producer warpgroup
 constexpr int WARP_PATCH = 14;
@@ -36,34 +35,6 @@ struct SepParams {
     int ry, fn;             // tile rows per frame, frames per tile
     int dbg;                // ablation bits (tools/ only): 1 no depthwise math, 2 no patch TMA, 8 no DSMEM push, 16 no weight TMA
 };
-
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
-                                            uint32_t bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
-        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
-        : "memory");
-}
-
-__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
-    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global [%0, {%1, %2, %3, %4}];"
-                 ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-
-// K-major, 64-byte swizzle UMMA descriptor: SBO = 512 B (8 rows x 64 B), layout SWIZZLE_64B = 4.
-__device__ __forceinline__ uint64_t make_desc64(uint32_t smem_addr) {
-    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) |
-           (4ull << 61);
-}
-// byte offset of element (row, k) inside a [rows][32 bf16] 64B-swizzled K-major tile (Swizzle<2,4,3>)
-__device__ __forceinline__ uint32_t swz64(int row, int k) {
-    return (uint32_t)(row * 64 + ((((k >> 3) ^ ((row >> 1) & 3)) << 4) | ((k & 7) << 1)));
-}
-
-// use `it` (0,1,2,...) of stage s may start once use it-1 has been consumed
-__device__ __forceinline__ void wait_stage_free(uint32_t bar_empty0, int s, uint32_t it, uint32_t ns = 0) {
-    if (it >= 1) mbar_wait_relaxed(bar_empty0 + 16 * s + 8 * ((it - 1) & 1), ((it - 1) >> 1) & 1, ns);
-}
 
 template <int KS, int TW, bool SHARE>
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -362,18 +333,6 @@ sep_tma_kernel(const __grid_constant__ SepParams SP, const __grid_constant__ CUt
         tc_fence_after();
         tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
     }
-}
-
-static bool make_map_b64(CUtensorMap* map, const void* base, int k_pad, int rows, int box_rows) {
-    EncodeTiledFn enc = get_encode();
-    if (!enc) return false;
-    cuuint64_t dims[2] = {(cuuint64_t)k_pad, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)k_pad * 2};
-    cuuint32_t box[2] = {(cuuint32_t)SBK, (cuuint32_t)box_rows};
-    cuuint32_t estr[2] = {1, 1};
-    return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // NHWC fp32 activations as a 4-D tensor (C, W, H, N); box = (32 ch, W + 2*PAD, rows + 2*PAD, frames)

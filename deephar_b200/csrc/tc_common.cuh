@@ -202,6 +202,37 @@ __device__ __forceinline__ uint32_t swz(int row, int k) {
 }
 
 
+// ---- pieces shared by the patch-staged kernels (conv_sep.cu, conv_patch.cu): 32-channel K-blocks, 64B swizzle ----
+constexpr int SBK = 32;                    // channels (bf16 K elements) per K-block = one 64-byte swizzle row
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
+                                            uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+        : "memory");
+}
+
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global [%0, {%1, %2, %3, %4}];"
+                 ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
+// K-major, 64-byte swizzle UMMA descriptor: SBO = 512 B (8 rows x 64 B), layout SWIZZLE_64B = 4.
+__device__ __forceinline__ uint64_t make_desc64(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) |
+           (4ull << 61);
+}
+// byte offset of element (row, k) inside a [rows][32 bf16] 64B-swizzled K-major tile (Swizzle<2,4,3>)
+__device__ __forceinline__ uint32_t swz64(int row, int k) {
+    return (uint32_t)(row * 64 + ((((k >> 3) ^ ((row >> 1) & 3)) << 4) | ((k & 7) << 1)));
+}
+
+// use `it` (0,1,2,...) of stage s may start once use it-1 has been consumed
+__device__ __forceinline__ void wait_stage_free(uint32_t bar_empty0, int s, uint32_t it, uint32_t ns = 0) {
+    if (it >= 1) mbar_wait_relaxed(bar_empty0 + 16 * s + 8 * ((it - 1) & 1), ((it - 1) >> 1) & 1, ns);
+}
+
+
 // TMEM accumulator slots.  A tile's accumulator is nsub sub-tiles of nw columns; sub-tile `sub` of this
 // CTA's tile number ti is "use" u = ti * nsub + sub and lives in slot u % nslots (slot_stride columns each),
 // guarded by tfull[slot] / tempty[slot].  With nslots > nsub the MMAs of tile ti+1 start in the spare
@@ -463,6 +494,19 @@ static inline bool make_map(CUtensorMap* map, const void* base, int k_pad, int r
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }
+
+static inline bool make_map_b64(CUtensorMap* map, const void* base, int k_pad, int rows, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)k_pad, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)k_pad * 2};
+    cuuint32_t box[2] = {(cuuint32_t)SBK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 
 // TMEM plan: as many nw-column slots as fit 512 columns (at most two tiles' worth).
 static inline void plan_tmem(TcParams& P) {

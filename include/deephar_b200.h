@@ -82,6 +82,7 @@ int         dh_set_workspace(dh_ctx* ctx, void* ptr, int64_t bytes);
 /* tuning switches: "share_a" (default 1) = 2-CTA clusters share the separable A tile over DSMEM;
  * "sep_tma" (default 1) = use the TMA-staged separable kernel where it applies;
  * "pw_smallk" (default 1) = CUDA-core kernel for wide 1x1 convs with Cin <= 64;
+ * "dense_patch" (default 1) = TMA-staged patch kernel (conv_patch.cu) for stride-1 Conv2D where it applies;
  * "dbg" (default 0) = timing-ablation bits for tools/ (results are WRONG when non-zero) */
 int         dh_set_option(dh_ctx* ctx, const char* name, int value);
 
@@ -92,8 +93,12 @@ int dh_tc_cout_pad(int cout);
 int dh_tc_k_pad(int k);
 /* which kernel family served the last dh_conv2d_f32 / dh_sepconv2d_f32 on this context:
  * 0 = CUDA-core (fp32 FFMA), 1 = tcgen05 kernel (conv_tc.cu), 2 = TMA-staged tcgen05 separable kernel (conv_sep.cu),
- * 3 = CUDA-core wide pointwise kernel for 1x1 convs with Cin <= 64 and Cout >= 128 (exact fp32). */
+ * 3 = CUDA-core wide pointwise kernel for 1x1 convs with Cin <= 64 and Cout >= 128 (exact fp32),
+ * 4 = TMA-staged patch tcgen05 kernel for stride-1 Conv2D (conv_patch.cu). */
 int dh_last_conv_path(dh_ctx* ctx);
+/* convolutions that no tensor-core / specialised kernel took and that ran on the generic CUDA-core
+ * implicit-GEMM kernel (path 0) since creation / reset: the silent-fallback counter. */
+int64_t dh_fallback_count(dh_ctx* ctx, int reset);
 
 /* keras Conv2D(use_bias=False) (layers.py:66-71) with fused pre/post ops.
  * w: HWIO (kh,kw,Cin,Cout) fp32 -- the keras kernel layout, unchanged.

@@ -85,7 +85,7 @@ def collect(model, prefix='', trainable=True, strip=()):
     return out
 
 
-def pin(case, ref_model, prod_model, seed, x, strip=()):
+def pin(case, ref_model, prod_model, seed, x, strip=(), x_recipe=None):
     ws = collect(ref_model, strip=strip)
     names = [n for n, _, _ in ws]
     assert len(set(names)) == len(names), 'duplicate weight names in the reference model'
@@ -103,39 +103,64 @@ def pin(case, ref_model, prod_model, seed, x, strip=()):
     if not isinstance(outs, (list, tuple)):
         outs = [outs]
     path = os.path.join(HERE, 'ref_%s.npz' % case)
-    blob = {'out%d' % i: np.asarray(o, dtype=np.float64) for i, o in enumerate(outs)}
+    # big outputs (exported heat-maps) are kept in float32: they are compared at 1e-3 / by arg-max
+    blob = {'out%d' % i: np.asarray(o, dtype=np.float64 if np.size(o) < 10000 else np.float32) for i, o in enumerate(outs)}
     blob['weight_names'] = np.array(sorted(trainable))
     blob['weight_shapes'] = np.array([repr(tuple(trainable[n]['value'].shape)) for n in sorted(trainable)])
     blob['fixed_names'] = np.array(sorted(n for n, w, frozen in ws if frozen))
     blob['optional_in_product'] = np.array(sorted(prod_model.optional_weights))
     blob['seed'] = np.array(seed)
-    blob['x'] = np.asarray(x, dtype=np.float32)
+    if x_recipe is None:
+        blob['x'] = np.asarray(x, dtype=np.float32)
+    else:           # large inputs: the test regenerates them; keep the recipe and a checksum
+        import zlib
+        blob['x_recipe'] = np.array(x_recipe)
+        blob['x_crc32'] = np.array(zlib.crc32(np.ascontiguousarray(x, dtype=np.float32).tobytes()))
     np.savez_compressed(path, **blob)
     print('%-28s %3d trainable + %2d fixed weights, %d outputs -> %s (%.0f KB)' % (
         case, len(trainable), len(ws) - len(trainable), len(outs), os.path.basename(path), os.path.getsize(path) / 1024.0))
 
 
 def main():
-    from ref_cases import MERGE_CASE, RECEPTION_CASES, SPNET_CASES
+    from ref_cases import LARGE_INPUT_CASES, MERGE_CASE, RECEPTION_CASES, SPNET_CASES, SPNET_FULL_CASES
+    only = set(sys.argv[1:])
     # ---- ReceptionNet (CVPR'18) ----
     for case, spec in RECEPTION_CASES.items():
         shape, kw, seed, xs = spec[:4]
         frames = spec[4] if len(spec) > 4 else 2
+        if only and case not in only:
+            continue
         fresh_process_state()
         ref = ref_reception.build(shape, **kw)
         prod = reception.build(shape, **kw)
-        pin(case, ref, prod, seed, synth.synth_frames(frames, shape[0], shape[1], seed=xs))
+        pin(case, ref, prod, seed, synth.synth_frames(frames, shape[0], shape[1], seed=xs),
+            x_recipe='synth_frames(%d,%d,%d,seed=%d)' % (frames, shape[0], shape[1], xs) if case in LARGE_INPUT_CASES else None)
 
     # ---- SPNet (TPAMI'20) ----
     rng = np.random.default_rng(11)
     layouts = {'pa16j2d': (ref_pa16j2d, pa16j2d), 'pa17j3d': (ref_pa17j3d, pa17j3d)}
     for case, (shape, layout, kw, seed, batch) in SPNET_CASES.items():
+        x_case = rng.uniform(-1.0, 1.0, (batch,) + shape)          # always drawn: keeps the shared stream's order
+        if only and case not in only:
+            continue
         fresh_process_state()
         ref = ref_spnet.build(RefModelConfig(shape, layouts[layout][0], **kw))
         prod = spnet.build(ModelConfig(shape, layouts[layout][1], **kw))
-        pin(case, ref, prod, seed, rng.uniform(-1.0, 1.0, (batch,) + shape))
+        pin(case, ref, prod, seed, x_case)
+
+    for case, (shape, layout, kw, seed, batch, xs) in SPNET_FULL_CASES.items():
+        if only and case not in only:
+            continue
+        fresh_process_state()
+        ref = ref_spnet.build(RefModelConfig(shape, layouts[layout][0], **kw))
+        prod = spnet.build(ModelConfig(shape, layouts[layout][1], **kw))
+        pin(case, ref, prod, seed, np.random.default_rng(xs).uniform(-1.0, 1.0, (batch,) + shape),
+            x_recipe='default_rng(%d).uniform(-1,1,%r)' % (xs, (batch,) + shape))
 
     # ---- CVPR'18 merge model (2-D pose + action) ----
+    x_merge = rng.uniform(-1.0, 1.0, (1, MERGE_CASE['num_frames']) + MERGE_CASE['input_shape'])
+    if only and 'merge_model' not in only:
+        return
     fresh_process_state()
     mc = MERGE_CASE
     ref_pe = ref_reception.build(mc['input_shape'], **mc['reception'])
@@ -144,7 +169,7 @@ def main():
     prod_pe = reception.build(mc['input_shape'], **mc['reception'])
     prod = action.build_merge_model(prod_pe, mc['num_actions'], mc['input_shape'], mc['num_frames'], mc['num_joints'],
                                     mc['num_blocks'], pose_dim=2)
-    pin('merge_model', ref, prod, mc['seed'], rng.uniform(-1.0, 1.0, (1, mc['num_frames']) + mc['input_shape']), strip=('td_',))
+    pin('merge_model', ref, prod, mc['seed'], x_merge, strip=('td_',))
 
 
 if __name__ == '__main__':

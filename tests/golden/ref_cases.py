@@ -12,6 +12,17 @@ RECEPTION_CASES = {
                                                     concat_pose_confidence=False), 1234, 31, 1),
 }
 
+# full-size BASELINE configs, inputs regenerated from their seed (the fixture stores seed + checksum, not the frames)
+RECEPTION_CASES.update({
+    # configs[2]: exp/h36m/eval_h36m.py:42-48 -- 3-D pose, 17 joints, 8 blocks, 256x256
+    'reception3d_c3_fullsize': ((256, 256, 3), dict(num_joints=17, dim=3, num_blocks=8, ksize=(5, 5),
+                                                    concat_pose_confidence=False), 1234, 41, 1),
+    # configs[0]/[1] with every block's heat-maps exported: arg-max pixels of all 8 heads
+    'reception2d_c1_heatmaps': ((256, 256, 3), dict(num_joints=16, dim=2, num_blocks=8, ksize=(5, 5), num_context_per_joint=2,
+                                                    concat_pose_confidence=False, export_heatmaps=True), 1234, 43, 1),
+})
+LARGE_INPUT_CASES = ('reception3d_c3_fullsize', 'reception2d_c1_heatmaps', 'spnet_penn_c4_t16', 'spnet_ntu_c5_t16')
+
 SPNET_CASES = {
     # case: (cfg input shape, pose layout name, ModelConfig kwargs, weight seed, batch)
     'spnet_penn_like': ((2, 128, 128, 3), 'pa16j2d',
@@ -26,6 +37,19 @@ SPNET_CASES = {
     'spnet_penn_c4_t2': ((2, 256, 256, 3), 'pa16j2d',
                          dict(num_actions=[15], num_pyramids=6, action_pyramids=[5, 6], num_levels=4, pose_replica=True,
                               num_pose_features=160, num_visual_features=160), 1234, 1),
+}
+
+# full clips: x = default_rng(seed_x).uniform(-1, 1, (batch,) + shape) (own generator per case)
+SPNET_FULL_CASES = {
+    # case: (cfg input shape, pose layout, ModelConfig kwargs, weight seed, batch, input seed)
+    # configs[3] (exp/pennaction/eval_penn_multitask.py:37-40 with 8 -> 16 frames): time_stride = 2 in the action head
+    'spnet_penn_c4_t16': ((16, 256, 256, 3), 'pa16j2d',
+                          dict(num_actions=[15], num_pyramids=6, action_pyramids=[5, 6], num_levels=4, pose_replica=True,
+                               num_pose_features=160, num_visual_features=160), 1234, 1, 101),
+    # configs[4] (exp/ntu/eval_ntu_multitask.py:35-38 with 8 -> 16 frames), 3-D poses, 60 actions
+    'spnet_ntu_c5_t16': ((16, 256, 256, 3), 'pa17j3d',
+                         dict(num_actions=[60], num_pyramids=2, action_pyramids=[1, 2], num_levels=4, num_pose_features=192,
+                              num_visual_features=192), 1234, 1, 102),
 }
 
 # CVPR'18 merge model (exp/pennaction/eval_penn_ar_pe_merge.py:42-62), small geometry

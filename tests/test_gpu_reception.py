@@ -95,3 +95,27 @@ def test_full_size_single_frame(cuda):
     refs = oracle_reception.forward(ops_torch, m.get_weights(), x, debug=dbg, **kw)
     outs = m.predict(x)
     _check(outs, [r.astype(np.float64) for r in refs], cond=dbg['ctx_cond'])
+
+
+def test_c2_batch32_equals_32_single_frame_calls(cuda):
+    """C2 (BASELINE.json configs[1]): the C1 model on a batch of 32 frames.  keras predict semantics: the
+    result of one b32 call is the concatenation of 32 b1 calls; frame 0 is the frame of the reference-builder
+    golden `ref_reception2d_c1_fullsize.npz` (same weights, seed 1234), so the b32 path is pinned to the
+    reference graph at the quoted size."""
+    import os
+    kw = dict(num_joints=16, dim=2, num_context_per_joint=2, num_blocks=8, ksize=(5, 5),
+              concat_pose_confidence=False)
+    m = reception.build((256, 256, 3), **kw).init_synthetic_weights(1234)
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'ref_reception2d_c1_fullsize.npz'))
+    x = np.concatenate([z['x'], synth.synth_frames(31, seed=77)], axis=0)
+    assert x.shape == (32, 256, 256, 3)
+    b32 = m.predict(x, batch_size=32)
+    b1 = m.predict(x, batch_size=1)
+    for a, b in zip(b32, b1):
+        assert a.shape == b.shape and a.shape[0] == 32
+        assert np.abs(a - b).max() <= 1e-5          # same kernels, same per-frame arithmetic
+    dbg = {}
+    from oracle import ops_torch
+    oracle_reception.forward(ops_torch, m.get_weights(), z['x'].astype(np.float64), debug=dbg, **kw)
+    refs = [z['out%d' % i] for i in range(16)]
+    _check([o[:1] for o in b32], refs, cond=dbg['ctx_cond'])

@@ -49,13 +49,60 @@ CONV_CASES = [
     (1, 32, 32, 32, 64, (3, 3), (1, 1), False),      # K-block straddles taps (Cin = 32)
     (1, 7, 5, 12, 272, (1, 1), (1, 1), False),       # M tail, ragged Cout (3-D RegMap width)
     (1, 16, 16, 64, 17, (1, 1), (1, 1), False),      # Cout = 17 (SPNet heat-maps): scalar epilogue
+    # --- shapes of the TMA-staged patch kernel (conv_patch.cu) ---
+    (2, 128, 128, 32, 64, (3, 3), (1, 1), False),    # stem conv3: one image row per tile, 130-pixel patch rows
+    (1, 128, 128, 32, 32, (3, 3), (1, 1), False),    # stem conv2
+    (1, 64, 64, 64, 96, (3, 3), (1, 1), False),      # stem 3x3 at 64x64: two channel blocks x 9 taps
+    (1, 64, 64, 64, 64, (5, 1), (1, 1), False),      # stem 5x1
+    (1, 64, 64, 64, 64, (1, 5), (1, 1), False),      # stem 1x5
+    (1, 64, 64, 160, 64, (1, 1), (1, 1), False),     # stem 1x1 on the concat (Cin = 5 blocks)
+    (3, 16, 16, 288, 576, (1, 1), (1, 1), True),     # rBlock expand (two N CTAs)
+    (2, 32, 32, 144, 288, (3, 3), (1, 1), True),     # SPNet residual unit 3x3 with BN prologue (masked halo)
+    (2, 128, 128, 48, 96, (3, 3), (1, 1), True),     # SPNet entry 3x3, Cin = 48 (half-empty channel block)
+    (5, 8, 8, 480, 16, (1, 1), (1, 1), True),        # SPNet heat-map conv at 8x8: odd frame count, 64-pixel virtual rows
+    (3, 8, 8, 64, 64, (3, 3), (1, 1), True),         # two frames per tile, tail tile, BN prologue mask
+    (7, 4, 4, 96, 32, (3, 3), (1, 1), True),         # 4x4 maps are not taken by the patch kernel (falls to conv_tc)
 ]
+
+
+def _patch_eligible(case):
+    n, h, w, cin, cout, size, strides, fused = case
+    if strides != (1, 1) or cin % 8:
+        return False
+    if size == (1, 1):
+        vw = 128
+        while vw > 1 and (h * w) % vw:
+            vw //= 2
+        if vw < 8:
+            return False
+        pc, pr, fn = vw, 128 // vw, 1
+    else:
+        if w not in (128, 64, 32, 16, 8):
+            return False
+        tr = 128 // w
+        if (h % tr if tr <= h else tr % h) != 0:
+            return False
+        pc, pr, fn = w + size[1] - 1, min(tr, h) + size[0] - 1, max(1, tr // h)
+    cp = (cout + 15) // 16 * 16
+    gy = (cp + 287) // 288
+    bn = ((cp + gy - 1) // gy + 15) // 16 * 16
+    if bn > 256:
+        bn = (bn + 31) // 32 * 32
+    stride = (128 * pc * pr * fn + 1023) // 1024 * 1024
+    fixed = 3 * 2 * 8192 + 4 * bn * 64 + (4 * 32 * 128 + 2 * 288 * 4) + 512 + 1024
+    return fixed + 2 * stride <= 227 * 1024
 
 
 @pytest.mark.parametrize('case', CONV_CASES)
 @pytest.mark.parametrize('precision', [3, 1])
-def test_conv_tc(dev, case, precision):
+@pytest.mark.parametrize('kernel', ['patch', 'reg'])
+def test_conv_tc(dev, case, precision, kernel):
+    """kernel = 'patch': conv_patch.cu (TMA-staged input patch, path 4) where it applies; 'reg': conv_tc.cu's
+    register im2col producer (path 1)."""
     n, h, w, cin, cout, size, strides, fused = case
+    if kernel == 'reg' and n * h * w * cin > (1 << 21) and precision == 1:
+        pytest.skip('large case: the register-producer kernel is covered at precision 3')
+    expect = 4 if (kernel == 'patch' and _patch_eligible(case)) else 1
     rng = np.random.default_rng(zlib.crc32(repr(case).encode()))
     x = rng.standard_normal((n, h, w, cin))
     wt = rng.standard_normal(size + (cin, cout)) / np.sqrt(size[0] * size[1] * cin)
@@ -79,11 +126,13 @@ def test_conv_tc(dev, case, precision):
     # the wide / small-Cin 1x1 shapes would be served by the CUDA-core pointwise kernel (test_gpu_ops.py):
     # switch it off so that this test keeps exercising the tensor-core kernel on them
     _ffi.check(dev.lib.dh_set_option(dev.ctx.handle, b'pw_smallk', 0))
+    _ffi.check(dev.lib.dh_set_option(dev.ctx.handle, b'dense_patch', 1 if kernel == 'patch' else 0))
     try:
         dev.call('dh_conv2d_f32', C.byref(xv), dev.put(wt).data_ptr(), C.byref(pk), C.byref(d), C.byref(ov))
     finally:
         _ffi.check(dev.lib.dh_set_option(dev.ctx.handle, b'pw_smallk', 1))
-    assert dev.lib.dh_last_conv_path(dev.ctx.handle) == 1, 'tensor-core path was not taken'
+        _ffi.check(dev.lib.dh_set_option(dev.ctx.handle, b'dense_patch', 1))
+    assert dev.lib.dh_last_conv_path(dev.ctx.handle) == expect, 'unexpected kernel path'
     e = _err(out.cpu().numpy(), ref)
     assert e <= (TOL3 if precision == 3 else TOL1), e
 
@@ -170,7 +219,7 @@ def test_tc_channel_views(dev):
     pk = _packed(dev, wt.reshape(64, 32))
     xv, ov = dev.view(dev.put(big), 16, 80), dev.view(cat, 4, 36)
     dev.call('dh_conv2d_f32', C.byref(xv), dev.put(wt).data_ptr(), C.byref(pk), C.byref(d), C.byref(ov))
-    assert dev.lib.dh_last_conv_path(dev.ctx.handle) == 1
+    assert dev.lib.dh_last_conv_path(dev.ctx.handle) == 4          # the patch kernel takes channel-sliced views
     got = cat.cpu().numpy()
     assert _err(got[..., 4:36], ref) <= TOL3
     assert np.all(got[..., :4] == 7.0) and np.all(got[..., 36:] == 7.0)

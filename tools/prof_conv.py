@@ -19,6 +19,8 @@ reps = int(sys.argv[9]) if len(sys.argv) > 9 else 5
 dev = Dev(torch)
 if os.environ.get('DH_DBG'):
     dev.lib.dh_set_option(dev.ctx.handle, b'dbg', int(os.environ['DH_DBG']))
+if os.environ.get('DH_PATCH'):
+    dev.lib.dh_set_option(dev.ctx.handle, b'dense_patch', int(os.environ['DH_PATCH']))
 if os.environ.get('DH_SHARE'):
     dev.lib.dh_set_option(dev.ctx.handle, b'share_a', int(os.environ['DH_SHARE']))
 rng = np.random.default_rng(0)
