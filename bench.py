@@ -4,19 +4,27 @@
   python bench.py --gpus N --steps K --warmup W            (ours; torchrun for N > 1)
   python bench.py --impl reference --gpus N --steps K --warmup W   (CPU arm, see below)
 
-Workload (config.workload): ReceptionNet 2-D pose, the model of BASELINE.json configs[1]
+Headline workload (config.workload): ReceptionNet 2-D pose, the model of BASELINE.json configs[1]
 (`reception.build((256,256,3), 16, dim=2, num_blocks=8, num_context_per_joint=2, ksize=(5,5))`,
-exp/mpii/eval_mpii_singleperson.py:42-49) on the headline batch: 32 clips x 16 frames of
-256x256x3 = 512 frames per GPU per step (TimeDistributed folds clips into frames), synthetic
-uniform[-1,1] frames and seeded synthetic weights (no datasets / checkpoints offline).
+exp/mpii/eval_mpii_singleperson.py:42-49) on the headline batch: 32 clips x 16 frames of 256x256x3 = 512 frames
+per step (TimeDistributed folds clips into frames), synthetic uniform[-1,1] frames and seeded synthetic weights
+(no datasets / checkpoints offline).
 
-  value  : frames/s, inputs resident in HBM (512 frames = 403 MB > L2, so no L2 flush is
-           needed between iterations), CUDA-event timed, max over ranks.
-  e2e    : frames/s through Model.predict() with pinned HOST input, H2D + D2H inside the
-           timed region.
-  --impl reference : the reference's Keras/TF forward cannot run here (no tensorflow/keras in
-           the image); the arm times the CPU port of the same graph
-           (oracle/, torch-CPU fp32, all host threads) on a bounded sample.
+  scaling : STRONG: the fixed 32-clip batch is split contiguously over the N ranks
+            (`dist.shard_range`: 32 / 16 / 8 / 4 clips per GPU), weights replicated, no data-path collective; the one
+            exchange step is a fixed-shape all-gather of the last block's (pose, visibility) over NCCL.  The weak
+            number (512 frames on every GPU) is reported under secondary.weak.
+  value   : frames/s, inputs resident in HBM, CUDA-event timed, max over ranks.  Forwards are CUDA-graph replays.
+  e2e     : frames/s through Model.predict() with pinned HOST input, H2D + D2H inside the timed region.
+  roofline: the dominant kernel of the step (CUDA events around every launch of one extra step): algorithmic
+            FLOPs / launch time vs the measured bf16 peak; `traffic` = DRAM bytes of that kernel from the committed
+            ncu capture (profiles/r2_traffic.json, written by tools/ncu_traffic.py from the raw ncu CSV).
+  secondary: the other BASELINE configs on the same box -- C3 (H36M 3-D, b32), C4 (PennAction SPNet, 16 clips),
+            C5 (NTU SPNet, 64 clips, action all-gather) -- and the soft-argmax 2-D / 3-D HBM micro-benchmarks.
+  --impl reference : the reference's Keras/TF forward cannot run here (no tensorflow/keras in the image,
+            SURVEY.md 8c); the arm times the CPU port of the same graph (oracle/, torch-CPU fp32, all host
+            threads): one step = one b32 forward of the C2 model (a 32-frame sample of the 512-frame step), plus
+            the C1 (b1) latency, medians over the timed iterations.
 """
 import argparse
 import json
@@ -33,8 +41,10 @@ sys.path.insert(0, ROOT)
 
 MODEL_KW = dict(num_joints=16, dim=2, num_context_per_joint=2, num_blocks=8, ksize=(5, 5),
                 concat_pose_confidence=False)
+C3_KW = dict(num_joints=17, dim=3, num_blocks=8, ksize=(5, 5), concat_pose_confidence=False)
 CLIPS, FRAMES = 32, 16
 METRIC = 'frames/sec (256x256, 16-frame clips, b32)'
+HEADLINE = 'reception2d_8blk_k5_j16 (BASELINE configs[1] model) x 32 clips x 16 frames'
 
 
 def measured_peaks():
@@ -46,6 +56,15 @@ def measured_peaks():
                 'bf16_tflops_sustained': p.get('bf16_tflops_sustained', p['bf16_tflops']),
                 'source': 'measured'}
     return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0, 'source': 'fallback'}
+
+
+def ncu_traffic():
+    """{kernel label: {'bytes_per_frame', 'source'}} from the committed ncu capture (tools/ncu_traffic.py)."""
+    path = os.path.join(ROOT, 'profiles', 'r2_traffic.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f)
+    return {}
 
 
 class ClockSampler(object):
@@ -100,49 +119,171 @@ class ClockSampler(object):
                 'samples': len(sm)}
 
 
-def cpu_port_frames_per_sec(n_frames, batch, warmup=1):
-    """CPU port (oracle, torch-CPU fp32/oneDNN, all threads) of the same model on a bounded sample."""
+# ------------------------------------------------------------------------------------------------------------------
+# workloads
+# ------------------------------------------------------------------------------------------------------------------
+def build_workload(name):
+    """-> (model, clip_model: bool, label).  Frames are 256x256x3; clip models take (clips, 16, 256, 256, 3)."""
+    if name in ('reception2d', 'reception3d'):
+        from deephar_b200 import reception
+        kw = MODEL_KW if name == 'reception2d' else C3_KW
+        label = HEADLINE if name == 'reception2d' else 'reception3d_8blk_k5_j17 (BASELINE configs[2] model, H36M 3-D)'
+        return reception.build((256, 256, 3), **kw).init_synthetic_weights(1234), False, label
+    from deephar_b200 import spnet
+    from deephar_b200.config import ModelConfig, pa16j2d, pa17j3d
+    if name == 'spnet_penn':
+        cfg = ModelConfig((FRAMES, 256, 256, 3), pa16j2d, num_actions=[15], num_pyramids=6, action_pyramids=[5, 6],
+                          num_levels=4, pose_replica=True, num_pose_features=160, num_visual_features=160)
+        label = 'spnet PennAction multitask (BASELINE configs[3] model), 16-frame clips'
+    else:
+        cfg = ModelConfig((FRAMES, 256, 256, 3), pa17j3d, num_actions=[60], num_pyramids=2, action_pyramids=[1, 2],
+                          num_levels=4, num_pose_features=192, num_visual_features=192)
+        label = 'spnet NTU 3D multitask (BASELINE configs[4] model), 16-frame clips'
+    return spnet.build(cfg).init_synthetic_weights(1234), True, label
+
+
+class Runner(object):
+    """One workload on this rank's shard of a global batch of `items` (clips, or frames for b32-of-frames configs)."""
+
+    def __init__(self, torch, model, clip_model, items_global, item_frames, rank, world, micro_frames, precision=3):
+        from deephar_b200.dist import shard_range
+        self.torch, self.model, self.world = torch, model, world
+        model.precision = precision
+        a, b = shard_range(items_global, rank, world)
+        self.items_global, self.items_local, self.item_frames = items_global, b - a, item_frames
+        self.frames_local = self.items_local * item_frames
+        self.clip_model = clip_model
+        shape = ((self.items_local, FRAMES, 256, 256, 3) if clip_model else (self.frames_local, 256, 256, 3))
+        gen = torch.Generator().manual_seed(1000 + a)
+        self.x_host = torch.empty(*shape, dtype=torch.float32).pin_memory()
+        if self.x_host.numel():
+            self.x_host.uniform_(-1.0, 1.0, generator=gen)
+        self.x_dev = self.x_host.cuda()
+        per = FRAMES if clip_model else 1
+        self.micro_items = max(1, min(micro_frames // per, shape[0])) if shape[0] else 1
+        self.spans = [(i, min(i + self.micro_items, shape[0])) for i in range(0, shape[0], self.micro_items)]
+        self.comm = None            # dist.Comm: the all-gather through the C ABI (set by main for world > 1)
+
+    def forward_all(self):
+        last = None
+        for (i, j) in self.spans:
+            last = self.model.forward_device(self.x_dev[i:j])
+        return last
+
+    def exchange(self, outs, which):
+        """The one exchange step of the data-parallel path: all-gather of the final outputs."""
+        if self.world == 1 or outs is None:
+            return outs
+        from deephar_b200.dist import gather_outputs
+        torch = self.torch
+        if which == 'pose':         # reception: last block's (pose, visibility) of the LAST micro-batch
+            local = torch.cat([outs[-2], outs[-1]], dim=-1)
+            return gather_outputs(local.contiguous(), self.world, comm=self.comm)
+        local = torch.stack([o for o in outs if o.dim() == 2], dim=1)    # action probabilities (B_local, n_pred, n_act)
+        return gather_outputs(local.contiguous(), self.world, comm=self.comm)
+
+    def step(self, which):
+        return self.exchange(self.forward_all(), which)
+
+
+def timed_steps(torch, dist, world, fn, steps, warmup):
+    """W warm-ups, then K steps bracketed by barrier + synchronize, CUDA events, max over ranks -> ms per step."""
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(warmup):
+        fn()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device='cuda')
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item()) / steps
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU arm (SURVEY.md 8d)
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_port(iters_b32, iters_b1, warm_b32=1, warm_b1=3):
+    """torch-CPU (oneDNN) fp32 port of the Keras graph (oracle/), all host threads: C2 (b32) and C1 (b1) medians."""
     import torch
     from deephar_b200 import reception
     from oracle import ops_torch, synth
     from oracle import reception as oracle_reception
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)                 # torchrun exports OMP_NUM_THREADS=1: undo it explicitly
     m = reception.build((256, 256, 3), **MODEL_KW).init_synthetic_weights(1234)
     table = m.get_weights()
-    x = synth.synth_frames(batch, seed=0)
-    for _ in range(warmup):
-        oracle_reception.forward(ops_torch, table, x, **MODEL_KW)
-    t0 = time.perf_counter()
-    done = 0
-    while done < n_frames:
-        oracle_reception.forward(ops_torch, table, x, **MODEL_KW)
-        done += batch
-    dt = time.perf_counter() - t0
-    return done / dt, torch.get_num_threads(), done, dt
+
+    def run(batch, warm, iters):
+        x = synth.synth_frames(batch, seed=0)
+        times = []
+        for i in range(warm + iters):
+            t0 = time.perf_counter()
+            oracle_reception.forward(ops_torch, table, x, **MODEL_KW)
+            dt = time.perf_counter() - t0
+            if i >= warm:
+                times.append(dt)
+        return times
+    t1 = run(1, warm_b1, iters_b1) if iters_b1 else []
+    t32 = run(32, warm_b32, iters_b32)
+    return {'b32_times': t32, 'b1_times': t1, 'cores': cores, 'threads': torch.get_num_threads()}
+
+
+def headline_config(world, frames_local, micro):
+    return {'workload': HEADLINE, 'global_batch_frames': CLIPS * FRAMES, 'frames_per_gpu': frames_local,
+            'micro_batch': micro, 'parallelism': 'dp%d' % world,
+            'l2': 'inputs (%.0f MB per GPU per step) + 7 GB of activations per forward >> 126 MB L2; no flush needed'
+                  % (frames_local * 256 * 256 * 3 * 4 / 1e6)}
 
 
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    per_step = 8           # frames per "step" of the bounded CPU sample
-    for _ in range(max(args.warmup, 1) - 1):
-        cpu_port_frames_per_sec(per_step, 4, warmup=0)
-    fps, cores, done, dt = cpu_port_frames_per_sec(per_step * args.steps, 4, warmup=1)
-    sample = '%d frames of the 512-frame step (batches of 4), torch-CPU fp32 port of the Keras graph' % done
+    from deephar_b200.dist import shard_range
+    r = cpu_port(iters_b32=args.steps, iters_b1=10, warm_b32=max(args.warmup, 1), warm_b1=3)
+    med32 = float(np.median(r['b32_times']))
+    fps = 32.0 / med32
+    a, b = shard_range(CLIPS, 0, args.gpus)
+    frames_local = (b - a) * FRAMES
+    sample = ('one b32 forward of the C2 model per step (32 of the 512 frames), median of %d timed steps = %.2f s; '
+              'C1 (b1) latency median of 10 = %.3f s; torch-CPU fp32 port of the Keras graph (oracle/), %d threads'
+              % (len(r['b32_times']), med32, float(np.median(r['b1_times'])), r['threads']))
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': fps, 'unit': 'frames/s', 'n_gpus': args.gpus,
-        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1000.0 * dt / args.steps,
-        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
-        'data': 'synthetic',
-        # same workload as the product arm; each step is a bounded sample of it (see cpu_baseline.sample)
-        'config': {'workload': 'reception2d_8blk_k5_j16 (BASELINE configs[1] model) x 32 clips x 16 frames',
-                   'global_batch_frames': CLIPS * FRAMES, 'sample_frames_per_step': per_step,
-                   'implementation': 'CPU port of the Keras graph (oracle/, torch-CPU fp32, all host threads); '
-                                     'keras 2.1.4 / tensorflow 1.6 are not installable in this image'},
-        'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1000.0 * med32,
+        'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': headline_config(args.gpus, frames_local, min(args.micro_batch, frames_local)),
+        'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': r['threads'], 'kind': 'port', 'sample': sample,
+                         'c1_b1_latency_s': float(np.median(r['b1_times'])), 'host_cpu_count': r['cores'],
+                         'implementation': 'CPU port of the Keras graph; keras 2.1.4 / tensorflow 1.6 are not '
+                                           'installable in this image (SURVEY.md 8c)'},
         'e2e': {'value': fps, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# micro-benchmarks: soft-argmax heads (BASELINE metric: "softargmax HBM GB/s")
+# ------------------------------------------------------------------------------------------------------------------
+def _time_launch(torch, launch, reps=10):
+    for _ in range(3):
+        launch()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        launch()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
 
 
 def softargmax_microbench(torch, model, peaks):
@@ -161,17 +302,7 @@ def softargmax_microbench(torch, model, peaks):
     def launch():
         _ffi.check(lib.dh_softargmax2d_ctx_f32(ctx, C.byref(hv), 16, 2, C.c_float(0.8), pose.data_ptr(),
                                                vis.data_ptr(), st), 'softargmax')
-    for _ in range(3):
-        launch()
-    torch.cuda.synchronize()
-    reps = 10
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(reps):
-        launch()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / reps
+    ms = _time_launch(torch, launch)
     bytes_ = n * (32 * 32 * 48 * 4 + 16 * 3 * 4)
     gbs = bytes_ / ms / 1e6
     return {'kernel': 'softargmax2d_ctx (32x32x48 maps, %d frames, %.0f MB > L2)' % (n, bytes_ / 1e6),
@@ -179,13 +310,27 @@ def softargmax_microbench(torch, model, peaks):
             'frac': gbs / peaks['hbm_gbs'], 'us_per_launch': ms * 1000.0, 'peak_source': peaks['source']}
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE `ncu --set full` capture of the dominant kernel (committed
-# under profiles/), per frame; the capture is a 128-frame launch, the bench launch is micro_batch frames.
-NCU_TRAFFIC = {
-    'sepconv 32x32x576->32x32x576 k5x5': {
-        'bytes_per_frame': (855.118336e6 + 270.342912e6) / 128,
-        'source': 'profiles/r1_septma_final.ncu-rep (128-frame launch: 855.1 MB read + 270.3 MB written), scaled per frame'},
-}
+def softargmax3d_microbench(torch, model, peaks):
+    """dh_softargmax3d_f32 on C3's volume: 256 frames x (32,32,16*17) = 285 MB (32 frames x 8 blocks of the b32 step)."""
+    import ctypes as C
+    from deephar_b200 import _ffi
+    n, nj, d = 256, 17, 16
+    g = torch.Generator(device='cuda').manual_seed(0)
+    h = torch.randn(n, 32, 32, nj * d, device='cuda', generator=g) * 3.0
+    pose = torch.empty(n, nj, 3, device='cuda')
+    vis = torch.empty(n, nj, 1, device='cuda')
+    hv = _ffi.dh_view(h.data_ptr(), n, 32, 32, nj * d, nj * d)
+    lib, ctx = _ffi.lib(), model._ctx.handle
+    st = torch.cuda.current_stream().cuda_stream
+
+    def launch():
+        _ffi.check(lib.dh_softargmax3d_f32(ctx, C.byref(hv), nj, d, pose.data_ptr(), vis.data_ptr(), st), 'softargmax3d')
+    ms = _time_launch(torch, launch)
+    bytes_ = n * (32 * 32 * nj * d * 4 + nj * 4 * 4)
+    gbs = bytes_ / ms / 1e6
+    return {'kernel': 'softargmax3d (32x32x272 volumes, %d frames, %.0f MB > L2)' % (n, bytes_ / 1e6),
+            'bound': 'hbm', 'achieved': gbs, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
+            'frac': gbs / peaks['hbm_gbs'], 'us_per_launch': ms * 1000.0, 'peak_source': peaks['source']}
 
 
 def main():
@@ -195,14 +340,16 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--micro-batch', type=int, default=256, help='frames per forward call')
-    ap.add_argument('--workload', default='reception2d', choices=['reception2d', 'spnet_penn', 'spnet_ntu'],
-                    help='reception2d = BASELINE configs[1] model (headline); spnet_* = configs[3]/[4] models')
+    ap.add_argument('--workload', default='reception2d', choices=['reception2d', 'reception3d', 'spnet_penn', 'spnet_ntu'],
+                    help='reception2d = BASELINE configs[1] model (headline); others: configs[2]/[3]/[4] models')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-secondary', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='plain launches instead of CUDA-graph replays')
     ap.add_argument('--precision', type=int, default=3)
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
     if args.impl == 'reference':
         return run_reference(args)
+    args.warmup = max(args.warmup, 3)
 
     import torch
     import torch.distributed as dist
@@ -216,130 +363,137 @@ def main():
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
 
     peaks = measured_peaks()
-    n_frames = CLIPS * FRAMES
-    mb = args.micro_batch
-    assert n_frames % mb == 0
-    if args.workload == 'reception2d':
-        from deephar_b200 import reception
-        model = reception.build((256, 256, 3), **MODEL_KW).init_synthetic_weights(1234)
-        in_shape, step_items, wl_name = (n_frames, 256, 256, 3), mb, \
-            'reception2d_8blk_k5_j16 (BASELINE configs[1] model) x 32 clips x 16 frames'
-    else:
-        from deephar_b200 import spnet
-        from deephar_b200.config import ModelConfig, pa16j2d, pa17j3d
-        if args.workload == 'spnet_penn':
-            cfg = ModelConfig((FRAMES, 256, 256, 3), pa16j2d, num_actions=[15], num_pyramids=6,
-                              action_pyramids=[5, 6], num_levels=4, pose_replica=True, num_pose_features=160,
-                              num_visual_features=160)
-            wl_name = 'spnet PennAction multitask (BASELINE configs[3] model) x 32 clips x 16 frames'
-        else:
-            cfg = ModelConfig((FRAMES, 256, 256, 3), pa17j3d, num_actions=[60], num_pyramids=2,
-                              action_pyramids=[1, 2], num_levels=4, num_pose_features=192, num_visual_features=192)
-            wl_name = 'spnet NTU 3D multitask (BASELINE configs[4] model) x 32 clips x 16 frames'
-        model = spnet.build(cfg).init_synthetic_weights(1234)
-        assert mb % FRAMES == 0
-        in_shape, step_items = (CLIPS, FRAMES, 256, 256, 3), mb // FRAMES
-    model.precision = args.precision
+    model, clip_model, wl_name = build_workload(args.workload)
+    model.use_cuda_graph = not args.no_graph
+    items_global = CLIPS
+    item_frames = FRAMES
+    run = Runner(torch, model, clip_model, items_global, item_frames, rank, world, args.micro_batch, args.precision)
+    comm = None
+    if world > 1:               # the exchange step goes through the C ABI (dh_comm_init / dh_allgather_f32)
+        from deephar_b200.dist import Comm
+        model._ensure_device_weights()
+        comm = Comm(model._ctx, rank, world)
+        run.comm = comm
+    which = 'action' if clip_model else 'pose'
+    n_frames = CLIPS * FRAMES                       # global frames per step (strong scaling: fixed)
+    micro = run.micro_items * (FRAMES if clip_model else 1)
 
-    # synthetic frames, uniform [-1,1], pinned host memory (e2e source) + a device copy (value)
-    gen = torch.Generator().manual_seed(rank)
-    x_host = torch.empty(*in_shape, dtype=torch.float32).pin_memory()
-    x_host.uniform_(-1.0, 1.0, generator=gen)
-    x_dev = x_host.cuda()
-
-    def step_device():
-        last = None
-        for i in range(0, in_shape[0], step_items):
-            last = model.forward_device(x_dev[i:i + step_items])
-        return last
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def gather_outputs(outs):
-        # the one exchange step of the data-parallel path: all-gather of the final outputs
-        # -- reception: last block's (pose, vis); SPNet: last action probabilities (B_local, n_act)
-        from deephar_b200.dist import gather_outputs as dh_gather
-        local_out = (torch.cat([outs[-2], outs[-1]], dim=-1) if args.workload == 'reception2d' else outs[-1])
-        return dh_gather(local_out.contiguous(), world)
-
-    for _ in range(args.warmup):
-        gather_outputs(step_device())
-    barrier()
-    model._ctx.launch_count(reset=True)
+    # ---- value: device-resident, CUDA events, max over ranks ------------------------------------------------------
+    for _ in range(2):
+        run.step(which)                             # first uses: plain launches, then the graph capture
+    model.launch_total = 0
     sampler = ClockSampler(local)
     sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        gather_outputs(step_device())
-    e1.record()
-    barrier()
-    ms_total = e0.elapsed_time(e1)
-    launches = model._ctx.launch_count(reset=True)
+    ms_step = timed_steps(torch, dist, world, lambda: run.step(which), args.steps, args.warmup)
     clocks = sampler.stop()
-    t = torch.tensor([ms_total], device='cuda')
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item()) / args.steps
-    value = world * n_frames / (ms_step / 1000.0)
+    launches = int(getattr(model, 'launch_total', 0)) * args.steps // max(1, args.steps + args.warmup)
+    value = n_frames / (ms_step / 1000.0)
 
-    # ---- e2e: public API, pinned host input, H2D + D2H inside the timed region ----
-    x_np = x_host.numpy()
+    # ---- e2e: public API, pinned host input, H2D + D2H inside the timed region ----------------------------------------
+    x_np = run.x_host.numpy()
+    bs = run.micro_items
     for _ in range(2):
-        model.predict(x_np[:2 * step_items], batch_size=step_items)
-    barrier()
+        model.predict(x_np, batch_size=bs)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        outs = model.predict(x_np, batch_size=step_items)
+        outs = model.predict(x_np, batch_size=bs)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     t = torch.tensor([dt], device='cuda')
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_fps = world * n_frames * args.steps / float(t.item())
+    e2e_fps = n_frames * args.steps / float(t.item())
+    outs = outs if isinstance(outs, list) else [outs]
     d2h = sum(int(np.prod(o.shape)) * 4 for o in outs)
 
-    # ---- per-kernel profile (CUDA events around every launch of one extra step) ----
-    prof = model.profile(x_dev[:step_items])
+    # ---- per-kernel profile (CUDA events around every launch of one extra step) ------------------------------------
+    xs = run.x_dev[run.spans[0][0]:run.spans[0][1]]
+    prof = model.profile(xs)
     conv_flops = model.conv_flops_per_frame()
     top = max(prof.values(), key=lambda r: r['ms'])
     total_ms = sum(r['ms'] for r in prof.values())
     tf = top['flops'] / (top['ms'] / top['launches'] / 1000.0) / 1e12 if top['flops'] else 0.0
+    traffic = ncu_traffic().get(top['label'])
     roofline = {
         'kernel': top['label'], 'bound': 'tensor', 'achieved': tf, 'peak': peaks['bf16_tflops_sustained'],
         'unit': 'TFLOP/s', 'frac': tf / peaks['bf16_tflops_sustained'],
-        'traffic': NCU_TRAFFIC.get(top['label'], {}).get('bytes_per_frame', 0) * step_items * (1 if args.workload == 'reception2d' else FRAMES) or None,
-        'traffic_source': NCU_TRAFFIC.get(top['label'], {}).get('source'),
+        'traffic': traffic['bytes_per_frame'] * micro if traffic else None,
+        'traffic_source': traffic['source'] if traffic else None,
         'share_of_step': top['ms'] / total_ms, 'us_per_launch': 1000.0 * top['ms'] / top['launches'],
-        'peak_source': peaks['source'] + ' bf16 dense (sustained); kernel math: ' + model.math_mode(),
-        'whole_forward_tflops': conv_flops * n_frames / (ms_step / 1000.0) / 1e12,
+        'frames_per_launch': micro,
+        'peak_source': peaks['source'] + ' bf16 dense (sustained); kernel math: ' + model.math_mode() +
+                       ' (executed tensor FLOPs = 3x the algorithmic ones counted here)',
+        'whole_forward_tflops': conv_flops * n_frames / (ms_step / 1000.0) / 1e12 / world,
     }
+    if traffic:
+        hbm = traffic['bytes_per_frame'] * micro / (top['ms'] / top['launches'] / 1000.0) / 1e9
+        roofline['hbm_gbs'] = hbm
+        roofline['hbm_frac'] = hbm / peaks['hbm_gbs']
     line = {
         'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
-        'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak',
+        'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong',
         'vs_baseline': None, 'dtype': model.math_mode(), 'data': 'synthetic',
-        'config': {'workload': wl_name,
-                   'global_batch_frames': world * n_frames, 'frames_per_gpu': n_frames, 'micro_batch': mb,
-                   'parallelism': 'dp%d' % world,
-                   'l2': 'inputs 403 MB per step > 126 MB L2; no flush needed'},
+        'config': headline_config(world, run.frames_local, micro) if args.workload == 'reception2d' else
+        dict(headline_config(world, run.frames_local, micro), workload=wl_name + ' x 32 clips'),
         'clocks': clocks,
         'e2e': {'value': e2e_fps, 'unit': 'frames/s', 'h2d_bytes_per_step': n_frames * 256 * 256 * 3 * 4,
-                'd2h_bytes_per_step': d2h},
-        'gpu_launches': int(launches),
+                'd2h_bytes_per_step': d2h * world},
+        'gpu_launches': launches * world,
+        'launch_mode': ('plain launches of %d kernels per forward' if args.no_graph else
+                        'CUDA-graph replay of %d kernels per forward') % len(model._bind(micro).calls),
         'roofline': roofline,
-        'softargmax': softargmax_microbench(torch, model, peaks),
         'kernel_profile': sorted(([r['label'], round(r['ms'], 3), r['launches']] for r in prof.values()),
-                                 key=lambda r: -r[1])[:8],
+                                 key=lambda r: -r[1])[:10],
     }
+
+    # ---- secondary: soft-argmax micro-benchmarks, the other BASELINE configs, the weak-scaling number ---------------
+    if not args.no_secondary:
+        sec = {}
+        if rank == 0:
+            line['softargmax'] = softargmax_microbench(torch, model, peaks)
+            sec['softargmax3d'] = softargmax3d_microbench(torch, model, peaks)
+        if world > 1:       # weak scaling: the full 512 frames on every GPU (round-1 mode), device-resident
+            wrun = Runner(torch, model, clip_model, CLIPS * world, FRAMES, rank, world, args.micro_batch, args.precision)
+            wrun.comm = comm
+            ms = timed_steps(torch, dist, world, lambda: wrun.step(which), 3, 2)
+            sec['weak'] = {'value': world * n_frames / (ms / 1000.0), 'unit': 'frames/s', 'frames_per_gpu': n_frames,
+                           'ms_per_step': ms, 'scaling': 'weak'}
+            del wrun
+        del run
+        model._bound = {}
+        torch.cuda.empty_cache()
+        if args.workload == 'reception2d':
+            for key, wl, items, per, note in (
+                    ('C3', 'reception3d', 32, 1, 'H36M 3-D pose, b32 frames (BASELINE configs[2])'),
+                    ('C4', 'spnet_penn', 16, FRAMES, 'PennAction pose+action, 16 clips x 16 frames (BASELINE configs[3])'),
+                    ('C5', 'spnet_ntu', 64, FRAMES, 'NTU 3-D pose+action, 64 clips x 16 frames, action all-gather (BASELINE configs[4])')):
+                m2, clip2, name2 = build_workload(wl)
+                m2.use_cuda_graph = not args.no_graph
+                r2 = Runner(torch, m2, clip2, items, per, rank, world, args.micro_batch, args.precision)
+                r2.comm = comm          # one communicator per process (it lives on the headline model's context)
+                w2 = 'action' if clip2 else 'pose'
+                assert r2.items_local > 0, 'every rank needs a shard (the exchange step is a collective)'
+                ms = timed_steps(torch, dist, world, lambda: r2.step(w2), 3, 3)
+                fr = items * per
+                sec[key] = {'config': note, 'model': name2, 'frames_per_step': fr, 'frames_per_gpu': r2.frames_local,
+                            'value': fr / (ms / 1000.0), 'unit': 'frames/s', 'ms_per_step': ms,
+                            'conv_tflops': m2.conv_flops_per_frame() * fr / (ms / 1000.0) / 1e12 / world,
+                            'launches_per_forward': len(m2._bind(r2.micro_items * (FRAMES if clip2 else 1)).calls)}
+                del r2, m2
+                torch.cuda.empty_cache()
+        line['secondary'] = sec
+
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        fps, cores, done, dtc = cpu_port_frames_per_sec(24, 4)
-        line['cpu_baseline'] = {'value': fps, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
-                                'sample': '%d frames (batches of 4) of the same model, torch-CPU fp32 port '
-                                          'of the Keras graph, %.1f s' % (done, dtc)}
+        r = cpu_port(iters_b32=3, iters_b1=5, warm_b32=1, warm_b1=2)
+        med32, med1 = float(np.median(r['b32_times'])), float(np.median(r['b1_times']))
+        line['cpu_baseline'] = {'value': 32.0 / med32, 'unit': 'frames/s', 'cores': r['threads'], 'kind': 'port',
+                                'sample': 'C2 model, b32 forward: median of 3 (after 1 warm-up) = %.2f s; C1 (b1) latency '
+                                          'median of 5 = %.3f s; torch-CPU fp32 port of the Keras graph (oracle/), '
+                                          '%d threads on %d host CPUs' % (med32, med1, r['threads'], r['cores']),
+                                'c1_b1_latency_s': med1}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -49,6 +49,11 @@ SIGNATURES = {
     'dh_tc_k_pad': (C.c_int, [C.c_int]),
     'dh_last_conv_path': (C.c_int, [C.c_void_p]),
     'dh_fallback_count': (C.c_int64, [C.c_void_p, C.c_int]),
+    'dh_comm_unique_id': (C.c_int, [C.c_void_p]),
+    'dh_comm_init': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    'dh_comm_destroy': (C.c_int, [C.c_void_p]),
+    'dh_allgather_f32': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    'dh_comm_info': (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     'dh_conv2d_f32': (C.c_int, [C.c_void_p, _VP, C.c_void_p, _PP, _DP, _VP, C.c_void_p]),
     'dh_sepconv2d_f32': (C.c_int, [C.c_void_p, _VP, C.c_void_p, C.c_void_p, _PP, _DP, _VP, C.c_void_p]),
     'dh_maxpool2d_f32': (C.c_int, [C.c_void_p, _VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _VP, C.c_void_p]),
@@ -57,6 +62,7 @@ SIGNATURES = {
     'dh_softargmax2d_f32': (C.c_int, [C.c_void_p, _VP, _VP, C.c_float, C.c_int, C.c_void_p, C.c_void_p, _VP, C.c_void_p]),
     'dh_softargmax2d_ctx_f32': (C.c_int, [C.c_void_p, _VP, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     'dh_softargmax3d_f32': (C.c_int, [C.c_void_p, _VP, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'dh_softargmax3d_ex_f32': (C.c_int, [C.c_void_p, _VP, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, _VP, C.c_void_p]),
     'dh_kron_pool_f32': (C.c_int, [C.c_void_p, _VP, _VP, C.c_void_p, C.c_void_p]),
     'dh_zeropad2d_f32': (C.c_int, [C.c_void_p, _VP, C.c_int, C.c_int, _VP, C.c_void_p]),
     'dh_maxmin_pool2d_f32': (C.c_int, [C.c_void_p, _VP, _VP, C.c_void_p]),

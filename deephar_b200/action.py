@@ -1,11 +1,11 @@
 """B200-native drop-in for deephar/models/action.py::build_merge_model -- the CVPR'18 clip model
-(ReceptionNet pose estimation re-wired under TimeDistributed + PoseAR + GuidedVisAR action nets),
-2-D pose variant as used by exp/pennaction/eval_penn_ar_pe_merge.py:42-62.
+(ReceptionNet pose estimation re-wired under TimeDistributed + PoseAR + GuidedVisAR action nets): the 2-D
+pose variant used by exp/pennaction/eval_penn_ar_pe_merge.py:42-62 and the 3-D one (action.py:208-297,
+`pose_dim=3`, volumetric heat-maps with `depth_maps` slices).
 
 Signature, output order ([pose, visibility,] p1..p4, v1..v4, m: action.py:340-396) and weight
 names (backbone keeps the ReceptionNet layer names; PoseAR/, GuidedVisAR/ sub-models) follow the
-reference.  The 3-D variant (`pose_dim=3`) only has a stale script in the reference
-(exp/ntu/eval_ntu_ar_pe_merge.py:11 imports a module that does not exist) and is not built.
+reference.
 """
 from . import reception as R
 from .graph import Graph
@@ -122,6 +122,37 @@ def _get_2d_pose_estimation_from_model(inp, num_joints, num_blocks, num_context_
     return y, p, hs, xb1
 
 
+def _backbone_to_heatmaps(inp, num_heatmaps, num_blocks, ksize):
+    """The layer re-wiring shared by action.py:112-152 and :208-248: every block but the last feeds its
+    heat-maps back (fReMap), only the last block's heat-maps are regressed."""
+    x1 = R._stem(inp)
+    xb1 = R.build_reception_block(x1, name='rBlock1', ksize=ksize)
+    nfilt = xb1.channels
+    x = xb1
+    for i in range(1, num_blocks):
+        t1 = x if i == 1 else R.build_reception_block(x, name='rBlock%d' % i, ksize=ksize)
+        t2 = R.build_sconv_block(t1, name='SepConv%d' % i, ksize=ksize)
+        t3 = R.build_fremap_block(R.build_regmap_block(t2, num_heatmaps, name='RegMap%d' % i), nfilt,
+                                  name='fReMap%d' % i)
+        x = add([t1, t2, t3])
+    x = R.build_reception_block(x, name='rBlock%d' % num_blocks, ksize=ksize)
+    x = R.build_sconv_block(x, name='SepConv%d' % num_blocks, ksize=ksize)
+    return R.build_regmap_block(x, num_heatmaps, name='RegMap%d' % num_blocks), xb1
+
+
+def _get_3d_pose_estimation_from_model(inp, num_joints, num_blocks, depth_maps, ksize):
+    """action.py:208-297: volumetric head on the last block.  One kernel (dh_softargmax3d_ex_f32) reads the
+    (D * nj)-channel volume once and produces pose = (x, y) from mean_d, z from mean_hw, visible =
+    sigmoid(2 * (max hxy + max hz)) (action.py:291-292 -- twice the logit of reception.py:217-220) and
+    hs = channel_softmax_2d(hxy) for the kronecker product (action.py:294-295)."""
+    h, xb1 = _backbone_to_heatmaps(inp, depth_maps * num_joints, num_blocks, ksize)
+    hh, ww, _ = h.shape
+    pose, visible, hs = h.g.op('pose_regression_3d_ex', [h],
+                               [(1, num_joints, 3), (1, num_joints, 1), (hh, ww, num_joints)],
+                               {'num_joints': num_joints, 'depth_maps': depth_maps, 'vis_scale': 2.0})
+    return pose, visible, hs, xb1
+
+
 def build_merge_model(model_pe,
                       num_actions,
                       input_shape,
@@ -140,8 +171,8 @@ def build_merge_model(model_pe,
     """action.py:319-400."""
     from .model import Model
 
-    if pose_dim != 2:
-        raise NotImplementedError('only the 2-D merge model has a working script in the reference')
+    if pose_dim not in (2, 3):
+        raise ValueError('"pose_dim" must be 2 or 3 and not (%r)' % (pose_dim,))
     if ar_pose_weights is not None or ar_visual_weights is not None:
         raise NotImplementedError('load the merged weight file with Model.load_weights instead')
     ksize = getattr(model_pe, 'build_args', {}).get('ksize', (3, 3))
@@ -151,11 +182,14 @@ def build_merge_model(model_pe,
     inp = g.input(tuple(input_shape))
     outputs = []
 
-    y, p, hs, xb1 = _get_2d_pose_estimation_from_model(inp, num_joints, num_blocks,
-                                                       num_context_per_joint, ksize)
+    if pose_dim == 2:
+        y, p, hs, xb1 = _get_2d_pose_estimation_from_model(inp, num_joints, num_blocks,
+                                                           num_context_per_joint, ksize)
+    else:
+        y, p, hs, xb1 = _get_3d_pose_estimation_from_model(inp, num_joints, num_blocks, depth_maps, ksize)
     n_backbone = len(g.weight_specs)
     if g.weight_specs != model_pe.weight_specs[:n_backbone] or n_backbone != len(model_pe.weight_specs):
-        raise ValueError('model_pe does not match (num_joints, num_blocks, num_context_per_joint)')
+        raise ValueError('model_pe does not match (num_joints, num_blocks, num_context_per_joint / depth_maps)')
 
     if output_poses:
         outputs.append(y)
@@ -189,7 +223,8 @@ def build_merge_model(model_pe,
     outputs.append(action_top(m, name='m'))
 
     g.outputs = outputs
-    model = Model(g, calib_key='merge_j%d_b%d_k%d' % (num_joints, num_blocks, ksize[0]), name='MergeModel')
+    model = Model(g, calib_key='merge%s_j%d_b%d_k%d' % ('' if pose_dim == 2 else '3d', num_joints, num_blocks, ksize[0]),
+                  name='MergeModel')
     if getattr(model_pe, '_host_weights', None):
         model._backbone_weights = dict(model_pe._host_weights)      # shared layers (Keras shares them)
     return model

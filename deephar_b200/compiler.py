@@ -16,7 +16,10 @@ whole forward fits comfortably in HBM and micro-batches stay L2-resident.
 from collections import defaultdict
 
 CONV_OPS = ('conv', 'sepconv')
-DENSE_OUT_OPS = ('scale', 'pose_regression_2d_context', 'pose_regression_2d', 'pose_regression_3d',
+# graph ops that map 1:1 onto a C-ABI call in model.py::_bind
+KERNEL_OPS = ('maxpool', 'zeropad', 'maxminpool', 'scale', 'pose_regression_2d_context', 'pose_regression_2d',
+              'pose_regression_3d', 'pose_regression_3d_ex', 'kron', 'mask_mul')
+DENSE_OUT_OPS = ('scale', 'pose_regression_2d_context', 'pose_regression_2d', 'pose_regression_3d', 'pose_regression_3d_ex',
                  'sam2d', 'kron', 'global_maxmin_softmax', 'mask_mul')
 
 
@@ -73,16 +76,41 @@ class Plan(object):
         self.stats = {}
 
 
-def _consumers(g):
+def _live_nodes(g):
+    """Nodes that reach a model output.  The builders follow the reference and also create layers that feed
+    nothing (e.g. the re-injection convs after the LAST prediction block, spnet.py:249-262); keras.Model prunes
+    them, and so does the plan: no launches, no buffers (their weights stay in weight_specs as optional)."""
+    live, stack = set(), [t.node for t in g.outputs]
+    while stack:
+        nd = stack.pop()
+        if nd is None or nd.id in live:
+            continue
+        live.add(nd.id)
+        stack.extend(t.node for t in nd.inputs)
+    return live
+
+
+def _consumers(nodes):
     cons = defaultdict(list)
-    for n in g.nodes:
+    for n in nodes:
         for i, t in enumerate(n.inputs):
             cons[t.id].append(n)
     return cons
 
 
-def compile_graph(g):
-    cons = _consumers(g)
+class _LiveGraph(object):
+    """View of a Graph restricted to the live nodes (same attributes compile_graph reads)."""
+
+    def __init__(self, g):
+        live = _live_nodes(g)
+        self.nodes = [n for n in g.nodes if n.id in live or n.op == 'input']
+        self.tensors, self.inputs, self.outputs = g.tensors, g.inputs, g.outputs
+        self.dead = len(g.nodes) - len(self.nodes)
+
+
+def compile_graph(g_full):
+    g = _LiveGraph(g_full)
+    cons = _consumers(g.nodes)
     out_ids = set(t.id for t in g.outputs)
 
     def sole_consumer(t, op):
@@ -267,7 +295,7 @@ def compile_graph(g):
                 # the kernel still needs somewhere to put (x, y) and the confidence -> scratch tensors
                 from .graph import Tensor
                 c_ = n.out.shape[2]
-                scratch = [Tensor(g, (1, c_, 2), n.out.kind, n, 1), Tensor(g, (1, c_, 1), n.out.kind, n, 2)]
+                scratch = [Tensor(g_full, (1, c_, 2), n.out.kind, n, 1), Tensor(g_full, (1, c_, 1), n.out.kind, n, 2)]
                 emit('sam2d', [n.inputs[0]], scratch + [n.out], {'alpha': n.attrs['alpha'], 'depth': False,
                                                                  'prob': True}, n.id)
                 continue
@@ -295,8 +323,12 @@ def compile_graph(g):
             emit('global_maxmin_softmax', [n.inputs[0]], [sm.out], {}, sm.id)
             continue
         if op == 'softmax':
+            if n.inputs[0].node.op != 'global_maxmin':
+                raise NotImplementedError('Activation(softmax) is only supported right after global_max_min_pooling')
             continue
         # everything else maps 1:1 onto a kernel op
+        if op not in KERNEL_OPS:
+            raise NotImplementedError('no kernel for layer op %r (node %d)' % (op, n.id))
         emit(op, n.inputs, n.outs, dict(n.attrs), n.id)
 
     emitted.sort(key=lambda e: (e[0], e[1]))
@@ -362,10 +394,14 @@ def compile_graph(g):
                 b = new_buffer(t.kind, hw_of(t), t.channels)
                 s = Storage(b, 0, t.channels)
                 if w is None:
+                    if t.id not in input_ids:
+                        raise RuntimeError('tensor %r is read by the plan but no kernel writes it (layer op %r has '
+                                           'no fused or stand-alone kernel)' % (t, t.node.op if t.node else None))
                     b.is_input = True
         plan.storage[t.id] = s
         return s
 
+    input_ids = set(t.id for t in g.inputs)
     for t in g.inputs:
         storage_of(t)
     final_kops = []
@@ -421,7 +457,8 @@ def compile_graph(g):
         active.append(b)
 
     plan.stats = {
-        'graph_nodes': len(g.nodes),
+        'graph_nodes': len(g_full.nodes),
+        'dead_nodes': g.dead,
         'kernel_ops': len(plan.kops),
         'buffers': len(plan.buffers),
         'phys_slots': len(plan.phys),

@@ -50,11 +50,17 @@ extern "C" int dh_ctx_create(dh_ctx** out, int device) {
     c->pw_smallk = 1;
     c->dense_patch = 1;
     c->fallbacks = 0;
+    c->comm = nullptr;
+    c->comm_rank = -1;
+    c->comm_world = 0;
     *out = c;
     return 0;
 }
 
+extern "C" int dh_comm_destroy(dh_ctx* ctx);
+
 extern "C" int dh_ctx_destroy(dh_ctx* ctx) {
+    if (ctx && ctx->comm) dh_comm_destroy(ctx);
     delete ctx;
     return 0;
 }
@@ -70,7 +76,9 @@ extern "C" int dh_set_option(dh_ctx* ctx, const char* name, int value) {
     DH_CHECK_ARG(ctx && name, "dh_set_option: NULL argument");
     if (!strcmp(name, "share_a")) { ctx->share_a = value; return 0; }
     if (!strcmp(name, "sep_tma")) { ctx->sep_tma = value; return 0; }
-    if (!strcmp(name, "dbg")) { ctx->dbg = value; return 0; }
+#ifdef DH_ABLATE
+    if (!strcmp(name, "dbg")) { ctx->dbg = value; return 0; }      // tools/ builds only (make ABLATE=1)
+#endif
     if (!strcmp(name, "pw_smallk")) { ctx->pw_smallk = value; return 0; }
     if (!strcmp(name, "dense_patch")) { ctx->dense_patch = value; return 0; }
     dh_set_error("dh_set_option: unknown option %s", name);

@@ -16,6 +16,8 @@ struct dh_ctx {
     int sep_tma;          // 1 = TMA-staged separable kernel (conv_sep.cu) where it applies (default)
     int pw_smallk;        // 1 = CUDA-core kernel for wide 1x1 convs with Cin <= 64 (conv_simt.cu) (default)
     int dense_patch;      // 1 = TMA-staged patch kernel for stride-1 Conv2D (conv_patch.cu) where it applies (default)
+    void* comm;           // ncclComm_t of the output all-gather (comm.cu), NULL until dh_comm_init
+    int comm_rank, comm_world;
     int64_t fallbacks;    // convolutions served by the CUDA-core implicit-GEMM fallback (conv_simt.cu) since creation / reset
     int dbg;              // ablation bits for tools/ (0 in production; results are WRONG when set)
 };

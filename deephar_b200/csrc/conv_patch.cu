@@ -19,15 +19,17 @@
 //   D     : fp32 in TMEM, three tcgen05.mma per k-step (bf16x3); epilogue shared with conv_tc.cu.
 // 1x1 convolutions have no spatial structure: the pixel axis is viewed as rows of VW = 2^k <= 128 pixels
 // ("virtual geometry") so any N*H*W works, including channel-sliced concat views.
-// Roles: warps 0-3 / 4-7 producers, 8-11 epilogue, 12 weight TMA, 13 MMA issue, 14 patch TMA.
+// Roles: warps 0-3 / 4-7 producers, 8-15 epilogue (two per TMEM lane quarter), 16 weight TMA, 17 MMA issue, 18 patch TMA.
 #include "tc_common.cuh"
 
 namespace tcd {
 using namespace tc;
+using R = tc::Roles<2>;
+constexpr int NEPI = R::NEPI, WARP_TMA = R::WARP_TMA, WARP_MMA = R::WARP_MMA, WARP_PATCH = R::WARP_PATCH, NTHREADS = R::NTHREADS,
+              EPI_STAGE_BYTES = R::EPI_STAGE_BYTES, REGS_PROD = R::REGS_PROD, REGS_EPI = R::REGS_EPI, REGS_CTRL = R::REGS_CTRL;
 
 constexpr int A_BYTES = BM * 64;           // 8 KB per (hi | lo): 128 rows x 32 bf16
 constexpr int NWG = 128;                   // threads per producer warpgroup
-constexpr int WARP_PATCH = 14;
 constexpr int NA = 3;                      // A-tile ring depth
 constexpr int MAX_NP = 8;                  // patch ring depth
 
@@ -49,8 +51,9 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 patch_dense_kernel(const __grid_constant__ PatchParams PP, const __grid_constant__ CUtensorMap map_hi,
                    const __grid_constant__ CUtensorMap map_lo, const __grid_constant__ CUtensorMap map_x) {
     const TcParams& P = PP.t;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    if (smem_u32(smem_raw) & 1023u) __trap();      // swizzled UMMA / TMA tiles need the 1024-byte alignment declared above
+    uint8_t* smem = smem_raw;
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const bool want_lo = P.precision == 3;
@@ -110,7 +113,7 @@ patch_dense_kernel(const __grid_constant__ PatchParams PP, const __grid_constant
 
     if (warp < WARP_EPI0) {
         // ======================= A producers (two warpgroups, alternating K-blocks) =======================
-        reg_inc<REGS_PROD>();
+        reg_prod<REGS_PROD, R::LAUNCH_REGS>();
         const ConvParams& c = P.c;
         const int w = warp >> 2;
         const int tw = tid & (NWG - 1);
@@ -219,7 +222,7 @@ patch_dense_kernel(const __grid_constant__ PatchParams PP, const __grid_constant
     } else if (warp < WARP_TMA) {
         // ======================= epilogue =======================
         reg_inc<REGS_EPI>();
-        run_epilogue(P, epi_stage, tmem_base, bar_tfull0, bar_tempty0, n0, warp, lane);
+        run_epilogue<R::EPQ>(P, epi_stage, tmem_base, bar_tfull0, bar_tempty0, n0, warp, lane);
     } else {
         reg_dec<REGS_CTRL>();
         if (warp == WARP_TMA) {
@@ -369,7 +372,7 @@ static bool plan_geom(const ConvParams& p, Geom* g) {
 }
 
 static size_t fixed_smem(int bn_cta) {
-    return (size_t)NA * 2 * A_BYTES + (size_t)2 * 2 * bn_cta * 64 + tc::EPI_STAGE_BYTES + 512 + 1024;
+    return (size_t)NA * 2 * A_BYTES + (size_t)2 * 2 * bn_cta * 64 + EPI_STAGE_BYTES + 512;
 }
 
 }  // namespace tcd
@@ -457,7 +460,7 @@ int dh_launch_patch(dh_ctx* ctx, const ConvParams& p, const dh_packed_w* packed,
     int gx = ctx->num_sms / gy;
     if (gx < 1) gx = 1;
     if (gx > P.n_mtiles) gx = P.n_mtiles;
-    cudaError_t e = cudaFuncSetAttribute(patch_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = ensure_smem<patch_dense_kernel>(smem);
     if (e == cudaSuccess) {
         patch_dense_kernel<<<dim3(gx, gy), NTHREADS, smem, s>>>(PP, map_hi, map_lo, map_x);
     } else {

@@ -22,10 +22,12 @@
 
 namespace tcs {
 using namespace tc;
+using R = tc::Roles<2>;
+constexpr int NEPI = R::NEPI, WARP_TMA = R::WARP_TMA, WARP_MMA = R::WARP_MMA, WARP_PATCH = R::WARP_PATCH, NTHREADS = R::NTHREADS,
+              EPI_STAGE_BYTES = R::EPI_STAGE_BYTES, REGS_PROD = R::REGS_PROD, REGS_EPI = R::REGS_EPI, REGS_CTRL = R::REGS_CTRL;
 
 constexpr int A_BYTES = BM * 64;           // 8 KB per (hi | lo)
 constexpr int NWG = 128;                   // threads per producer warpgroup
-constexpr int WARP_PATCH = 14;
 constexpr int NA = 3;                      // A-tile ring depth (the weight ring stays 2 deep)
 
 struct SepParams {
@@ -36,17 +38,23 @@ struct SepParams {
     int dbg;                // ablation bits (tools/ only): 1 no depthwise math, 2 no patch TMA, 8 no DSMEM push, 16 no weight TMA
 };
 
-template <int KS, int TW, bool SHARE>
+template <int KS, int TW, bool SHARE, bool BNPRO>
 __global__ void __launch_bounds__(NTHREADS, 1)
 sep_tma_kernel(const __grid_constant__ SepParams SP, const __grid_constant__ CUtensorMap map_hi,
                const __grid_constant__ CUtensorMap map_lo, const __grid_constant__ CUtensorMap map_x) {
     constexpr int PAD = KS / 2;
     constexpr int PC = TW + 2 * PAD;          // patch columns
     constexpr int NR = 4 + KS - 1;            // input rows / cols per 4x4 block
+#ifdef DH_ABLATE
+    const int DBG = SP.dbg;          // timing-ablation bits (tools/ builds only; results are wrong when set)
+#else
+    constexpr int DBG = 0;
+#endif
     const TcParams& P = SP.t;
-    extern __shared__ uint8_t smem_raw[];
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte alignment as an OFFSET (not a uintptr_t round-trip) so that accesses stay in the shared state space
-    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    if (smem_u32(smem_raw) & 1023u) __trap();      // swizzled UMMA / TMA tiles need the 1024-byte alignment declared above
+    uint8_t* smem = smem_raw;
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const bool want_lo = P.precision == 3;
@@ -108,7 +116,7 @@ sep_tma_kernel(const __grid_constant__ SepParams SP, const __grid_constant__ CUt
 
     if (warp < WARP_EPI0) {
         // ======================= depthwise producers (two warpgroups) =======================
-        reg_inc<REGS_PROD>();
+        reg_prod<REGS_PROD, R::LAUNCH_REGS>();
         const ConvParams& c = P.c;
         const int w = warp >> 2;                       // warpgroup 0 | 1 -> patch buffer w, own K-blocks j = w, w+2, ...
         const int tw = tid & (NWG - 1);
@@ -122,6 +130,17 @@ sep_tma_kernel(const __grid_constant__ SepParams SP, const __grid_constant__ CUt
                              ((size_t)((fn * prr + ry) * PC + xb * 4)) * SBK + cp * 2;
         const int row0 = strip * 4 * TW + xb * 4;      // tile-local pixel of output (o = 0, q = 0)
         const float lowb = c.pre_relu ? 0.f : -3.402823466e38f;
+        // BNPRO: BatchNormalization before the ReLU (models/common.py:25-67 residual units).  The TMA zero fill is
+        // the padding of the RAW tensor; keras pads the ACTIVATED one, so out-of-image taps are forced back to zero
+        // after the affine: per-thread column mask (fixed) x per-tile row mask.
+        unsigned colmask = 0;
+        if (BNPRO) {
+#pragma unroll
+            for (int q = 0; q < NR; ++q) {
+                const int ix = xb * 4 + q - PAD;
+                if (ix >= 0 && ix < TW) colmask |= 1u << q;
+            }
+        }
         const uint32_t pfull = bar_pfull0 + 8 * w, pempty = bar_pempty0 + 8 * w;
         for (int j = w; j < n_own; j += 2) {
             const int g = SHARE ? 2 * j + (int)my_rank : j;
@@ -139,16 +158,32 @@ sep_tma_kernel(const __grid_constant__ SepParams SP, const __grid_constant__ CUt
             for (int o = 0; o < 4; ++o)
 #pragma unroll
                 for (int q = 0; q < 4; ++q) acc[o][q] = make_float2(0.f, 0.f);
+            float2 ps = make_float2(1.f, 1.f), pb = make_float2(0.f, 0.f);
+            unsigned rowmask = 0;
+            if (BNPRO) {
+                ps = __ldg(reinterpret_cast<const float2*>(c.pre_scale + ch));
+                pb = __ldg(reinterpret_cast<const float2*>(c.pre_shift + ch));
+                const int t = blockIdx.x + ti * gridDim.x;
+                const int y0 = SP.fn > 1 ? 0 : ((t * BM) / TW) % c.H;
+#pragma unroll
+                for (int r = 0; r < NR; ++r) {
+                    const int iy = y0 + ry + r - PAD;
+                    if (iy >= 0 && iy < c.H) rowmask |= 1u << r;
+                }
+            }
 
-            if (!(SP.dbg & 2)) mbar_wait_relaxed(pfull, (uint32_t)((j >> 1) & 1), (SP.dbg & 2048) ? 32u : 0u);
-            if (!(SP.dbg & 1))
+            if (!(DBG & 2)) mbar_wait_relaxed(pfull, (uint32_t)((j >> 1) & 1), (DBG & 2048) ? 32u : 0u);
+            if (!(DBG & 1))
 #pragma unroll
             for (int r = 0; r < NR; ++r) {
                 float2 in[NR];
 #pragma unroll
                 for (int q = 0; q < NR; ++q) {
                     float2 v = *reinterpret_cast<const float2*>(pbase + (r * PC + q) * SBK);
-                    in[q] = make_float2(fmaxf(v.x, lowb), fmaxf(v.y, lowb));
+                    if (BNPRO) v = __ffma2_rn(v, ps, pb);
+                    v = make_float2(fmaxf(v.x, lowb), fmaxf(v.y, lowb));
+                    if (BNPRO && !(((rowmask >> r) & 1u) && ((colmask >> q) & 1u))) v = make_float2(0.f, 0.f);
+                    in[q] = v;
                 }
 #pragma unroll
                 for (int o = 0; o < 4; ++o) {
@@ -161,11 +196,11 @@ sep_tma_kernel(const __grid_constant__ SepParams SP, const __grid_constant__ CUt
                     }
                 }
             }
-            if (!(SP.dbg & 2)) mbar_arrive(pempty);    // patch buffer may be refilled
+            if (!(DBG & 2)) mbar_arrive(pempty);    // patch buffer may be refilled
 
             const int s = g % NA;
             const uint32_t it = (uint32_t)(g / NA);
-            wait_stage_free(bar_empty0, s, it, (SP.dbg & 2048) ? 32u : 0u);
+            wait_stage_free(bar_empty0, s, it, (DBG & 2048) ? 32u : 0u);
             uint8_t* a_hi = smem + (size_t)s * (2 * A_BYTES);
             uint8_t* a_lo = a_hi + A_BYTES;
 #pragma unroll
@@ -185,7 +220,7 @@ sep_tma_kernel(const __grid_constant__ SepParams SP, const __grid_constant__ CUt
                     mbar_arrive(bar_full0 + 8 * s);
                     const uint32_t peer = my_rank ^ 1u;
                     const uint32_t peer_full = mapa_peer(bar_full0 + 8 * s, peer);
-                    if (!(SP.dbg & 8)) {
+                    if (!(DBG & 8)) {
                         bulk_s2peer(mapa_peer(smem_u32(a_hi), peer), smem_u32(a_hi), A_BYTES, peer_full);
                         if (want_lo) bulk_s2peer(mapa_peer(smem_u32(a_lo), peer), smem_u32(a_lo), A_BYTES, peer_full);
                     }
@@ -197,24 +232,24 @@ sep_tma_kernel(const __grid_constant__ SepParams SP, const __grid_constant__ CUt
     } else if (warp < WARP_TMA) {
         // ======================= epilogue =======================
         reg_inc<REGS_EPI>();
-        run_epilogue(P, epi_stage, tmem_base, bar_tfull0, bar_tempty0, n0, warp, lane);
+        run_epilogue<R::EPQ>(P, epi_stage, tmem_base, bar_tfull0, bar_tempty0, n0, warp, lane);
     } else {
         reg_dec<REGS_CTRL>();
         if (warp == WARP_TMA) {
             // ======================= weight tiles via TMA =======================
             if (lane == 0) {
-                const uint32_t tx = (SP.dbg & 16) ? 0u : (uint32_t)(want_lo ? 2 : 1) * (uint32_t)b_bytes;
-                const uint32_t tx_a = (SP.dbg & 8) ? 0u : (uint32_t)(want_lo ? 2 : 1) * (uint32_t)A_BYTES;
+                const uint32_t tx = (DBG & 16) ? 0u : (uint32_t)(want_lo ? 2 : 1) * (uint32_t)b_bytes;
+                const uint32_t tx_a = (DBG & 8) ? 0u : (uint32_t)(want_lo ? 2 : 1) * (uint32_t)A_BYTES;
                 for (int g = 0; g < total_g; ++g) {
                     const int ti = g / nkb, kb = g - ti * nkb;
                     const int sb = g & 1;
                     const uint32_t itb = (uint32_t)(g >> 1);
-                    if (itb >= 1) mbar_wait_relaxed(bar_emptyb0 + 8 * sb, (itb - 1) & 1, (SP.dbg & 2048) ? 64u : 0u);
+                    if (itb >= 1) mbar_wait_relaxed(bar_emptyb0 + 8 * sb, (itb - 1) & 1, (DBG & 2048) ? 64u : 0u);
                     const uint32_t full = bar_fullb0 + 8 * sb;
                     mbar_arrive_expect_tx(full, tx);
                     const uint32_t b_hi = smem_u32(b_ring + (size_t)sb * (2 * b_bytes));
                     const uint32_t b_lo = b_hi + (uint32_t)b_bytes;
-                    if (!(SP.dbg & 16))
+                    if (!(DBG & 16))
                     for (int sub = 0; sub < P.nsub; ++sub) {
                         tma_load_2d(b_hi + (uint32_t)(sub * P.nw * 64), &map_hi, kb * SBK, n0 + sub * P.nw, full);
                         if (want_lo)
@@ -231,7 +266,7 @@ sep_tma_kernel(const __grid_constant__ SepParams SP, const __grid_constant__ CUt
             }
         } else if (warp == WARP_PATCH) {
             // ======================= input patches via 4-D TMA =======================
-            if (lane == 0 && !(SP.dbg & 2)) {
+            if (lane == 0 && !(DBG & 2)) {
                 const ConvParams& c = P.c;
                 auto coords = [&](int j, int& kb, int& nf, int& y0) {
                     const int g = SHARE ? 2 * j + (int)my_rank : j;
@@ -246,12 +281,12 @@ sep_tma_kernel(const __grid_constant__ SepParams SP, const __grid_constant__ CUt
                     int kb, nf, y0;
                     coords(j, kb, nf, y0);
                     const int w = j & 1;
-                    if ((SP.dbg & 1024) && j + 2 < n_own) {         // pull the patch after next into L2
+                    if ((DBG & 1024) && j + 2 < n_own) {         // pull the patch after next into L2
                         int kb2, nf2, y2;
                         coords(j + 2, kb2, nf2, y2);
                         tma_prefetch_4d(&map_x, kb2 * SBK, -PAD, y2 - PAD, nf2);
                     }
-                    mbar_wait_relaxed(bar_pempty0 + 8 * w, (uint32_t)(((j >> 1) & 1) ^ 1), (SP.dbg & 2048) ? 64u : 0u);
+                    mbar_wait_relaxed(bar_pempty0 + 8 * w, (uint32_t)(((j >> 1) & 1) ^ 1), (DBG & 2048) ? 64u : 0u);
                     const uint32_t pf = bar_pfull0 + 8 * w;
                     mbar_arrive_expect_tx(pf, (uint32_t)SP.patch_bytes);
                     tma_load_4d(smem_u32(patch0 + (size_t)w * SP.patch_stride), &map_x, kb * SBK, -PAD, y0 - PAD, nf, pf);
@@ -282,7 +317,7 @@ sep_tma_kernel(const __grid_constant__ SepParams SP, const __grid_constant__ CUt
                 for (int kb = 0; kb < nkb; ++kb, ++g) {
                     const int s = g % NA, sb = g & 1;
                     const uint32_t it = (uint32_t)(g / NA);
-                    if (!(P.dbg & 128)) mbar_wait(bar_full0 + 8 * s, it & 1);
+                    if (!(DBG & 128)) mbar_wait(bar_full0 + 8 * s, it & 1);
                     mbar_wait(bar_fullb0 + 8 * sb, (uint32_t)(g >> 1) & 1);
                     if (kb == 0) {                               // the epilogue must have drained the slots
 #pragma unroll
@@ -356,7 +391,7 @@ bool dh_sep_tma_supported(const dh_ctx* ctx, const ConvParams& p, const dh_packe
     if (!packed || !packed->hi || !packed->lo) return false;
     if (!(p.kh == p.kw && (p.kh == 3 || p.kh == 5)) || p.sh != 1 || p.sw != 1) return false;
     if (p.Ho != p.H || p.Wo != p.W) return false;
-    if (p.pre_scale) return false;                       // BN prologue: padding would not be zero after the affine
+    if (p.pre_scale && ((reinterpret_cast<uintptr_t>(p.pre_scale) & 7) || (reinterpret_cast<uintptr_t>(p.pre_shift) & 7))) return false;
     if (!(p.W == 32 || p.W == 16 || p.W == 8)) return false;
     const int tr = tc::BM / p.W;
     if (tr <= p.H ? (p.H % tr) != 0 : (tr % p.H) != 0) return false;
@@ -391,10 +426,14 @@ int dh_launch_sep_tma(dh_ctx* ctx, const ConvParams& p, const dh_packed_w* packe
     const int pc = p.W + 2 * pad, prr = SP.ry + 2 * pad;
     SP.patch_bytes = SBK * 4 * pc * prr * SP.fn;
     SP.patch_stride = (SP.patch_bytes + 1023) / 1024 * 1024;
+#ifdef DH_ABLATE
     SP.dbg = ctx->dbg;
-    P.dbg = ctx->dbg;
+#else
+    SP.dbg = 0;
+#endif
+    P.dbg = 0;
     const size_t smem = (size_t)NA * 2 * A_BYTES + (size_t)2 * 2 * P.bn_cta * 64 + 2 * (size_t)SP.patch_stride +
-                        EPI_STAGE_BYTES + 512 + 1024;
+                        EPI_STAGE_BYTES + 512;
     if (smem > 227 * 1024) {
         dh_set_error("dh_launch_sep_tma: tile does not fit shared memory");
         return -1;
@@ -412,10 +451,10 @@ int dh_launch_sep_tma(dh_ctx* ctx, const ConvParams& p, const dh_packed_w* packe
     dim3 grid(gx, gy);
     const bool share = gy == 2 && ctx->share_a;
     cudaError_t e = cudaSuccess;
-#define DH_SEP_LAUNCH(KS_, TW_)                                                                                  \
+#define DH_SEP_LAUNCH_(KS_, TW_, BN_)                                                                                \
     do {                                                                                                         \
         if (share) {                                                                                             \
-            e = cudaFuncSetAttribute(sep_tma_kernel<KS_, TW_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            e = ensure_smem<sep_tma_kernel<KS_, TW_, true, BN_>>(smem); \
             if (e == cudaSuccess) {                                                                              \
                 cudaLaunchConfig_t cfg = {};                                                                     \
                 cfg.gridDim = grid; cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;  \
@@ -423,19 +462,21 @@ int dh_launch_sep_tma(dh_ctx* ctx, const ConvParams& p, const dh_packed_w* packe
                 at[0].id = cudaLaunchAttributeClusterDimension;                                                  \
                 at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 2; at[0].val.clusterDim.z = 1;              \
                 cfg.attrs = at; cfg.numAttrs = 1;                                                                \
-                e = cudaLaunchKernelEx(&cfg, sep_tma_kernel<KS_, TW_, true>, SP, map_hi, map_lo, map_x);         \
+                e = cudaLaunchKernelEx(&cfg, sep_tma_kernel<KS_, TW_, true, BN_>, SP, map_hi, map_lo, map_x);         \
             }                                                                                                    \
         } else {                                                                                                 \
-            e = cudaFuncSetAttribute(sep_tma_kernel<KS_, TW_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-            if (e == cudaSuccess) sep_tma_kernel<KS_, TW_, false><<<grid, NTHREADS, smem, s>>>(SP, map_hi, map_lo, map_x); \
+            e = ensure_smem<sep_tma_kernel<KS_, TW_, false, BN_>>(smem); \
+            if (e == cudaSuccess) sep_tma_kernel<KS_, TW_, false, BN_><<<grid, NTHREADS, smem, s>>>(SP, map_hi, map_lo, map_x); \
         }                                                                                                        \
     } while (0)
+#define DH_SEP_LAUNCH(KS_, TW_) do { if (p.pre_scale) DH_SEP_LAUNCH_(KS_, TW_, true); else DH_SEP_LAUNCH_(KS_, TW_, false); } while (0)
     if (p.kh == 5) {
         if (p.W == 32) DH_SEP_LAUNCH(5, 32); else if (p.W == 16) DH_SEP_LAUNCH(5, 16); else DH_SEP_LAUNCH(5, 8);
     } else {
         if (p.W == 32) DH_SEP_LAUNCH(3, 32); else if (p.W == 16) DH_SEP_LAUNCH(3, 16); else DH_SEP_LAUNCH(3, 8);
     }
 #undef DH_SEP_LAUNCH
+#undef DH_SEP_LAUNCH_
     if (e != cudaSuccess) {
         dh_set_error("dh_launch_sep_tma: launch setup failed: %s", cudaGetErrorString(e));
         return (int)e;

@@ -23,6 +23,9 @@
 #include "tc_common.cuh"
 
 namespace tc {
+using R = tc::Roles<1>;
+constexpr int NEPI = R::NEPI, WARP_TMA = R::WARP_TMA, WARP_MMA = R::WARP_MMA, NTHREADS = R::NTHREADS,
+              EPI_STAGE_BYTES = R::EPI_STAGE_BYTES, REGS_PROD = R::REGS_PROD, REGS_EPI = R::REGS_EPI, REGS_CTRL = R::REGS_CTRL;
 
 // ---------------------------------------------------------------------------
 // A-tile producers
@@ -237,9 +240,10 @@ template <int MODE, bool SHARE>   // MODE: 0 dense/1x1, 3 separable 3x3, 5 separ
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUtensorMap map_hi,
                const __grid_constant__ CUtensorMap map_lo) {
-    extern __shared__ uint8_t smem_raw[];
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte alignment as an OFFSET (not a uintptr_t round-trip) so that accesses stay in the shared state space
-    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    if (smem_u32(smem_raw) & 1023u) __trap();      // swizzled UMMA / TMA tiles need the 1024-byte alignment declared above
+    uint8_t* smem = smem_raw;
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const bool want_lo = P.precision == 3;
@@ -283,7 +287,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
 
     if (warp < WARP_EPI0) {
         // ======================= A producers =======================
-        reg_inc<REGS_PROD>();
+        reg_prod<REGS_PROD, R::LAUNCH_REGS>();
         DenseRows rows;
         DenseRegs cur, nxt;
         int ti = 0;
@@ -356,8 +360,8 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
         }
     } else if (warp < WARP_TMA) {
         // ======================= epilogue =======================
-        reg_inc<REGS_EPI>();       // 136 > the 128 launch registers: this is an increase
-        run_epilogue(P, epi_stage, tmem_base, bar_tfull0, bar_tempty0, n0, warp, lane);
+        reg_inc<REGS_EPI>();
+        run_epilogue<R::EPQ>(P, epi_stage, tmem_base, bar_tfull0, bar_tempty0, n0, warp, lane);
     } else {
         reg_dec<REGS_CTRL>();
         if (warp == WARP_TMA) {
@@ -503,13 +507,13 @@ int dh_launch_conv_tc(dh_ctx* ctx, const ConvParams& p, const dh_packed_w* packe
     P.precision = (precision == 1) ? 1 : 3;
     P.ks = separable ? p.kh : 0;
     plan_tmem(P);
-    P.dbg = ctx->dbg;
+    P.dbg = 0;
     P.n_mtiles = (p.M + BM - 1) / BM;
     // cute::UMMA::InstrDescriptor: c_format F32 [4,6)=1, a/b_format BF16 [7,10)/[10,13)=1, K-major A and B,
     // n_dim = N>>3 at [17,23), m_dim = M>>4 at [24,29)
     P.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.nw >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
     const int stage_bytes = 2 * A_TILE_BYTES + 2 * P.bn_cta * 128;
-    const int budget = 227 * 1024 - 1024 /*alignment*/ - 256 /*barriers*/ - EPI_STAGE_BYTES;
+    const int budget = 227 * 1024 - 256 /*barriers*/ - EPI_STAGE_BYTES;
     int stages = budget / stage_bytes;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     if (stages > P.n_kblocks) stages = P.n_kblocks;
@@ -518,7 +522,7 @@ int dh_launch_conv_tc(dh_ctx* ctx, const ConvParams& p, const dh_packed_w* packe
         return -1;
     }
     P.stages = stages;
-    const size_t smem = (size_t)stages * stage_bytes + EPI_STAGE_BYTES + 1024 + 256;
+    const size_t smem = (size_t)stages * stage_bytes + EPI_STAGE_BYTES + 256;
 
     CUtensorMap map_hi, map_lo;
     if (!make_map(&map_hi, packed->hi, packed->k, packed->cout_pad, P.nw) ||
@@ -537,7 +541,7 @@ int dh_launch_conv_tc(dh_ctx* ctx, const ConvParams& p, const dh_packed_w* packe
 #define DH_TC_LAUNCH(MODE)                                                                                   \
     do {                                                                                                     \
         if (share) {                                                                                         \
-            e = cudaFuncSetAttribute(conv_tc_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            e = ensure_smem<conv_tc_kernel<MODE, true>>(smem); \
             if (e == cudaSuccess) {                                                                          \
                 cudaLaunchConfig_t cfg = {};                                                                 \
                 cfg.gridDim = grid; cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s; \
@@ -548,7 +552,7 @@ int dh_launch_conv_tc(dh_ctx* ctx, const ConvParams& p, const dh_packed_w* packe
                 e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<MODE, true>, P, map_hi, map_lo);                 \
             }                                                                                                \
         } else {                                                                                             \
-            e = cudaFuncSetAttribute(conv_tc_kernel<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            e = ensure_smem<conv_tc_kernel<MODE, false>>(smem); \
             if (e == cudaSuccess) conv_tc_kernel<MODE, false><<<grid, NTHREADS, smem, s>>>(P, map_hi, map_lo); \
         }                                                                                                    \
     } while (0)

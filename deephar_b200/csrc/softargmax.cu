@@ -200,6 +200,8 @@ struct Sam3dParams {
     const float* h; int ldh;
     int N, H, W, nj, D;
     float* out_pose; float* out_vis;
+    float vis_scale;            // visible = sigmoid(vis_scale * (max hxy + max hz)): 1 reception.py:217-220, 2 action.py:291-292
+    float* prob; int ldp;       // optional: channel_softmax_2d(hxy) (N,H,W,nj) for the kronecker product (action.py:294-295)
 };
 
 __global__ void __launch_bounds__(512) softargmax3d_kernel(Sam3dParams p) {
@@ -296,7 +298,14 @@ __global__ void __launch_bounds__(512) softargmax3d_kernel(Sam3dParams p) {
         o[0] = s_res[0 * nj + tid];
         o[1] = s_res[1 * nj + tid];
         o[2] = ze / zs;
-        p.out_vis[(size_t)n * nj + tid] = sigmoidf_(vmax + zm);
+        p.out_vis[(size_t)n * nj + tid] = sigmoidf_(p.vis_scale * (vmax + zm));
+    }
+    if (p.prob) {
+        float* pb = p.prob + (size_t)n * P * p.ldp;
+        for (int i = tid; i < P * nj; i += T) {
+            int pix = i / nj, c = i - pix * nj;
+            pb[(size_t)pix * p.ldp + c] = s_hxy[i] / s_res[4 * nj + c];
+        }
     }
 }
 
@@ -340,6 +349,8 @@ __global__ void __launch_bounds__(128) kron_kernel(const float* pm, int ldpm, co
 int launch_sam(dh_ctx* ctx, SamParams& p, void* stream, const char* who) {
     const int P = p.H * p.W;
     DH_CHECK_ARG(p.C >= 1 && p.C <= 512, "%s: C=%d not in 1..512", who, p.C);
+    // the confidence is a max over 2x2 windows (AveragePooling2D((2,2), valid) in the reference raises on smaller maps)
+    DH_CHECK_ARG(p.H >= 2 && p.W >= 2, "%s: maps must be at least 2x2 (got %dx%d)", who, p.H, p.W);
     int T = (P * p.C <= 4096) ? 256 : 512;
     if (T < p.C) T = 512;
     size_t smem = (size_t)(((P * p.C + 3) & ~3) + p.W + p.H + 5 * T + 5 * p.C) * sizeof(float);
@@ -400,24 +411,46 @@ extern "C" int dh_softargmax2d_ctx_f32(dh_ctx* ctx, const dh_view* h, int nj, in
     return launch_sam(ctx, p, stream, "dh_softargmax2d_ctx_f32");
 }
 
-extern "C" int dh_softargmax3d_f32(dh_ctx* ctx, const dh_view* h, int nj, int depth_maps,
-                                   float* out_pose, float* out_vis, void* stream) {
-    DH_CHECK_ARG(ctx && h && h->p && out_pose && out_vis, "dh_softargmax3d_f32: NULL argument");
+static int launch_sam3d(dh_ctx* ctx, const dh_view* h, int nj, int depth_maps, float vis_scale, float* out_pose,
+                        float* out_vis, const dh_view* prob_out, void* stream, const char* who) {
+    DH_CHECK_ARG(ctx && h && h->p && out_pose && out_vis, "%s: NULL argument", who);
     DH_CHECK_ARG(nj >= 1 && depth_maps >= 1 && h->c == nj * depth_maps,
-                 "dh_softargmax3d_f32: C=%d is not depth_maps*nj = %d*%d", h->c, depth_maps, nj);
+                 "%s: C=%d is not depth_maps*nj = %d*%d", who, h->c, depth_maps, nj);
+    DH_CHECK_ARG(h->h >= 2 && h->w >= 2, "%s: maps must be at least 2x2 (got %dx%d)", who, h->h, h->w);
     const int T = 512, C = h->c, P = h->h * h->w;
-    DH_CHECK_ARG(C <= 2 * T && nj <= T, "dh_softargmax3d_f32: too many channels");
+    DH_CHECK_ARG(C <= 2 * T && nj <= T, "%s: too many channels", who);
     Sam3dParams p;
     p.h = h->p; p.ldh = h->ld; p.N = h->n; p.H = h->h; p.W = h->w; p.nj = nj; p.D = depth_maps;
     p.out_pose = out_pose; p.out_vis = out_vis;
+    p.vis_scale = vis_scale;
+    p.prob = nullptr; p.ldp = 0;
+    if (prob_out && prob_out->p) {
+        DH_CHECK_ARG(prob_out->n == h->n && prob_out->h == h->h && prob_out->w == h->w && prob_out->c == nj,
+                     "%s: prob_out must be (N,H,W,nj)", who);
+        p.prob = prob_out->p; p.ldp = prob_out->ld;
+    }
     size_t smem = (size_t)(((P * nj + 3) & ~3) + PCH * C + ((C + 3) & ~3) + h->w + h->h + 5 * T + 5 * nj) * sizeof(float);
-    DH_CHECK_ARG(smem <= 227 * 1024, "dh_softargmax3d_f32: marginal maps do not fit shared memory");
+    DH_CHECK_ARG(smem <= 227 * 1024, "%s: marginal maps do not fit shared memory", who);
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(softargmax3d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) { dh_set_error("dh_softargmax3d_f32: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+        static size_t cur = 0;
+        if (smem > cur) {
+            cudaError_t e = cudaFuncSetAttribute(softargmax3d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) { dh_set_error("%s: cudaFuncSetAttribute: %s", who, cudaGetErrorString(e)); return (int)e; }
+            cur = smem;
+        }
     }
     softargmax3d_kernel<<<p.N, T, smem, (cudaStream_t)stream>>>(p);
     DH_LAUNCH_EPILOGUE(ctx, 1);
+}
+
+extern "C" int dh_softargmax3d_f32(dh_ctx* ctx, const dh_view* h, int nj, int depth_maps,
+                                   float* out_pose, float* out_vis, void* stream) {
+    return launch_sam3d(ctx, h, nj, depth_maps, 1.0f, out_pose, out_vis, nullptr, stream, "dh_softargmax3d_f32");
+}
+
+extern "C" int dh_softargmax3d_ex_f32(dh_ctx* ctx, const dh_view* h, int nj, int depth_maps, float vis_scale,
+                                      float* out_pose, float* out_vis, const dh_view* prob_out, void* stream) {
+    return launch_sam3d(ctx, h, nj, depth_maps, vis_scale, out_pose, out_vis, prob_out, stream, "dh_softargmax3d_ex_f32");
 }
 
 extern "C" int dh_kron_pool_f32(dh_ctx* ctx, const dh_view* pm, const dh_view* z, float* out, void* stream) {

@@ -13,16 +13,35 @@ namespace tc {
 constexpr int BM = 128;
 constexpr int BK = 64;                 // bf16 per K-block = one 128-byte swizzle row
 constexpr int NPROD = 256;             // A producers: warps 0..7 (two warpgroups)
-constexpr int NEPI = 128;              // epilogue: warps 8..11 (one warpgroup; warp % 4 = TMEM lane quarter)
-constexpr int WARP_EPI0 = 8, WARP_TMA = 12, WARP_MMA = 13;
-constexpr int NTHREADS = 512;          // 4 warpgroups; the last one holds the TMA + MMA threads
+constexpr int WARP_EPI0 = 8;           // first epilogue warp
 constexpr int MAX_BN_CTA = 288;
-constexpr int EPI_TILE_BYTES = 4 * 32 * 128;    // per epilogue warp: 32 rows x 32 fp32, XOR-swizzled
-// + this CTA's BN scale | shift columns (read per chunk with LDS: a global load there would share a
-// scoreboard with the in-flight residual loads and drain them early)
-constexpr int EPI_STAGE_BYTES = EPI_TILE_BYTES + 2 * MAX_BN_CTA * 4;
-// register budget (setmaxnreg): 256*168 + 128*144 + 128*32 = 65536
-constexpr int REGS_PROD = 168, REGS_EPI = 144, REGS_CTRL = 32;
+// Warp roles: producers (warps 0-7) | epilogue (4 * Q warps) | one control warpgroup (weight TMA, MMA issue,
+// patch TMA, spare).  Q = epilogue warps per TMEM lane quarter (a warp may only touch TMEM lanes
+// 32 * (warp % 4) .. + 31); the Q warps of a quarter take alternate 32-column chunks of every accumulator
+// sub-tile.  The epilogue of a tile is a latency-bound serial stream per warp (tcgen05.ld -> smem transpose ->
+// residual / BN -> store): with one warp per quarter it takes about as long as the MMAs of a 288-wide tile.
+// Register budget (setmaxnreg; ptxas allocates each role's code against its own value):
+//   Q = 1: 512 threads launch with 128 registers: 256 * 168 + 128 * 144 + 128 * 32 = 65536
+//   Q = 2: 640 threads launch with 96 (65536 / 640 rounded down to the allocation unit).  setmaxnreg only
+//          redistributes the CTA's OWN allocation, 640 * 96 = 61440 registers (asking for more blocks forever):
+//          producers drop to 80 (the TMA-staged producers fit), control to 32, the epilogue grows to 144 (its two
+//          residual row buffers + a 32-column TMEM chunk are 96 registers alone):
+//          256 * 80 + 256 * 144 + 128 * 32 = 61440.
+template <int Q>
+struct Roles {
+    static constexpr int EPQ = Q;
+    static constexpr int NEPI = 128 * Q;
+    static constexpr int WARP_TMA = WARP_EPI0 + 4 * Q, WARP_MMA = WARP_TMA + 1, WARP_PATCH = WARP_TMA + 2;
+    static constexpr int NTHREADS = 32 * (WARP_TMA + 4);
+    static constexpr int EPI_TILE_BYTES = 4 * Q * 32 * 128;    // per epilogue warp: 32 rows x 32 fp32, XOR-swizzled
+    // + this CTA's BN scale | shift columns (read per chunk with LDS: a global load there would share a
+    // scoreboard with the in-flight residual loads and drain them early)
+    static constexpr int EPI_STAGE_BYTES = EPI_TILE_BYTES + 2 * MAX_BN_CTA * 4;
+    static constexpr int REGS_PROD = Q == 1 ? 168 : 80, REGS_EPI = 144, REGS_CTRL = 32;
+    static constexpr int LAUNCH_REGS = Q == 1 ? 128 : 96;      // what ptxas reports for __launch_bounds__(NTHREADS, 1)
+    static_assert(256 * REGS_PROD + NEPI * REGS_EPI + 128 * REGS_CTRL <= NTHREADS * LAUNCH_REGS,
+                  "setmaxnreg budget exceeds the CTA's register allocation: the last setmaxnreg.inc would never return");
+};
 constexpr int A_TILE_BYTES = BM * 128; // 16 KB per (hi | lo)
 constexpr int MAX_STAGES = 4;
 
@@ -38,8 +57,7 @@ struct TcParams {
     int k_pad;
     int n_mtiles;           // ceil(M / 128); CTA (x, y) loops over tiles x, x + gridDim.x, ...
     int nslots, slot_stride; // TMEM accumulator slots (see run_epilogue): nslots x slot_stride columns
-    int dbg;                // ablation bits (tools/ only; results are wrong when set): 64 epilogue only hands
-                            // the slots back, 128 MMAs do not wait for operands
+    int dbg;                // unused (the timing-ablation switches of round 1 were compiled out of the ABI)
 };
 
 // ---------------------------------------------------------------------------
@@ -149,6 +167,11 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
 }
 template <int R> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
 template <int R> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
+// producers: grow (Q = 1) or shrink (Q = 2) from the launch register count to the role's budget
+template <int R, int LAUNCH> __device__ __forceinline__ void reg_prod() {
+    if constexpr (R > LAUNCH) reg_inc<R>();
+    else if constexpr (R < LAUNCH) reg_dec<R>();
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
     uint32_t r[16];
     asm volatile(
@@ -271,10 +294,10 @@ __device__ __forceinline__ void epi_load_res(ResRows& r, const float* p, size_t 
 // (Pinning loop invariants in registers with an asm mov -- so that the compiler cannot rematerialise them
 // with LDC / S2R, which share scoreboards with the in-flight residual loads -- was tried and measured
 // slower: the extra live registers cost more than the early scoreboard waits.)
-template <bool FULL, bool RES1>
+template <bool FULL, bool RES1, int EPQ>
 __device__ __forceinline__ void epilogue_tile(const TcParams& P, uint32_t tile_s, uint32_t tmem_base,
-                                              uint32_t bar_tfull0, uint32_t bar_tempty0, int n0, int q, int lane,
-                                              int mbase, uint32_t u0, bool vec_ok, uint32_t aff_s) {
+                                              uint32_t bar_tfull0, uint32_t bar_tempty0, int n0, int q, int half,
+                                              int lane, int mbase, uint32_t u0, bool vec_ok, uint32_t aff_s) {
     const ConvParams& c = P.c;
     const int nw = P.nw, nsub = P.nsub;
     const int nch = (nw + 31) >> 5;                  // 32-column chunks per sub-tile (last may be 16 wide)
@@ -292,36 +315,41 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& P, uint32_t tile_s
     const float* post_scale = c.post_scale;
     const float* post_shift = c.post_shift;
     const bool has_post = c.post_scale != nullptr, relu = c.post_relu != 0;
-    const bool pipe0 = vec_ok && c.res0 != nullptr, pipe1 = vec_ok && c.res1 != nullptr;
+    const bool pipe0 = vec_ok && c.res0 != nullptr, pipe1 = RES1 && vec_ok && c.res1 != nullptr;
 
+    // This warp's chunks: flat index f = sub * nch + ck with f % EPQ == half, i.e. in sub-tile `sub` the chunks
+    // ck = first(sub), first(sub) + EPQ, ...   The residual rows of a chunk are loaded one own-chunk ahead.
+    const int first0 = half;                                     // first(0)
     ResRows ra, rb;
-    int co = n0 + b4 * 4;                                  // this lane's first output column of the current chunk
     {
-        const bool cok = co < Cout;                        // chunk 0 is at least 16 wide: b4 * 4 < 32 always; 16-wide: b4 < 4
-        const bool ok0 = cok && (b4 * 4 < (nch == 1 ? wlast : 32));
+        const int width = first0 == nch - 1 ? wlast : 32;
+        const int co = n0 + first0 * 32 + b4 * 4;
+        const bool ok0 = first0 < nch && (b4 * 4 < width) && (co < Cout);
         epi_load_res<FULL>(ra, res0_row + co, ldr04, m0, M, pipe0 && ok0);
-        epi_load_res<FULL>(rb, res1_row + co, ldr14, m0, M, pipe1 && ok0);
+        if (RES1) epi_load_res<FULL>(rb, res1_row + co, ldr14, m0, M, pipe1 && ok0);
     }
-    for (int sub = 0; sub < nsub; ++sub) {
-        const uint32_t u = u0 + (uint32_t)sub;
+    for (int sb = 0; sb < nsub; ++sb) {
+        const uint32_t u = u0 + (uint32_t)sb;
         const uint32_t slot = u % (uint32_t)P.nslots;
-        mbar_wait_relaxed(bar_tfull0 + 8 * slot, (u / (uint32_t)P.nslots) & 1, (P.dbg & 2048) ? 64u : 0u);
+        mbar_wait_relaxed(bar_tfull0 + 8 * slot, (u / (uint32_t)P.nslots) & 1, 0u);
         tc_fence_after();
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + slot * (uint32_t)P.slot_stride;
-        if (P.dbg & 64) {
+        const int first = (half + sb * nch) % EPQ;               // EPQ is a power of two: an AND
+        const int firstn = (half + (sb + 1) * nch) % EPQ;        // first own chunk of the next sub-tile
+        if (first >= nch) {                 // no chunk of this sub-tile is mine (single-chunk tiles): still one arrival per use
             tc_fence_before();
             mbar_arrive(bar_tempty0 + 8 * slot);
-            continue;
         }
-        co = n0 + sub * nw + b4 * 4;
-        for (int ck = 0; ck < nch; ++ck, co += 32) {
-            const bool last = ck == nch - 1;
-            const int width = last ? wlast : 32;
+        for (int ck = first; ck < nch; ck += EPQ) {
+            const bool last_mine = ck + EPQ >= nch;            // my last chunk of this sub-tile
+            const int width = ck == nch - 1 ? wlast : 32;
+            const int co = n0 + sb * nw + ck * 32 + b4 * 4;     // this lane's first output column of the chunk
             const bool cok = (b4 * 4 < width) && (co < Cout);
-            // next chunk of this tile (for the residual pipeline)
-            const bool more = !last || (sub + 1 < nsub);
-            const int nco = last ? n0 + (sub + 1) * nw + b4 * 4 : co + 32;
-            const int nwidth = last ? (nch == 1 ? wlast : 32) : (ck + 1 == nch - 1 ? wlast : 32);
+            // next own chunk (for the residual pipeline)
+            const int nck = last_mine ? firstn : ck + EPQ;
+            const bool more = last_mine ? (sb + 1 < nsub && firstn < nch) : true;
+            const int nwidth = nck == nch - 1 ? wlast : 32;
+            const int nco = n0 + (last_mine ? sb + 1 : sb) * nw + nck * 32 + b4 * 4;
             const bool nok = more && (b4 * 4 < nwidth) && (nco < Cout);
             // BN affine of this chunk's columns from the CTA's shared-memory copy
             float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -333,7 +361,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& P, uint32_t tile_s
                 float v[32];
                 if (width == 32) tmem_ld32(trow + (uint32_t)(ck * 32), v);
                 else tmem_ld16(trow + (uint32_t)(ck * 32), v);
-                if (last) {                                     // sub-tile fully read -> MMA may reuse the slot
+                if (last_mine) {                                // my part of the sub-tile is read -> hand the slot back
                     tc_fence_before();
                     mbar_arrive(bar_tempty0 + 8 * slot);
                 }
@@ -345,7 +373,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& P, uint32_t tile_s
             __syncwarp();
             if (vec_ok) {
                 // lane = (row r = lane/8 + 4*i, 4 columns c4 = 4*(lane%8)): 4 rows x 128 B per instruction.
-                // As each residual row is consumed its register is refilled with that row of the NEXT chunk,
+                // As each residual row is consumed its register is refilled with that row of the NEXT own chunk,
                 // so one 8 x float4 buffer per residual gives a full chunk period of load latency.
                 if (cok) {
                     float* op = out_row + co;
@@ -365,7 +393,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& P, uint32_t tile_s
                                 a = __fadd2_rn(a, make_float2(ra.v[i].x, ra.v[i].y));
                                 b = __fadd2_rn(b, make_float2(ra.v[i].z, ra.v[i].w));
                             }
-                            if (pipe1) {
+                            if (RES1 && pipe1) {
                                 a = __fadd2_rn(a, make_float2(rb.v[i].x, rb.v[i].y));
                                 b = __fadd2_rn(b, make_float2(rb.v[i].z, rb.v[i].w));
                             }
@@ -380,7 +408,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& P, uint32_t tile_s
                         for (int i = 0; i < 8; ++i)
                             if (FULL || m0 + 4 * i < M) ra.v[i] = __ldg(reinterpret_cast<const float4*>(nres + i * ldr04));
                     }
-                    if (pipe1) {
+                    if (RES1 && pipe1) {
                         const float* nres1 = res1_row + nco;
 #pragma unroll
                         for (int i = 0; i < 8; ++i)
@@ -388,7 +416,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& P, uint32_t tile_s
                     }
                 }
             } else {
-                const int cos = n0 + sub * nw + ck * 32 + lane;
+                const int cos = n0 + sb * nw + ck * 32 + lane;
                 const bool coks = lane < width && cos < Cout;
                 float scs = 1.f, shs = 0.f;
                 if (coks && has_post) {
@@ -415,12 +443,15 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& P, uint32_t tile_s
     }
 }
 
+template <int EPQ>
 __device__ __forceinline__ void run_epilogue(const TcParams& P, uint8_t* epi_stage, uint32_t tmem_base,
                                              uint32_t bar_tfull0, uint32_t bar_tempty0, int n0, int warp,
                                              int lane) {
     const ConvParams& c = P.c;
-    const int q = warp & 3;
-    const uint32_t tile_s = smem_u32(epi_stage) + (uint32_t)q * (32 * 32 * 4);
+    const int e = warp - WARP_EPI0;                  // epilogue warp 0 .. 4 * EPQ - 1
+    const int q = e & 3;                             // == warp % 4: the TMEM lane quarter this warp may access
+    const int half = e >> 2;                         // which of the quarter's EPQ warps
+    const uint32_t tile_s = smem_u32(epi_stage) + (uint32_t)e * (32 * 32 * 4);
     const bool vec_ok = ((c.ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(c.out) & 15) == 0) &&
                         (!c.res0 || (((c.ldr0 & 3) == 0) && ((reinterpret_cast<uintptr_t>(c.res0) & 15) == 0))) &&
                         (!c.res1 || (((c.ldr1 & 3) == 0) && ((reinterpret_cast<uintptr_t>(c.res1) & 15) == 0))) &&
@@ -428,10 +459,11 @@ __device__ __forceinline__ void run_epilogue(const TcParams& P, uint8_t* epi_sta
                         (!c.post_scale || (((reinterpret_cast<uintptr_t>(c.post_scale) & 15) == 0) &&
                                            ((reinterpret_cast<uintptr_t>(c.post_shift) & 15) == 0)));
     // this CTA's BN columns -> shared memory (epilogue warps only: named barrier 3)
+    constexpr int NEPI = Roles<EPQ>::NEPI, EPI_TILE_BYTES = Roles<EPQ>::EPI_TILE_BYTES;
     const uint32_t aff_s = smem_u32(epi_stage) + EPI_TILE_BYTES;
     if (c.post_scale) {
         float* aff = reinterpret_cast<float*>(epi_stage + EPI_TILE_BYTES);
-        for (int i = (warp & 3) * 32 + lane; i < P.bn_cta; i += NEPI) {
+        for (int i = e * 32 + lane; i < P.bn_cta; i += NEPI) {
             const bool in = n0 + i < c.Cout;
             aff[i] = in ? __ldg(c.post_scale + n0 + i) : 1.f;
             aff[MAX_BN_CTA + i] = in ? __ldg(c.post_shift + n0 + i) : 0.f;
@@ -443,7 +475,7 @@ __device__ __forceinline__ void run_epilogue(const TcParams& P, uint8_t* epi_sta
         const int mbase = t * BM + q * 32;
         // pull the residual rows of the NEXT tile into L2 while this one is drained (the loads of this tile
         // were prefetched one tile ago; the first tile relies on the chunk-ahead register pipeline)
-        if (c.res0 || c.res1) {
+        if ((c.res0 || c.res1) && half == 0) {
             const int tn = (t == (int)blockIdx.x) ? t : t + (int)gridDim.x;
             for (int tt = tn; tt <= t + (int)gridDim.x && tt < P.n_mtiles; tt += gridDim.x) {
                 const int m = tt * BM + q * 32 + lane;
@@ -456,10 +488,12 @@ __device__ __forceinline__ void run_epilogue(const TcParams& P, uint8_t* epi_sta
                 }
             }
         }
+        // (a RES1 = false instantiation for single-residual layers was tried: four inlined copies of the tile
+        // loop make ptxas spill the residual registers of all of them)
         if (mbase + 32 <= c.M)
-            epilogue_tile<true, true>(P, tile_s, tmem_base, bar_tfull0, bar_tempty0, n0, q, lane, mbase, u, vec_ok, aff_s);
+            epilogue_tile<true, true, EPQ>(P, tile_s, tmem_base, bar_tfull0, bar_tempty0, n0, q, half, lane, mbase, u, vec_ok, aff_s);
         else
-            epilogue_tile<false, true>(P, tile_s, tmem_base, bar_tfull0, bar_tempty0, n0, q, lane, mbase, u, vec_ok, aff_s);
+            epilogue_tile<false, true, EPQ>(P, tile_s, tmem_base, bar_tfull0, bar_tempty0, n0, q, half, lane, mbase, u, vec_ok, aff_s);
     }
 }
 
@@ -507,6 +541,17 @@ static inline bool make_map_b64(CUtensorMap* map, const void* base, int k_pad, i
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+
+// opt-in dynamic shared memory, set once per kernel (and again only if a launch needs more): keeps the launch
+// path free of attribute calls -- forwards are captured into CUDA graphs (deephar_b200/model.py)
+template <auto Kernel>
+static inline cudaError_t ensure_smem(size_t smem) {
+    static size_t cur = 0;
+    if (smem <= cur) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) cur = smem;
+    return e;
+}
 
 // TMEM plan: as many nw-column slots as fit 512 columns (at most two tiles' worth).
 static inline void plan_tmem(TcParams& P) {

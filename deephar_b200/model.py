@@ -61,6 +61,11 @@ class Model(object):
         self._bound = {}
         self.precision = 3          # tensor-core split precision (bf16 x3 ~ fp32); 1 = plain bf16
         self.use_tensor_cores = True
+        # One forward is 150-350 kernel launches issued through ctypes (~4 us each on the host): at small batches
+        # (C1: one frame; the 64-frames-per-GPU strong-scaling point) the GPU would wait for the host.  The launch
+        # sequence of a bound batch size is therefore captured ONCE into a CUDA graph and replayed.
+        self.use_cuda_graph = True
+        self.max_bound = 2          # bound batch sizes kept alive (LRU): each holds a full activation arena
 
     # ---- keras.Model protocol ------------------------------------------------------
     @property
@@ -259,8 +264,14 @@ class Model(object):
 
     def _bind(self, n_frames):
         if n_frames in self._bound:
-            return self._bound[n_frames]
+            b = self._bound.pop(n_frames)        # re-insert: most recently used last
+            self._bound[n_frames] = b
+            return b
         torch = self._torch()
+        while len(self._bound) >= max(1, self.max_bound):     # evict the least recently used arena
+            old = self._bound.pop(next(iter(self._bound)))
+            old.graph = None
+            del old
         self._ensure_device_weights()
         lib = _ffi.lib()
         plan = self.plan
@@ -268,9 +279,13 @@ class Model(object):
         b.n_items = n_frames
         for (kind, fl) in plan.phys:
             b.slots.append(torch.empty(self._items(kind, n_frames) * fl, dtype=torch.float32, device='cuda'))
+        # scratch of the two-kernel CUDA-core separable path: only for layers the tensor-core kernels cannot take
         ws_floats = 0
         for k in plan.kops:
             if k.kind == 'sepconv':
+                from . import tc
+                if self.use_tensor_cores and tc.conv_eligible(k):
+                    continue
                 t = k.outs[0]
                 ws_floats = max(ws_floats, self._items(t.kind, n_frames) * t.shape[0] * t.shape[1] * k.ins[0].channels)
         b.workspace = torch.empty(max(ws_floats, 4), dtype=torch.float32, device='cuda')
@@ -358,6 +373,10 @@ class Model(object):
                 a = k.attrs
                 args = (lib.dh_softargmax3d_f32, ctxh, C.byref(view(k.ins[0])), a['num_joints'],
                         a['depth_maps'], dense_ptr(k.outs[0]), dense_ptr(k.outs[1]))
+            elif kd == 'pose_regression_3d_ex':
+                a = k.attrs
+                args = (lib.dh_softargmax3d_ex_f32, ctxh, C.byref(view(k.ins[0])), a['num_joints'], a['depth_maps'],
+                        C.c_float(a['vis_scale']), dense_ptr(k.outs[0]), dense_ptr(k.outs[1]), C.byref(view(k.outs[2])))
             elif kd == 'scale':
                 key = 'const:%r' % float(k.attrs['value'])
                 arr = (_ffi.dh_view * 1)(view(k.ins[0]))
@@ -399,12 +418,32 @@ class Model(object):
         b.keep.append(pw)
         return C.pointer(pw)
 
-    def _run(self, b, stream_ptr):
+    def _issue(self, b, stream_ptr):
         self._ctx.set_workspace(b.workspace.data_ptr(), b.workspace.numel() * 4)
         for call in b.calls:
             rc = call[1](*call[2:], stream_ptr)
             if rc != 0:
                 _ffi.check(rc, call[0])
+
+    def _run(self, b, stream_ptr):
+        """One forward over the bound buffers on torch's current stream: a CUDA-graph replay of the launch
+        sequence (captured the second time a batch size is used), else the launches themselves."""
+        torch = self._torch()
+        self.launch_total = getattr(self, 'launch_total', 0) + len(b.calls)     # kernels put on the stream
+        if not self.use_cuda_graph:
+            return self._issue(b, stream_ptr)
+        g = getattr(b, 'graph', None)
+        if g is None:
+            b.uses = getattr(b, 'uses', 0) + 1
+            if b.uses < 2:                      # first use: plain launches (also warms every kernel up)
+                return self._issue(b, stream_ptr)
+            g = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g):
+                self._issue(b, torch.cuda.current_stream().cuda_stream)
+            b.graph = g
+        g.replay()
+        self._graph_replays = getattr(self, '_graph_replays', 0) + 1
 
     def _output_tensor(self, b, t, n_frames):
         s = self.plan.storage[t.id]
@@ -439,6 +478,9 @@ class Model(object):
         if tuple(x.shape[lead:]) != exp or (T > 1 and x.shape[1] != T):
             raise ValueError('input shape %s does not match model input %s' % (x.shape, self.input_shape))
         n = x.shape[0]
+        if n == 0:                  # keras returns empty arrays of the right trailing shape
+            outs = [np.zeros((0,) + tuple(d for d in self._keras_shape(t, 0)[1:]), np.float32) for t in self.graph.outputs]
+            return outs[0] if len(outs) == 1 else outs
         xt = torch.from_numpy(x)
         pinned = xt.is_pinned()
         item = int(np.prod(x.shape[1:]))

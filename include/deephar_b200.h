@@ -83,7 +83,7 @@ int         dh_set_workspace(dh_ctx* ctx, void* ptr, int64_t bytes);
  * "sep_tma" (default 1) = use the TMA-staged separable kernel where it applies;
  * "pw_smallk" (default 1) = CUDA-core kernel for wide 1x1 convs with Cin <= 64;
  * "dense_patch" (default 1) = TMA-staged patch kernel (conv_patch.cu) for stride-1 Conv2D where it applies;
- * "dbg" (default 0) = timing-ablation bits for tools/ (results are WRONG when non-zero) */
+ * (the round-1 "dbg" timing-ablation switch only exists in tools/ builds: make ABLATE=1) */
 int         dh_set_option(dh_ctx* ctx, const char* name, int value);
 
 /* --- convolutions -------------------------------------------------------- */
@@ -149,6 +149,12 @@ int dh_softargmax2d_ctx_f32(dh_ctx* ctx, const dh_view* h, int nj, int n_ctx, fl
 int dh_softargmax3d_f32(dh_ctx* ctx, const dh_view* h, int nj, int depth_maps,
                         float* out_pose, float* out_vis, void* stream);
 
+/* deephar/models/action.py:208-297 _get_3d_pose_estimation_from_model (CVPR'18 merge model, 3-D pose): same head as
+ * dh_softargmax3d_f32 with visible = sigmoid(vis_scale * (max hxy + max hz)) (vis_scale = 2, action.py:291-292)
+ * and, if prob_out != NULL-p, prob_out (N,H,W,nj) = channel_softmax_2d(hxy) for the kronecker product (:294-295). */
+int dh_softargmax3d_ex_f32(dh_ctx* ctx, const dh_view* h, int nj, int depth_maps, float vis_scale,
+                           float* out_pose, float* out_vis, const dh_view* prob_out, void* stream);
+
 /* layers.py:478-508 kronecker_prod for clips: out[n,j,f] = sum_hw P[n,h,w,j] * Z[n,h,w,f]. */
 int dh_kron_pool_f32(dh_ctx* ctx, const dh_view* p, const dh_view* z, float* out, void* stream);
 
@@ -162,6 +168,22 @@ int dh_global_maxmin_softmax_f32(dh_ctx* ctx, const dh_view* x, float* out, void
 /* out[b,t,j,:] = p[b,t,j,:] * c[b,t,j,0]   (spnet.py:110-111) */
 int dh_mask_mul_f32(dh_ctx* ctx, const float* p, const float* c, int64_t rows, int dim, float* out,
                     void* stream);
+
+/* --- multi-GPU exchange step ---------------------------------
+ * One process per GPU; the clip batch is sharded, weights replicated, and the ONLY communication of the forward
+ * path is an all-gather of the per-rank outputs (action probabilities, optionally poses).  The reference has
+ * no multi-GPU path (single process: exp/ntu/eval_ntu_multitask.py:35-54); these calls are what a data-parallel
+ * evaluator runs after Model.predict() on its shard.  NCCL is bound at run time (dlopen), no link dependency.
+ * Return values > 1000 are ncclResult_t + 1000. */
+/* rank 0: 128-byte ncclUniqueId to hand to every rank (any out-of-band channel: torch.distributed store, MPI, file) */
+int dh_comm_unique_id(void* out128);
+/* collective over all `world` ranks (each with its own ctx / device) */
+int dh_comm_init(dh_ctx* ctx, int rank, int world, const void* unique_id128);
+int dh_comm_destroy(dh_ctx* ctx);
+/* recv[r*count .. (r+1)*count) = rank r's send[0 .. count); fp32 device buffers; asynchronous on `stream` */
+int dh_allgather_f32(dh_ctx* ctx, const float* send, float* recv, int64_t count, void* stream);
+/* rank / world of the context's communicator (-1 / 0 if none) and the NCCL version in use (0 if not loadable) */
+int dh_comm_info(dh_ctx* ctx, int* rank, int* world, int* nccl_version);
 
 #ifdef __cplusplus
 }

@@ -1,5 +1,5 @@
-"""CPU restatement of deephar/models/action.py::build_merge_model (CVPR'18 clip model, 2-D pose
-variant -- the only one with a working script, exp/pennaction/eval_penn_ar_pe_merge.py:42-62).
+"""CPU restatement of deephar/models/action.py::build_merge_model (CVPR'18 clip model): the 2-D pose
+variant (exp/pennaction/eval_penn_ar_pe_merge.py:42-62) and the 3-D one (action.py:208-297, pose_dim=3).
 TEST INFRASTRUCTURE (see oracle/__init__.py).
 
 `forward(ops, weights, x, ...)`: x (B,T,H,W,3) -> 9 action probability vectors
@@ -75,9 +75,10 @@ def visual_model(c0, f, num_actions):
 
 
 def forward(ops, weight_table, x, num_actions, num_joints, num_blocks, num_context_per_joint=2,
-            ksize=(5, 5), output_poses=False, weighted_merge=True, return_weights_used=False):
-    """action.py:319-400 with pose_dim=2 on a ReceptionNet built as in
-    eval_penn_ar_pe_merge.py:51-53."""
+            ksize=(5, 5), output_poses=False, weighted_merge=True, return_weights_used=False,
+            pose_dim=2, depth_maps=8):
+    """action.py:319-400 on a ReceptionNet built as in eval_penn_ar_pe_merge.py:51-53 (pose_dim=2) or with
+    dim=3, depth_maps=`depth_maps` (pose_dim=3, action.py:208-297)."""
     w = Weights(weight_table, ops)
     c = Ctx(ops, w)
     x = ops.from_numpy(x)
@@ -88,7 +89,7 @@ def forward(ops, weight_table, x, num_actions, num_joints, num_blocks, num_conte
     x1 = R._stem(c, x)
     xb1 = R._reception_block(c, x1, 'rBlock1', ksize)
     nfilt = xb1.shape[-1]
-    num_heatmaps = (num_context_per_joint + 1) * num_joints
+    num_heatmaps = (num_context_per_joint + 1) * num_joints if pose_dim == 2 else depth_maps * num_joints
 
     def sepconv_blk(t, i):
         return c.sub('SepConv%d' % i).separable_act_conv_bn(t, nfilt, ksize)
@@ -112,14 +113,24 @@ def forward(ops, weight_table, x, num_actions, num_joints, num_blocks, num_conte
     xx = sepconv_blk(xx, num_blocks)
     h = regmap(xx, num_blocks)
 
-    hs = h[..., :num_joints]
-    hc = h[..., num_joints:]
-    ys = R.softargmax_2d_model(ops, hs)
-    yc = R.softargmax_2d_model(ops, hc)
-    pc = R.joints_probability_model(ops, hc)
-    y = R.context_aggregation_model(ops, ys, yc, pc, num_joints, num_context_per_joint, 0.8)
-    p = R.joints_probability_model(ops, 4 * hs)                     # action.py:200
-    hs_prob = ops.channel_softmax_2d(hs)                            # action.py:202-203
+    if pose_dim == 2:
+        hs = h[..., :num_joints]
+        hc = h[..., num_joints:]
+        ys = R.softargmax_2d_model(ops, hs)
+        yc = R.softargmax_2d_model(ops, hc)
+        pc = R.joints_probability_model(ops, hc)
+        y = R.context_aggregation_model(ops, ys, yc, pc, num_joints, num_context_per_joint, 0.8)
+        p = R.joints_probability_model(ops, 4 * hs)                     # action.py:200
+        hs_prob = ops.channel_softmax_2d(hs)                            # action.py:202-203
+    else:
+        # action.py:265-295: the reception 3-D head with visible = sigmoid(2 * (vxy + vz))
+        n_, hh, ww, ch = h.shape
+        h5 = h.reshape(n_, hh, ww, depth_maps, num_joints)
+        hxy = ops.mean(h5, 3)
+        hz = ops.mean(h5, (1, 2))
+        y = ops.concat([R.softargmax_2d_model(ops, hxy), R.softargmax_1d_model(ops, hz)])
+        p = ops.sigmoid(2 * (ops.amax(hxy, (1, 2)) + ops.amax(hz, 1)))[..., None]
+        hs_prob = ops.channel_softmax_2d(hxy)
 
     unf = lambda t: t.reshape((B, T) + tuple(t.shape[1:]))
     y, p = unf(y), unf(p)

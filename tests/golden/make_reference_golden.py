@@ -85,7 +85,7 @@ def collect(model, prefix='', trainable=True, strip=()):
     return out
 
 
-def pin(case, ref_model, prod_model, seed, x, strip=(), x_recipe=None):
+def pin(case, ref_model, prod_model, seed, x, strip=(), x_recipe=None, weight_hook=None):
     ws = collect(ref_model, strip=strip)
     names = [n for n, _, _ in ws]
     assert len(set(names)) == len(names), 'duplicate weight names in the reference model'
@@ -97,6 +97,8 @@ def pin(case, ref_model, prod_model, seed, x, strip=(), x_recipe=None):
         assert tuple(w['value'].shape) == tuple(specs[n]), (n, w['value'].shape, specs[n])
     prod_model.init_synthetic_weights(seed)
     table = prod_model.get_weights()
+    if weight_hook is not None:
+        table = weight_hook(table)
     for n, w in trainable.items():
         w['value'] = np.asarray(table[n], dtype=np.float64)
     outs = ref_model.predict(np.asarray(x, dtype=np.float64))
@@ -122,7 +124,7 @@ def pin(case, ref_model, prod_model, seed, x, strip=(), x_recipe=None):
 
 
 def main():
-    from ref_cases import LARGE_INPUT_CASES, MERGE_CASE, RECEPTION_CASES, SPNET_CASES, SPNET_FULL_CASES
+    from ref_cases import LARGE_INPUT_CASES, MERGE3D_CASE, MERGE_CASE, RECEPTION_CASES, SPNET_CASES, SPNET_FULL_CASES
     only = set(sys.argv[1:])
     # ---- ReceptionNet (CVPR'18) ----
     for case, spec in RECEPTION_CASES.items():
@@ -159,6 +161,17 @@ def main():
 
     # ---- CVPR'18 merge model (2-D pose + action) ----
     x_merge = rng.uniform(-1.0, 1.0, (1, MERGE_CASE['num_frames']) + MERGE_CASE['input_shape'])
+    if not only or 'merge3d_model' in only:
+        fresh_process_state()
+        mc = MERGE3D_CASE
+        ref_pe = ref_reception.build(mc['input_shape'], **mc['reception'])
+        ref = ref_action.build_merge_model(ref_pe, mc['num_actions'], mc['input_shape'], mc['num_frames'], mc['num_joints'],
+                                           mc['num_blocks'], pose_dim=3, depth_maps=mc['depth_maps'], output_poses=True)
+        prod_pe = reception.build(mc['input_shape'], **mc['reception'])
+        prod = action.build_merge_model(prod_pe, mc['num_actions'], mc['input_shape'], mc['num_frames'], mc['num_joints'],
+                                        mc['num_blocks'], pose_dim=3, depth_maps=mc['depth_maps'], output_poses=True)
+        pin('merge3d_model', ref, prod, mc['seed'],
+            np.random.default_rng(77).uniform(-1.0, 1.0, (2, mc['num_frames']) + mc['input_shape']), strip=('td_',))
     if only and 'merge_model' not in only:
         return
     fresh_process_state()
@@ -169,7 +182,9 @@ def main():
     prod_pe = reception.build(mc['input_shape'], **mc['reception'])
     prod = action.build_merge_model(prod_pe, mc['num_actions'], mc['input_shape'], mc['num_frames'], mc['num_joints'],
                                     mc['num_blocks'], pose_dim=2)
-    pin('merge_model', ref, prod, mc['seed'], x_merge, strip=('td_',))
+    from ref_cases import positive_last_regmap
+    pin('merge_model', ref, prod, mc['seed'], x_merge, strip=('td_',),
+        weight_hook=lambda t: positive_last_regmap(t, mc['num_blocks']))
 
 
 if __name__ == '__main__':

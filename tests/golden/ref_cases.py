@@ -53,5 +53,23 @@ SPNET_FULL_CASES = {
 }
 
 # CVPR'18 merge model (exp/pennaction/eval_penn_ar_pe_merge.py:42-62), small geometry
+def positive_last_regmap(table, num_blocks):
+    """Weight hook of the merge-model cases: |kernel| for the LAST RegMap conv.  Its input is ReLU(x) >= 0, so the
+    heat-maps and with them the raw joint confidences are >= 0 and the context aggregation's division by
+    sum(pc) (blocks.py:264-267) is perfectly conditioned for every joint -- the action outputs, which consume ALL
+    joints' poses, can then be held to the 1e-3 bar instead of being bounded by the worst joint's cancellation."""
+    import numpy as np
+    out = dict(table)
+    for name in table:
+        if name.startswith('RegMap%d/' % num_blocks) and name.endswith('/kernel'):
+            out[name] = np.abs(table[name])
+    return out
+
+
 MERGE_CASE = dict(input_shape=(64, 64, 3), num_frames=4, num_actions=15, num_joints=16, num_blocks=4, seed=3,
                   reception=dict(num_joints=16, dim=2, num_blocks=4, num_context_per_joint=2, ksize=(5, 5)))
+
+# the 3-D variant of the merge model (action.py:208-297 via build_merge_model(pose_dim=3)); 20 joints (pa20j3d):
+# the PoseAR net pools and re-upsamples the joint axis, which only closes for joint counts divisible by 4
+MERGE3D_CASE = dict(input_shape=(64, 64, 3), num_frames=4, num_actions=15, num_joints=20, num_blocks=2, depth_maps=8, seed=9,
+                    reception=dict(num_joints=20, dim=3, num_blocks=2, depth_maps=8, ksize=(5, 5)))

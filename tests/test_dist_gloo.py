@@ -26,7 +26,7 @@ def _worker(rank, world, port, n_clips, out_path):
     x = torch.randn(n_clips, 4, 8, 8, 3, generator=g)
     a, b = shard_range(n_clips, rank, world)
     local = _fake_forward(x[a:b])
-    full = gather_outputs(local, world)
+    full = gather_outputs(local, world, n_global=n_clips)
     if rank == 0:
         np.save(out_path, full.numpy())
     dist.destroy_process_group()

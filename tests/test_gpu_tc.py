@@ -89,7 +89,7 @@ def _patch_eligible(case):
     if bn > 256:
         bn = (bn + 31) // 32 * 32
     stride = (128 * pc * pr * fn + 1023) // 1024 * 1024
-    fixed = 3 * 2 * 8192 + 4 * bn * 64 + (4 * 32 * 128 + 2 * 288 * 4) + 512 + 1024
+    fixed = 3 * 2 * 8192 + 4 * bn * 64 + (8 * 32 * 128 + 2 * 288 * 4) + 512
     return fixed + 2 * stride <= 227 * 1024
 
 

@@ -30,10 +30,20 @@ def test_merge_full_size_config():
     m = action.build_merge_model(pe, 15, (256, 256, 3), 16, 16, 4, pose_dim=2)
     assert m.input_shape == (None, 16, 256, 256, 3)
     assert abs(m.conv_flops_per_frame() - 12.0e9) / 12.0e9 < 0.02        # 12.00 GFLOP backbone
-    with pytest.raises(NotImplementedError):
-        action.build_merge_model(pe, 15, (256, 256, 3), 16, 16, 4, pose_dim=3)
+    with pytest.raises(ValueError):
+        action.build_merge_model(pe, 15, (256, 256, 3), 16, 16, 4, pose_dim=3)   # a 2-D pose network under the 3-D head
     with pytest.raises(ValueError):
         action.build_merge_model(pe, 15, (256, 256, 3), 16, 16, 3, pose_dim=2)   # wrong num_blocks
+
+
+def test_merge_3d_variant_builds():
+    """action.py:208-297 (pose_dim=3): volumetric head; outputs [pose, visible, p1..p4, v1..v4, m]."""
+    pe = reception.build((128, 128, 3), 20, dim=3, num_blocks=2, depth_maps=8, ksize=(5, 5))
+    m = action.build_merge_model(pe, 60, (128, 128, 3), 8, 20, 2, pose_dim=3, depth_maps=8, output_poses=True)
+    assert m.output_shape[:2] == [(None, 8, 20, 3), (None, 8, 20, 1)] and len(m.outputs) == 11
+    assert [k.kind for k in m.plan.kops].count('pose_regression_3d_ex') == 1
+    with pytest.raises(ValueError):
+        action.build_merge_model(pe, 60, (128, 128, 3), 8, 20, 2, pose_dim=3, depth_maps=16)
 
 
 @pytest.mark.gpu

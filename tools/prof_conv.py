@@ -17,10 +17,12 @@ n, h, w, cin, cout, k = [int(a) for a in sys.argv[2:8]]
 precision = int(sys.argv[8]) if len(sys.argv) > 8 else 3
 reps = int(sys.argv[9]) if len(sys.argv) > 9 else 5
 dev = Dev(torch)
-if os.environ.get('DH_DBG'):
-    dev.lib.dh_set_option(dev.ctx.handle, b'dbg', int(os.environ['DH_DBG']))
+if os.environ.get('DH_DBG'):        # only in `make ABLATE=1` builds
+    _ffi.check(dev.lib.dh_set_option(dev.ctx.handle, b'dbg', int(os.environ['DH_DBG'])), 'dbg (needs make ABLATE=1)')
 if os.environ.get('DH_PATCH'):
     dev.lib.dh_set_option(dev.ctx.handle, b'dense_patch', int(os.environ['DH_PATCH']))
+if os.environ.get('DH_PWSMALLK'):
+    dev.lib.dh_set_option(dev.ctx.handle, b'pw_smallk', int(os.environ['DH_PWSMALLK']))
 if os.environ.get('DH_SHARE'):
     dev.lib.dh_set_option(dev.ctx.handle, b'share_a', int(os.environ['DH_SHARE']))
 rng = np.random.default_rng(0)
