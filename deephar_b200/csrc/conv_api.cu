@@ -31,7 +31,7 @@ extern "C" int dh_conv2d_f32(dh_ctx* ctx, const dh_view* x, const float* w_hwio,
         DH_LAUNCH_EPILOGUE(ctx, 1);
     }
     ctx->last_conv_path = 0;
-    ctx->fallbacks += 1;
+    if (!dh_conv_smallk_ok(p)) ctx->fallbacks += 1;      // the direct K <= 32 kernel is a specialised path, not a fallback
     dh_launch_conv_simt(p, s);
     DH_LAUNCH_EPILOGUE(ctx, 1);
 }

@@ -20,6 +20,7 @@ struct ConvParams {
 int dh_fill_conv_params(ConvParams* p, const dh_view* x, const dh_conv_desc* d, const dh_view* out,
                         int cout, const char* who);
 void dh_launch_conv_simt(const ConvParams& p, cudaStream_t s);
+bool dh_conv_smallk_ok(const ConvParams& p);
 // wide pointwise conv with a small reduction (conv_simt.cu), exact fp32
 bool dh_pw_smallk_supported(const ConvParams& p);
 int dh_launch_pw_smallk(const ConvParams& p, int num_sms, cudaStream_t s);

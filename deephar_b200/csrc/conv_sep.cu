@@ -22,12 +22,13 @@
 
 namespace tcs {
 using namespace tc;
-using R = tc::Roles<2>;
-constexpr int NEPI = R::NEPI, WARP_TMA = R::WARP_TMA, WARP_MMA = R::WARP_MMA, WARP_PATCH = R::WARP_PATCH, NTHREADS = R::NTHREADS,
+using R = tc::Roles<2, 1>;
+constexpr int NEPI = R::NEPI, WARP_EPI0 = R::WARP_EPI0, WARP_TMA = R::WARP_TMA, WARP_MMA = R::WARP_MMA, WARP_PATCH = R::WARP_PATCH, NTHREADS = R::NTHREADS,
               EPI_STAGE_BYTES = R::EPI_STAGE_BYTES, REGS_PROD = R::REGS_PROD, REGS_EPI = R::REGS_EPI, REGS_CTRL = R::REGS_CTRL;
 
 constexpr int A_BYTES = BM * 64;           // 8 KB per (hi | lo)
 constexpr int NWG = 128;                   // threads per producer warpgroup
+constexpr int NPW = 1;                     // producer warpgroups (see tc_common.cuh Roles: one, with 192 registers)
 constexpr int NA = 3;                      // A-tile ring depth (the weight ring stays 2 deep)
 
 struct SepParams {
@@ -118,7 +119,7 @@ sep_tma_kernel(const __grid_constant__ SepParams SP, const __grid_constant__ CUt
         // ======================= depthwise producers (two warpgroups) =======================
         reg_prod<REGS_PROD, R::LAUNCH_REGS>();
         const ConvParams& c = P.c;
-        const int w = warp >> 2;                       // warpgroup 0 | 1 -> patch buffer w, own K-blocks j = w, w+2, ...
+        const int w = warp >> 2;                       // producer warpgroup: own K-blocks j = w, w + NPW, ...; patch buffer j & 1
         const int tw = tid & (NWG - 1);
         const int cp = tw & 15;                        // channel pair inside the 32-channel K-block
         const int blk = tw >> 4;                       // 4x4 pixel block inside the 128-pixel tile
@@ -126,7 +127,7 @@ sep_tma_kernel(const __grid_constant__ SepParams SP, const __grid_constant__ CUt
         const int strip = blk / XB, xb = blk - strip * XB;
         const int fn = (strip * 4) / SP.ry, ry = (strip * 4) - fn * SP.ry;
         const int prr = SP.ry + 2 * PAD;               // patch rows per frame
-        const float* pbase = reinterpret_cast<const float*>(patch0 + (size_t)w * SP.patch_stride) +
+        const float* pbase0 = reinterpret_cast<const float*>(patch0) +
                              ((size_t)((fn * prr + ry) * PC + xb * 4)) * SBK + cp * 2;
         const int row0 = strip * 4 * TW + xb * 4;      // tile-local pixel of output (o = 0, q = 0)
         const float lowb = c.pre_relu ? 0.f : -3.402823466e38f;
@@ -141,8 +142,10 @@ sep_tma_kernel(const __grid_constant__ SepParams SP, const __grid_constant__ CUt
                 if (ix >= 0 && ix < TW) colmask |= 1u << q;
             }
         }
-        const uint32_t pfull = bar_pfull0 + 8 * w, pempty = bar_pempty0 + 8 * w;
-        for (int j = w; j < n_own; j += 2) {
+        for (int j = w; j < n_own; j += NPW) {
+            const int pb_i = j & 1;                      // patch buffer of own K-block j (filled by the patch-TMA warp in j order)
+            const uint32_t pfull = bar_pfull0 + 8 * pb_i, pempty = bar_pempty0 + 8 * pb_i;
+            const float* pbase = pbase0 + (size_t)pb_i * (SP.patch_stride / 4);
             const int g = SHARE ? 2 * j + (int)my_rank : j;
             const int ti = g / nkb, kb = g - ti * nkb;
             const int ch = kb * SBK + cp * 2;
@@ -232,7 +235,7 @@ sep_tma_kernel(const __grid_constant__ SepParams SP, const __grid_constant__ CUt
     } else if (warp < WARP_TMA) {
         // ======================= epilogue =======================
         reg_inc<REGS_EPI>();
-        run_epilogue<R::EPQ>(P, epi_stage, tmem_base, bar_tfull0, bar_tempty0, n0, warp, lane);
+        run_epilogue<R::EPQ>(P, epi_stage, tmem_base, bar_tfull0, bar_tempty0, n0, warp - WARP_EPI0, lane);
     } else {
         reg_dec<REGS_CTRL>();
         if (warp == WARP_TMA) {

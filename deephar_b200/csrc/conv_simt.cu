@@ -437,6 +437,9 @@ int dh_launch_pw_smallk(const ConvParams& p, int num_sms, cudaStream_t s) {
     return pw_launch<4, 512, true>(p, num_sms, s);
 }
 
+// true if dh_launch_conv_simt serves `p` with the direct small-K kernel (not the generic implicit-GEMM fallback)
+bool dh_conv_smallk_ok(const ConvParams& p) { return smallk_ok(p); }
+
 void dh_launch_conv_simt(const ConvParams& p, cudaStream_t s) {
     if (smallk_ok(p)) {
         const int cgn = p.Cout / 8;

@@ -24,7 +24,7 @@
 
 namespace tc {
 using R = tc::Roles<1>;
-constexpr int NEPI = R::NEPI, WARP_TMA = R::WARP_TMA, WARP_MMA = R::WARP_MMA, NTHREADS = R::NTHREADS,
+constexpr int NEPI = R::NEPI, WARP_EPI0 = R::WARP_EPI0, WARP_TMA = R::WARP_TMA, WARP_MMA = R::WARP_MMA, NTHREADS = R::NTHREADS,
               EPI_STAGE_BYTES = R::EPI_STAGE_BYTES, REGS_PROD = R::REGS_PROD, REGS_EPI = R::REGS_EPI, REGS_CTRL = R::REGS_CTRL;
 
 // ---------------------------------------------------------------------------
@@ -361,7 +361,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
     } else if (warp < WARP_TMA) {
         // ======================= epilogue =======================
         reg_inc<REGS_EPI>();
-        run_epilogue<R::EPQ>(P, epi_stage, tmem_base, bar_tfull0, bar_tempty0, n0, warp, lane);
+        run_epilogue<R::EPQ>(P, epi_stage, tmem_base, bar_tfull0, bar_tempty0, n0, warp - WARP_EPI0, lane);
     } else {
         reg_dec<REGS_CTRL>();
         if (warp == WARP_TMA) {

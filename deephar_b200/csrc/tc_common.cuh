@@ -13,33 +13,36 @@ namespace tc {
 constexpr int BM = 128;
 constexpr int BK = 64;                 // bf16 per K-block = one 128-byte swizzle row
 constexpr int NPROD = 256;             // A producers: warps 0..7 (two warpgroups)
-constexpr int WARP_EPI0 = 8;           // first epilogue warp
 constexpr int MAX_BN_CTA = 288;
-// Warp roles: producers (warps 0-7) | epilogue (4 * Q warps) | one control warpgroup (weight TMA, MMA issue,
+// Warp roles: producers (NPW warpgroups) | epilogue (4 * Q warps) | one control warpgroup (weight TMA, MMA issue,
 // patch TMA, spare).  Q = epilogue warps per TMEM lane quarter (a warp may only touch TMEM lanes
 // 32 * (warp % 4) .. + 31); the Q warps of a quarter take alternate 32-column chunks of every accumulator
 // sub-tile.  The epilogue of a tile is a latency-bound serial stream per warp (tcgen05.ld -> smem transpose ->
 // residual / BN -> store): with one warp per quarter it takes about as long as the MMAs of a 288-wide tile.
 // Register budget (setmaxnreg; ptxas allocates each role's code against its own value):
 //   Q = 1: 512 threads launch with 128 registers: 256 * 168 + 128 * 144 + 128 * 32 = 65536
-//   Q = 2: 640 threads launch with 96 (65536 / 640 rounded down to the allocation unit).  setmaxnreg only
+//   Q = 2, NPW = 1 (conv_sep.cu): 512 threads launch with 128: ONE producer warpgroup with 192 registers (the 5x5
+//          depthwise keeps 25 tap pairs + 16 accumulator pairs + an input row in registers: ~115, and it spills
+//          below that), 128 * 192 + 256 * 144 + 128 * 32 = 65536.
+//   Q = 2, NPW = 2 (conv_patch.cu): 640 threads launch with 96 (65536 / 640 rounded down to the allocation unit).  setmaxnreg only
 //          redistributes the CTA's OWN allocation, 640 * 96 = 61440 registers (asking for more blocks forever):
 //          producers drop to 80 (the TMA-staged producers fit), control to 32, the epilogue grows to 144 (its two
 //          residual row buffers + a 32-column TMEM chunk are 96 registers alone):
 //          256 * 80 + 256 * 144 + 128 * 32 = 61440.
-template <int Q>
+template <int Q, int NPW = 2>
 struct Roles {
     static constexpr int EPQ = Q;
     static constexpr int NEPI = 128 * Q;
+    static constexpr int WARP_EPI0 = 4 * NPW;               // first epilogue warp
     static constexpr int WARP_TMA = WARP_EPI0 + 4 * Q, WARP_MMA = WARP_TMA + 1, WARP_PATCH = WARP_TMA + 2;
     static constexpr int NTHREADS = 32 * (WARP_TMA + 4);
     static constexpr int EPI_TILE_BYTES = 4 * Q * 32 * 128;    // per epilogue warp: 32 rows x 32 fp32, XOR-swizzled
     // + this CTA's BN scale | shift columns (read per chunk with LDS: a global load there would share a
     // scoreboard with the in-flight residual loads and drain them early)
     static constexpr int EPI_STAGE_BYTES = EPI_TILE_BYTES + 2 * MAX_BN_CTA * 4;
-    static constexpr int REGS_PROD = Q == 1 ? 168 : 80, REGS_EPI = 144, REGS_CTRL = 32;
-    static constexpr int LAUNCH_REGS = Q == 1 ? 128 : 96;      // what ptxas reports for __launch_bounds__(NTHREADS, 1)
-    static_assert(256 * REGS_PROD + NEPI * REGS_EPI + 128 * REGS_CTRL <= NTHREADS * LAUNCH_REGS,
+    static constexpr int REGS_PROD = Q == 1 ? 168 : (NPW == 1 ? 192 : 80), REGS_EPI = 144, REGS_CTRL = 32;
+    static constexpr int LAUNCH_REGS = NTHREADS <= 512 ? 128 : 96;      // what ptxas reports for __launch_bounds__(NTHREADS, 1)
+    static_assert(128 * NPW * REGS_PROD + NEPI * REGS_EPI + 128 * REGS_CTRL <= NTHREADS * LAUNCH_REGS,
                   "setmaxnreg budget exceeds the CTA's register allocation: the last setmaxnreg.inc would never return");
 };
 constexpr int A_TILE_BYTES = BM * 128; // 16 KB per (hi | lo)
@@ -445,10 +448,11 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& P, uint32_t tile_s
 
 template <int EPQ>
 __device__ __forceinline__ void run_epilogue(const TcParams& P, uint8_t* epi_stage, uint32_t tmem_base,
-                                             uint32_t bar_tfull0, uint32_t bar_tempty0, int n0, int warp,
+                                             uint32_t bar_tfull0, uint32_t bar_tempty0, int n0, int e,
                                              int lane) {
+    // e: epilogue warp 0 .. 4 * EPQ - 1 (warp index minus the kernel's first epilogue warp; a multiple of 4 apart
+    // from the hardware warp index, so e & 3 == warp % 4)
     const ConvParams& c = P.c;
-    const int e = warp - WARP_EPI0;                  // epilogue warp 0 .. 4 * EPQ - 1
     const int q = e & 3;                             // == warp % 4: the TMEM lane quarter this warp may access
     const int half = e >> 2;                         // which of the quarter's EPQ warps
     const uint32_t tile_s = smem_u32(epi_stage) + (uint32_t)e * (32 * 32 * 4);

@@ -1,0 +1,103 @@
+"""Evaluator-side post-processing on the GPU -- the step AFTER the forward path in the
+reference's evaluators: poses back to image coordinates with the inverse crop affine, then PCKh / mean distance
+(exp/common/mpii_tools.py:93-129, deephar/utils/transform.py:136-209, deephar/measures.py:5-93).  Same function
+names and argument meaning as the reference; arrays may be numpy (copied to the device) or CUDA tensors, results
+come back as numpy / python floats.  One kernel (dh_pose_eval_f32); no CPU path.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _ffi
+
+# measures.py:63-65: pelvis and thorax are ignored, "according to the file 'annolist2matrix.m'"
+PCKH_USED_JOINTS = [2, 3, 4, 5, 6, 7, 10, 11, 12, 13, 14, 15, 8, 9]
+
+_ctx = {}
+
+
+def _context(torch):
+    dev = torch.cuda.current_device()
+    if dev not in _ctx:
+        _ctx[dev] = _ffi.Context(dev)
+    return _ctx[dev]
+
+
+def _dev(torch, a, dtype=None):
+    if not torch.is_tensor(a):
+        a = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32 if dtype is None else dtype))
+    return a.to(device='cuda', dtype=torch.float32).contiguous()
+
+
+def _run(poses, A, inverse, y_true=None, head_size=None, refp=0.5):
+    import torch
+    if not torch.cuda.is_available():
+        raise _ffi.DeepharB200Error('deephar_b200.postprocess needs a CUDA device; there is no CPU fallback')
+    p = _dev(torch, poses)
+    assert p.dim() == 3 and p.shape[2] >= 2, 'transform_pose_sequence: expected 3D tensor, got %s' % (tuple(p.shape),)
+    a = _dev(torch, A)
+    per_sample = a.dim() == 3
+    if per_sample:
+        assert len(a) == len(p), 'A is %s and poses is %s' % (tuple(a.shape), tuple(p.shape))
+    n, nj = int(p.shape[0]), int(p.shape[1])
+    out = torch.empty(n, nj, 2, device='cuda', dtype=torch.float32)
+    hits = torch.zeros(nj, device='cuda', dtype=torch.int32)
+    valid = torch.zeros(nj, device='cuda', dtype=torch.int32)
+    dsum = torch.zeros(nj, device='cuda', dtype=torch.float64)
+    yt = _dev(torch, y_true)[:, :, :2].contiguous() if y_true is not None else None
+    hs = _dev(torch, head_size).reshape(-1) if head_size is not None else None
+    if yt is not None:
+        assert yt.shape[:2] == p.shape[:2]
+    if hs is not None:
+        assert len(hs) == n
+    ctx = _context(torch)
+    rc = _ffi.lib().dh_pose_eval_f32(ctx.handle, p.data_ptr(), int(p.shape[2]), a.data_ptr(), 1 if per_sample else 0,
+                                     1 if inverse else 0, yt.data_ptr() if yt is not None else None,
+                                     hs.data_ptr() if hs is not None else None, C.c_float(refp), n, nj, out.data_ptr(),
+                                     hits.data_ptr(), valid.data_ptr(), dsum.data_ptr(),
+                                     torch.cuda.current_stream().cuda_stream)
+    _ffi.check(rc, 'dh_pose_eval_f32')
+    return out, hits, valid, dsum
+
+
+def transform_pose_sequence(A, poses, inverse=True):
+    """deephar/utils/transform.py:174-209: [num_samples, num_points, 2] poses through A (one [3,3] map or one per
+    sample), inverted first if `inverse`."""
+    out, _, _, _ = _run(poses, A, inverse)
+    return out.cpu().numpy()
+
+
+def pckh(y_true, y_pred, head_size, refp=0.5, A=None):
+    """deephar/measures.py:49-76.  With `A` the predictions are first mapped by inv(A) (what the evaluator does
+    on the host before calling pckh, mpii_tools.py:118-119) -- one kernel for both."""
+    import torch
+    eye = np.eye(3, dtype=np.float32)
+    _, hits, valid, _ = _run(y_pred, A if A is not None else eye, A is not None, y_true, head_size, refp)
+    used = torch.tensor(PCKH_USED_JOINTS, device='cuda')
+    return float(hits[used].sum().item()) / float(valid[used].sum().item())
+
+
+def mean_distance_error(y_true, y_pred):
+    """deephar/measures.py:18-47 for 2-D poses."""
+    _, _, valid, dsum = _run(y_pred, np.eye(3, dtype=np.float32), False, y_true, None, 0.0)
+    return float(dsum.sum().item()) / float(valid.sum().item())
+
+
+def eval_singleperson_pckh(model, fval, pval, afmat_val, headsize_val, batch_size=8, refp=0.5, pred_per_block=1):
+    """exp/common/mpii_tools.py:63-129 for single-frame models: predict, map every block's pose back with
+    inv(afmat) and score it -- poses stay on the device between the soft-argmax head and the score."""
+    import torch
+    fval = np.ascontiguousarray(fval, dtype=np.float32)
+    num_blocks = int(len(model.outputs) / pred_per_block)
+    y_true = transform_pose_sequence(np.array(afmat_val, dtype=np.float32), np.asarray(pval)[:, :, :2], inverse=True)
+    hits = [None] * num_blocks
+    valid = [None] * num_blocks
+    for i in range(0, len(fval), batch_size):
+        outs = model.forward_device(torch.from_numpy(fval[i:i + batch_size]).cuda())
+        for b in range(num_blocks):
+            _, h, v, _ = _run(outs[pred_per_block * b][:, :, :2], afmat_val[i:i + batch_size], True,
+                              y_true[i:i + batch_size], headsize_val[i:i + batch_size], refp)
+            hits[b] = h if hits[b] is None else hits[b] + h
+            valid[b] = v if valid[b] is None else valid[b] + v
+    used = torch.tensor(PCKH_USED_JOINTS, device='cuda')
+    return [float(hits[b][used].sum().item()) / float(valid[b][used].sum().item()) for b in range(num_blocks)]

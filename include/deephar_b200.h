@@ -169,6 +169,19 @@ int dh_global_maxmin_softmax_f32(dh_ctx* ctx, const dh_view* x, float* out, void
 int dh_mask_mul_f32(dh_ctx* ctx, const float* p, const float* c, int64_t rows, int dim, float* out,
                     void* stream);
 
+/* --- evaluator-side post-processing ------------------------------
+ * deephar/utils/transform.py:136-209 transform_pose_sequence(A, poses, inverse) + deephar/measures.py:5-93
+ * (pckh, mean_distance_error) as the evaluators use them after predict (exp/common/mpii_tools.py:93-129):
+ *   out_pose[n,j,:] = (M_n [x, y, 1]^T)[0:2],  M_n = inverse ? inv(A_n) : A_n   (fp64 inverse, like np.linalg.inv)
+ * and, if y_true != NULL, per joint j over the samples whose annotation is valid (both coords > -1e6):
+ *   valid[j] += 1;  dist_sum[j] += |y_true - out_pose|;  hits[j] += (dist / head_size[n] <= refp)
+ * (head_size may be NULL: plain distance threshold).  pred: (N, nj, pred_ld >= 2) device floats;
+ * afmat: (N,3,3) if per_sample_mat else (1,3,3); hits / valid: int32 (nj), dist_sum: double (nj), accumulated
+ * (zero them first).  PCKh = sum(hits[used]) / sum(valid[used]). */
+int dh_pose_eval_f32(dh_ctx* ctx, const float* pred, int pred_ld, const float* afmat, int per_sample_mat,
+                     int inverse, const float* y_true, const float* head_size, float refp, int N, int nj,
+                     float* out_pose, int* hits, int* valid, double* dist_sum, void* stream);
+
 /* --- multi-GPU exchange step ---------------------------------
  * One process per GPU; the clip batch is sharded, weights replicated, and the ONLY communication of the forward
  * path is an all-gather of the per-rank outputs (action probabilities, optionally poses).  The reference has

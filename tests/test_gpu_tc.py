@@ -158,7 +158,7 @@ SEP_CASES = [
 
 def _tma_eligible(case):
     n, h, w, cin, cout, k, mode = case
-    return mode != 'bn_act' and w in (32, 16, 8) and cin % 32 == 0
+    return w in (32, 16, 8) and cin % 32 == 0          # (BN-prologue layers included: the halo is masked after the affine)
 
 
 @pytest.mark.parametrize('case', SEP_CASES)

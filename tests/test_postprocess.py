@@ -1,0 +1,55 @@
+"""evaluator post-processing.  CPU: the oracle vs the outputs of the reference's own numpy code
+(tests/golden/ref_postprocess.npz, written by make_postprocess_golden.py).  GPU: dh_pose_eval_f32 vs both."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import postprocess as oracle_pp
+
+Z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'ref_postprocess.npz'))
+
+
+def test_oracle_matches_reference_postprocessing():
+    y = oracle_pp.transform_pose_sequence(Z['A'], Z['y_pred_crop'], inverse=True)
+    assert np.abs(y - Z['y_pred']).max() <= 1e-9 * np.abs(Z['y_pred']).max()
+    f = oracle_pp.transform_pose_sequence(Z['A'][0], Z['y_pred_crop'], inverse=False)
+    assert np.abs(f - Z['fwd']).max() <= 1e-12
+    assert oracle_pp.pckh(Z['y_true'], Z['y_pred'], Z['head'], 0.5) == pytest.approx(float(Z['pckh05']), abs=1e-12)
+    assert oracle_pp.pckh(Z['y_true'], Z['y_pred'], Z['head'], 0.2) == pytest.approx(float(Z['pckh02']), abs=1e-12)
+    assert oracle_pp.mean_distance_error(Z['y_true'], Z['y_pred']) == pytest.approx(float(Z['mde']), rel=1e-12)
+
+
+@pytest.mark.gpu
+def test_gpu_postprocessing_matches_reference(cuda):
+    from deephar_b200 import postprocess as pp
+    y = pp.transform_pose_sequence(Z['A'], Z['y_pred_crop'], inverse=True)
+    assert np.abs(y - Z['y_pred']).max() <= 2e-6 * np.abs(Z['y_pred']).max()          # fp32 output of an fp64 transform
+    f = pp.transform_pose_sequence(Z['A'][0], Z['y_pred_crop'], inverse=False)
+    assert np.abs(f - Z['fwd']).max() <= 1e-6
+    # the score from crop-space predictions in ONE kernel (inverse map + threshold), as the evaluator does in two steps
+    assert pp.pckh(Z['y_true'], Z['y_pred_crop'], Z['head'], 0.5, A=Z['A']) == pytest.approx(float(Z['pckh05']), abs=1e-9)
+    assert pp.pckh(Z['y_true'], Z['y_pred'], Z['head'], 0.2) == pytest.approx(float(Z['pckh02']), abs=1e-9)
+    assert pp.mean_distance_error(Z['y_true'], Z['y_pred']) == pytest.approx(float(Z['mde']), rel=1e-5)
+
+
+@pytest.mark.gpu
+def test_eval_singleperson_pckh_end_to_end(cuda):
+    """exp/common/mpii_tools.py:63-129 on a tiny model: the device path must give the score the host path gives."""
+    from deephar_b200 import postprocess as pp
+    from deephar_b200 import reception
+    from oracle import synth
+    m = reception.build((64, 64, 3), num_joints=16, dim=2, num_context_per_joint=2, num_blocks=2, ksize=(3, 3),
+                        concat_pose_confidence=False).init_synthetic_weights(5)
+    n = 6
+    x = synth.synth_frames(n, 64, 64, seed=9)
+    rng = np.random.default_rng(1)
+    A = np.tile(np.array([[1 / 200.0, 0, 0.1], [0, 1 / 200.0, 0.2], [0, 0, 1]]), (n, 1, 1))
+    pval = rng.uniform(0.2, 0.8, (n, 16, 2))
+    head = rng.uniform(30, 50, (n, 1))
+    scores = pp.eval_singleperson_pckh(m, x, pval, A, head, batch_size=4, refp=0.5, pred_per_block=2)
+    outs = m.predict(x, batch_size=4)
+    y_true = oracle_pp.transform_pose_sequence(A, pval, inverse=True)
+    for b in range(2):
+        y_pred = oracle_pp.transform_pose_sequence(A, outs[2 * b], inverse=True)
+        assert scores[b] == pytest.approx(oracle_pp.pckh(y_true, y_pred, head, 0.5), abs=1e-9)

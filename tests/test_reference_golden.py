@@ -158,7 +158,7 @@ def test_product_matches_reference_graph(cuda, case):
         oracle_reception.forward(ops_torch if case.endswith(('fullsize', 'c1_heatmaps')) else ops_np, m.get_weights(),
                                  x.astype(np.float64), debug=dbg, **RECEPTION_CASES[case][1])
         cond = [np.asarray(c, dtype=np.float64) for c in dbg['ctx_cond']]
-    skipped = total = 0
+    skipped = total = ties = maps = 0
     per_block = 3 if (case in RECEPTION_CASES and RECEPTION_CASES[case][1].get('export_heatmaps') and
                       not RECEPTION_CASES[case][1].get('concat_pose_confidence', True)) else 2
     for i, (o, r) in enumerate(zip(outs, ref_outs)):
@@ -166,7 +166,7 @@ def test_product_matches_reference_graph(cuda, case):
         scale = np.maximum(np.abs(r), 1.0)
         err = np.abs(o.astype(np.float64) - r) / scale
         lim = 1e-3
-        if r.ndim == 4 and r.shape[1] == r.shape[2] and r.shape[1] > 4:
+        if per_block == 3 and i % per_block == 2:
             # exported heat-maps: north-star "bit-exact for argmax joint indices" -- the arg-max pixel of every
             # joint map must be the reference's, unless the reference's two best pixels are closer than the
             # value tolerance (a tie no fp32 implementation can order)
@@ -176,7 +176,8 @@ def test_product_matches_reference_graph(cuda, case):
             tie = (top2[:, 1] - top2[:, 0]) <= 2e-3 * np.maximum(1.0, np.abs(top2[:, 1]))
             same = fo.argmax(axis=1) == fr.argmax(axis=1)
             assert np.all(same | tie), '%s output %d: arg-max pixel differs on %d maps' % (case, i, int((~(same | tie)).sum()))
-            assert tie.mean() < 0.05
+            ties += int(tie.sum())
+            maps += tie.size
             err = np.abs(o.astype(np.float64) - r) / max(1.0, float(np.abs(r).max()))
         # (the merge-model fixtures use heat-maps that keep the context division well conditioned for every joint
         # -- ref_cases.positive_last_regmap -- so all of p1..p4, v1..v4, m are held to the 1e-3 bar)
@@ -190,3 +191,5 @@ def test_product_matches_reference_graph(cuda, case):
         assert np.all(err <= lim), '%s output %d: max err %g' % (case, i, float(err.max()))
     if total:
         assert skipped <= max(1, total // 50)
+    if maps:
+        assert ties <= max(1, maps // 20), '%d of %d heat-maps have an unresolvable top-2 tie' % (ties, maps)
