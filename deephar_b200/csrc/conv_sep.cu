@@ -142,6 +142,21 @@ sep_tma_kernel(const __grid_constant__ SepParams SP, const __grid_constant__ CUt
                 if (ix >= 0 && ix < TW) colmask |= 1u << q;
             }
         }
+        // depthwise taps of the thread's two channels: loaded for the NEXT own K-block right after the math of the
+        // current one (the registers are dead then), so the global-load latency hides behind the bf16 split / stage
+        // hand-over instead of stalling the first FMA of every K-block
+        float2 wt[KS][KS];
+        auto load_taps = [&](int jn) {
+            const int gn = SHARE ? 2 * jn + (int)my_rank : jn;
+            const int kbn = gn % nkb;
+            const float* wp = c.w_dw + kbn * SBK + cp * 2;
+#pragma unroll
+            for (int a = 0; a < KS; ++a)
+#pragma unroll
+                for (int b = 0; b < KS; ++b)
+                    wt[a][b] = __ldg(reinterpret_cast<const float2*>(wp + (size_t)(a * KS + b) * c.Cin));
+        };
+        if (w < n_own) load_taps(w);
         for (int j = w; j < n_own; j += NPW) {
             const int pb_i = j & 1;                      // patch buffer of own K-block j (filled by the patch-TMA warp in j order)
             const uint32_t pfull = bar_pfull0 + 8 * pb_i, pempty = bar_pempty0 + 8 * pb_i;
@@ -149,13 +164,7 @@ sep_tma_kernel(const __grid_constant__ SepParams SP, const __grid_constant__ CUt
             const int g = SHARE ? 2 * j + (int)my_rank : j;
             const int ti = g / nkb, kb = g - ti * nkb;
             const int ch = kb * SBK + cp * 2;
-            float2 wt[KS][KS];
-            const float* wp = c.w_dw + ch;
-#pragma unroll
-            for (int a = 0; a < KS; ++a)
-#pragma unroll
-                for (int b = 0; b < KS; ++b)
-                    wt[a][b] = __ldg(reinterpret_cast<const float2*>(wp + (size_t)(a * KS + b) * c.Cin));
+            // (the KS x KS tap pairs of this K-block's two channels were loaded one iteration ago: `wt`)
             float2 acc[4][4];
 #pragma unroll
             for (int o = 0; o < 4; ++o)
@@ -176,10 +185,10 @@ sep_tma_kernel(const __grid_constant__ SepParams SP, const __grid_constant__ CUt
             }
 
             if (!(DBG & 2)) mbar_wait_relaxed(pfull, (uint32_t)((j >> 1) & 1), (DBG & 2048) ? 32u : 0u);
-            if (!(DBG & 1))
-#pragma unroll
-            for (int r = 0; r < NR; ++r) {
-                float2 in[NR];
+            // input rows are loaded one row ahead of their FMAs (two register rows, compile-time ping-pong); within
+            // a row the FMAs go tap-column by tap-column over all (output row, output column) accumulators, so
+            // consecutive FFMA2 never touch the same accumulator
+            auto load_row = [&](int r, float2* in) {
 #pragma unroll
                 for (int q = 0; q < NR; ++q) {
                     float2 v = *reinterpret_cast<const float2*>(pbase + (r * PC + q) * SBK);
@@ -188,17 +197,27 @@ sep_tma_kernel(const __grid_constant__ SepParams SP, const __grid_constant__ CUt
                     if (BNPRO && !(((rowmask >> r) & 1u) && ((colmask >> q) & 1u))) v = make_float2(0.f, 0.f);
                     in[q] = v;
                 }
+            };
+            if (!(DBG & 1)) {
+                float2 inb[2][NR];
+                load_row(0, inb[0]);
 #pragma unroll
-                for (int o = 0; o < 4; ++o) {
-                    const int ky = r - o;          // compile-time after unrolling
-                    if (ky >= 0 && ky < KS) {
+                for (int r = 0; r < NR; ++r) {
+                    if (r + 1 < NR) load_row(r + 1, inb[(r + 1) & 1]);
+                    const float2* in = inb[r & 1];
 #pragma unroll
-                        for (int q = 0; q < 4; ++q)
+                    for (int kx = 0; kx < KS; ++kx)
 #pragma unroll
-                            for (int kx = 0; kx < KS; ++kx) acc[o][q] = __ffma2_rn(wt[ky][kx], in[q + kx], acc[o][q]);
-                    }
+                        for (int o = 0; o < 4; ++o) {
+                            const int ky = r - o;          // compile-time after unrolling
+                            if (ky >= 0 && ky < KS) {
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) acc[o][q] = __ffma2_rn(wt[ky][kx], in[q + kx], acc[o][q]);
+                            }
+                        }
                 }
             }
+            if (j + NPW < n_own) load_taps(j + NPW);
             if (!(DBG & 2)) mbar_arrive(pempty);    // patch buffer may be refilled
 
             const int s = g % NA;

@@ -61,7 +61,7 @@ __device__ __forceinline__ void dense_rows_init(const ConvParams& c, int m0, int
 // stage they will be written to, so the global/L2 latency overlaps the previous block's work.
 struct DenseRegs {
     float4 v[8];
-    unsigned ok;       // bit i: element i is inside the image (and k < K)
+    unsigned ok;       // bit 4 i + e: component e of row i is inside the image (and k < K)
     float4 ps, pb;
 };
 
@@ -90,11 +90,56 @@ __device__ __forceinline__ void dense_load(const TcParams& P, const DenseRows& R
         const bool ok = kval && R.base[i] >= 0 && iy >= 0 && iy < c.H && ix >= 0 && ix < c.W;
         D.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (ok) {
-            D.ok |= 1u << i;
+            D.ok |= 0xfu << (4 * i);
             D.v[i] = __ldg(reinterpret_cast<const float4*>(c.x + (size_t)(R.base[i] + iy * c.W + ix) * c.ldx + ci));
         }
     }
 }
+
+// Same item, for layers the 16-byte gather cannot take: Cin not a multiple of 4 (SPNet's 7x7x3 first conv,
+// models/spnet.py:317-325; the heat-map re-injection convs on nj / 2 nj channels, spnet.py:236-247), or a
+// channel-sliced input view at an unaligned offset.  The 4 k's of an item then belong to different taps /
+// pixels: each is decoded and loaded on its own (L1 serves the overlap between neighbouring pixels).
+__device__ __forceinline__ void dense_load_scalar(const TcParams& P, const DenseRows& R, int kb, int tid, DenseRegs& D) {
+    const ConvParams& c = P.c;
+    const int k0 = kb * BK + (tid & 15) * 4;
+    int ci[4], ky[4], kx[4];
+    bool kv[4];
+    float ps[4] = {1.f, 1.f, 1.f, 1.f}, pb[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int k = k0 + e;
+        kv[e] = k < c.K;
+        const int tap = kv[e] ? k / c.Cin : 0;
+        ci[e] = kv[e] ? k - tap * c.Cin : 0;
+        ky[e] = tap / c.kw;
+        kx[e] = tap - ky[e] * c.kw;
+        if (kv[e] && c.pre_scale) {
+            ps[e] = __ldg(c.pre_scale + ci[e]);
+            pb[e] = __ldg(c.pre_shift + ci[e]);
+        }
+    }
+    D.ps = make_float4(ps[0], ps[1], ps[2], ps[3]);
+    D.pb = make_float4(pb[0], pb[1], pb[2], pb[3]);
+    D.ok = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int iy = (R.yx[i] >> 16) + ky[e], ix = (int)(short)(R.yx[i] & 0xffff) + kx[e];
+            const bool ok = kv[e] && R.base[i] >= 0 && iy >= 0 && iy < c.H && ix >= 0 && ix < c.W;
+            v[e] = 0.f;
+            if (ok) {
+                D.ok |= 1u << (4 * i + e);
+                v[e] = __ldg(c.x + (size_t)(R.base[i] + iy * c.W + ix) * c.ldx + ci[e]);
+            }
+        }
+        D.v[i] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
+
+__device__ __forceinline__ void dense_load_any(const TcParams& P, const DenseRows& R, int kb, int tid, DenseRegs& D);
 
 __device__ __forceinline__ void dense_store(const TcParams& P, const DenseRegs& D, uint8_t* a_hi, uint8_t* a_lo,
                                             int tid, bool want_lo) {
@@ -103,11 +148,18 @@ __device__ __forceinline__ void dense_store(const TcParams& P, const DenseRegs& 
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         float4 t = D.v[i];
-        if ((D.ok >> i) & 1u) {
+        const unsigned m = (D.ok >> (4 * i)) & 0xfu;       // padding / K tail stay zero AFTER the prologue
+        if (m) {
             t.x = fmaf(t.x, D.ps.x, D.pb.x); t.y = fmaf(t.y, D.ps.y, D.pb.y);
             t.z = fmaf(t.z, D.ps.z, D.pb.z); t.w = fmaf(t.w, D.ps.w, D.pb.w);
             if (c.pre_relu) {
                 t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f);
+            }
+            if (m != 0xfu) {
+                if (!(m & 1u)) t.x = 0.f;
+                if (!(m & 2u)) t.y = 0.f;
+                if (!(m & 4u)) t.z = 0.f;
+                if (!(m & 8u)) t.w = 0.f;
             }
         }
         uint32_t h0, l0, h1, l1;
@@ -222,6 +274,11 @@ __device__ __forceinline__ void produce_sep(const TcParams& P, int kb, uint8_t* 
         }
 }
 
+__device__ __forceinline__ void dense_load_any(const TcParams& P, const DenseRows& R, int kb, int tid, DenseRegs& D) {
+    if (P.ks < 0) dense_load_scalar(P, R, kb, tid, D);     // ks = -1: scalar gather (set by the launcher)
+    else dense_load(P, R, kb, tid, D);
+}
+
 // ---------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------
@@ -299,7 +356,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
             int t_l = blockIdx.x, kb_l = 0;
             if (t_l < P.n_mtiles) {
                 dense_rows_init(P.c, t_l * BM, tid, rows);
-                dense_load(P, rows, 0, tid, cur);
+                dense_load_any(P, rows, 0, tid, cur);
                 if (++kb_l == nkb) { kb_l = 0; t_l += gridDim.x; }
             }
             int s = 0;
@@ -309,7 +366,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
                     const bool more = t_l < P.n_mtiles;
                     if (more) {
                         if (kb_l == 0) dense_rows_init(P.c, t_l * BM, tid, rows);
-                        dense_load(P, rows, kb_l, tid, nxt);
+                        dense_load_any(P, rows, kb_l, tid, nxt);
                         if (++kb_l == nkb) { kb_l = 0; t_l += gridDim.x; }
                     }
                     mbar_wait(bar_empty0 + 8 * s, (it & 1) ^ 1);
@@ -328,13 +385,13 @@ conv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUten
             const int kb_first = SHARE ? (int)((my_rank ^ (uint32_t)g0) & 1u) : 0;   // (g0 + kb) % 2 == my_rank
             if (MODE == 0) {
                 dense_rows_init(P.c, m0, tid, rows);
-                dense_load(P, rows, 0, tid, cur);
+                dense_load_any(P, rows, 0, tid, cur);
             }
             for (int kb = kb_first; kb < nkb; kb += SHARE ? 2 : 1) {
                 const int g = g0 + kb;
                 const int s = g % P.stages;
                 const uint32_t it = (uint32_t)(g / P.stages);
-                if (MODE == 0 && kb + 1 < nkb) dense_load(P, rows, kb + 1, tid, nxt);   // prefetch next K-block
+                if (MODE == 0 && kb + 1 < nkb) dense_load_any(P, rows, kb + 1, tid, nxt);   // prefetch next K-block
                 mbar_wait(bar_empty0 + 8 * s, (it & 1) ^ 1);
                 uint8_t* a_hi = smem + (size_t)s * stage_bytes;
                 uint8_t* a_lo = a_hi + A_TILE_BYTES;
@@ -473,10 +530,11 @@ extern "C" int dh_tc_k_pad(int k) { return (k + tc::BK - 1) / tc::BK * tc::BK; }
 bool dh_tc_supported(const ConvParams& p, const dh_packed_w* packed, bool separable) {
     if (!packed || !packed->hi) return false;
     if (p.M < 1) return false;
-    if ((reinterpret_cast<uintptr_t>(p.x) & 15) != 0) return false;
+    const bool x16 = (reinterpret_cast<uintptr_t>(p.x) & 15) == 0;
+    if (separable && !x16) return false;
     const int K = separable ? p.Cin : p.kh * p.kw * p.Cin;
     if (packed->k != dh_tc_k_pad(K) || packed->cout_pad != dh_tc_cout_pad(p.Cout)) return false;
-    if (p.pre_scale && ((reinterpret_cast<uintptr_t>(p.pre_scale) & 15) || (reinterpret_cast<uintptr_t>(p.pre_shift) & 15)))
+    if (separable && p.pre_scale && ((reinterpret_cast<uintptr_t>(p.pre_scale) & 15) || (reinterpret_cast<uintptr_t>(p.pre_shift) & 15)))
         return false;
     if ((int64_t)p.N * p.H * p.W * p.ldx >= (1ll << 31)) return false;    // int32 pixel*ld products in the producers
     if (separable) {
@@ -489,8 +547,13 @@ bool dh_tc_supported(const ConvParams& p, const dh_packed_w* packed, bool separa
         if (p.M % (4 * p.W) != 0) return false;
         return true;
     }
-    if ((p.Cin & 3) || (p.ldx & 3)) return false;
+    // dense: any Cin / alignment (the producer falls back to a scalar gather: dh_tc_scalar_gather)
     return true;
+}
+
+static bool dh_tc_scalar_gather(const ConvParams& p) {
+    return (p.Cin & 3) || (p.ldx & 3) || (reinterpret_cast<uintptr_t>(p.x) & 15) ||
+           (p.pre_scale && ((reinterpret_cast<uintptr_t>(p.pre_scale) & 15) || (reinterpret_cast<uintptr_t>(p.pre_shift) & 15)));
 }
 
 int dh_launch_conv_tc(dh_ctx* ctx, const ConvParams& p, const dh_packed_w* packed, bool separable, int precision,
@@ -505,7 +568,7 @@ int dh_launch_conv_tc(dh_ctx* ctx, const ConvParams& p, const dh_packed_w* packe
     int gy;
     tile_n(p.Cout, &P.bn_cta, &gy, &P.nsub, &P.nw);
     P.precision = (precision == 1) ? 1 : 3;
-    P.ks = separable ? p.kh : 0;
+    P.ks = separable ? p.kh : (dh_tc_scalar_gather(p) ? -1 : 0);
     plan_tmem(P);
     P.dbg = 0;
     P.n_mtiles = (p.M + BM - 1) / BM;

@@ -411,12 +411,20 @@ extern "C" int dh_softargmax2d_ctx_f32(dh_ctx* ctx, const dh_view* h, int nj, in
     return launch_sam(ctx, p, stream, "dh_softargmax2d_ctx_f32");
 }
 
+bool dh_sam3d_stream_supported(const dh_view* h, int nj, int depth_maps);
+int dh_sam3d_stream_launch(dh_ctx* ctx, const dh_view* h, int nj, int depth_maps, float vis_scale, float* out_pose,
+                           float* out_vis, void* stream);
+
 static int launch_sam3d(dh_ctx* ctx, const dh_view* h, int nj, int depth_maps, float vis_scale, float* out_pose,
                         float* out_vis, const dh_view* prob_out, void* stream, const char* who) {
     DH_CHECK_ARG(ctx && h && h->p && out_pose && out_vis, "%s: NULL argument", who);
     DH_CHECK_ARG(nj >= 1 && depth_maps >= 1 && h->c == nj * depth_maps,
                  "%s: C=%d is not depth_maps*nj = %d*%d", who, h->c, depth_maps, nj);
     DH_CHECK_ARG(h->h >= 2 && h->w >= 2, "%s: maps must be at least 2x2 (got %dx%d)", who, h->h, h->w);
+    // large dense volumes: the cluster-split streaming kernel (softargmax_stream.cu); the probability export of the
+    // merge model and odd shapes stay on the staged kernel below
+    if (!(prob_out && prob_out->p) && ctx->sam3d_stream && dh_sam3d_stream_supported(h, nj, depth_maps))
+        return dh_sam3d_stream_launch(ctx, h, nj, depth_maps, vis_scale, out_pose, out_vis, stream);
     const int T = 512, C = h->c, P = h->h * h->w;
     DH_CHECK_ARG(C <= 2 * T && nj <= T, "%s: too many channels", who);
     Sam3dParams p;

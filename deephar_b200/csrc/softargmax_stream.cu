@@ -282,3 +282,250 @@ int dh_sam_stream_launch(dh_ctx* ctx, const dh_view* h, int nj, int n_ctx, float
     sam_stream_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(p);
     DH_LAUNCH_EPILOGUE(ctx, 1);
 }
+
+// =====================================================================================================
+// Volumetric (3-D) head, streaming version: reception.py:193-222 pose_regression_3d (+ the merge model's
+// vis_scale = 2, action.py:291-292).  h (N,H,W,D*nj), channel = d*nj + j, 1 114 112 B per frame at C3.
+//
+// A frame is split over a CLUSTER of 4 CTAs (pixel quarters): with one CTA per frame the b32 step of C3 would
+// keep 32 of 148 SMs busy.  Each CTA streams its 256 pixels through a 4-stage ring of 16-pixel chunks (1-D TMA
+// bulk copies, ~70 KB in flight per CTA, two CTAs per SM) and accumulates on the fly
+//   hxy[p][j] = mean_d h[p][d*nj+j]   (complete for its own pixels -> kept in shared memory, 17 KB)
+//   hz[c]    += h[p][c]               (partial sums over its pixels)
+// then reduces hxy to per-joint online-softmax statistics (max, sum e, sum e*x, sum e*y).  After a cluster
+// barrier rank 0 reads the other CTAs' partials over distributed shared memory, merges them, runs the 1-D
+// soft-argmax over depth and writes (x, y, z) and the visibility: 17 x 4 floats per frame, nothing else.
+// =====================================================================================================
+namespace sam3ds {
+using sstream::bulk_g2s;
+using sstream::mbar_arrive;
+using sstream::mbar_expect_tx;
+using sstream::mbar_init;
+using sstream::mbar_wait;
+using sstream::smem_u32;
+
+constexpr int PXC = 16;        // pixels per chunk
+constexpr int STAGES = 4;
+constexpr int CL = 4;          // CTAs per frame (cluster size)
+constexpr int PARTS = 16;      // pixel partitions of the per-joint reduction
+
+struct Params {
+    const float* h;
+    int N, H, W, nj, D;
+    float vis_scale;
+    float* out_pose;           // (N, nj, 3)
+    float* out_vis;            // (N, nj, 1)
+    int ncons;                 // consumer threads (multiple of 32): >= max(PXC * nj, C)
+};
+
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float ld_peer(const float* local, uint32_t rank) {
+    uint32_t a;
+    float v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(a) : "r"(smem_u32(local)), "r"(rank));
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ float gridv(int i, int n) {      // np.linspace(0, 1, n)[i] as float32 (utils/math.py:6-19)
+    const double step = n > 1 ? 1.0 / (double)(n - 1) : 0.0;
+    return (n > 1 && i == n - 1) ? 1.0f : (float)(i * step);
+}
+
+__global__ void __launch_bounds__(512) sam3d_stream_kernel(Params p) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    const int nj = p.nj, D = p.D, C = nj * D, P = p.H * p.W;
+    const int PL = P / CL;                         // pixels of this CTA
+    const int nchunks = PL / PXC;
+    const int tid = threadIdx.x;
+    const uint32_t rank = cluster_rank();
+    const int n = blockIdx.y;
+    float* ring = reinterpret_cast<float*>(smem_raw);                 // [STAGES][PXC][C]
+    float* s_hxy = ring + (size_t)STAGES * PXC * C;                   // [PL][nj]
+    float* s_hz = s_hxy + (size_t)PL * nj;                            // [C]   partial sums over this CTA's pixels
+    float* s_st = s_hz + C;                                           // [4][nj]: m, s, sx, sy of this CTA's pixels
+    float* s_part = s_st + 4 * nj;                                    // [PARTS][4][nj]
+    float* s_tot = s_part + PARTS * 4 * nj;                           // [C]   rank 0: hz over the whole frame
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_tot + C + ((PL * nj + 2 * C + 4 * nj + PARTS * 4 * nj) & 1));
+    const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + STAGES);
+    const int ncons = p.ncons;
+    const uint32_t chunk_bytes = (uint32_t)(PXC * C) * 4u;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, ncons >> 5);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (tid >= ncons) {
+        // ===================== producer (one thread of the last warp) =====================
+        if (tid == ncons) {
+            const float* src = p.h + ((size_t)n * P + (size_t)rank * PL) * C;
+            for (int i = 0; i < nchunks; ++i) {
+                const int s = i % STAGES;
+                const uint32_t it = (uint32_t)(i / STAGES);
+                mbar_wait(bar_empty + 8 * s, (it & 1) ^ 1);
+                mbar_expect_tx(bar_full + 8 * s, chunk_bytes);
+                bulk_g2s(smem_u32(ring + (size_t)s * PXC * C), src + (size_t)i * PXC * C, chunk_bytes, bar_full + 8 * s);
+            }
+        }
+    } else {
+        // ===================== consumers =====================
+        const int pa = tid / nj, ja = tid - pa * nj;       // role A: (chunk pixel, joint) -> mean over depth
+        const bool role_a = tid < PXC * nj, role_b = tid < C;
+        const float inv_d = 1.0f / (float)D;
+        float hz_acc = 0.f;
+        for (int i = 0; i < nchunks; ++i) {
+            const int s = i % STAGES;
+            mbar_wait(bar_full + 8 * s, (uint32_t)(i / STAGES) & 1);
+            const float* ck = ring + (size_t)s * PXC * C;
+            if (role_a) {
+                float a = 0.f;
+                for (int d = 0; d < D; ++d) a += ck[pa * C + d * nj + ja];
+                s_hxy[(i * PXC + pa) * nj + ja] = a * inv_d;
+            }
+            if (role_b) {
+                float a = 0.f;
+#pragma unroll
+                for (int q = 0; q < PXC; ++q) a += ck[q * C + tid];
+                hz_acc += a;
+            }
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(bar_empty + 8 * s);
+        }
+        if (role_b) s_hz[tid] = hz_acc;
+        asm volatile("bar.sync 1, %0;" ::"r"(ncons) : "memory");
+        // per-joint statistics of this CTA's pixels: PARTS partitions, then one combine
+        if (tid < PARTS * nj) {
+            const int j = tid % nj, part = tid / nj;
+            float m = -FLT_MAX;
+            for (int px = part; px < PL; px += PARTS) m = fmaxf(m, s_hxy[px * nj + j]);
+            float sum = 0.f, sx = 0.f, sy = 0.f;
+            for (int px = part; px < PL; px += PARTS) {
+                const int gp = (int)rank * PL + px;
+                const int row = gp / p.W, col = gp - row * p.W;
+                const float e = expf(s_hxy[px * nj + j] - m);
+                sum += e;
+                sx = fmaf(e, gridv(col, p.W), sx);
+                sy = fmaf(e, gridv(row, p.H), sy);
+            }
+            s_part[(part * 4 + 0) * nj + j] = m;
+            s_part[(part * 4 + 1) * nj + j] = sum;
+            s_part[(part * 4 + 2) * nj + j] = sx;
+            s_part[(part * 4 + 3) * nj + j] = sy;
+        }
+        asm volatile("bar.sync 1, %0;" ::"r"(ncons) : "memory");
+        if (tid < nj) {
+            float M = -FLT_MAX;
+            for (int q = 0; q < PARTS; ++q) M = fmaxf(M, s_part[(q * 4 + 0) * nj + tid]);
+            float S = 0.f, SX = 0.f, SY = 0.f;
+            for (int q = 0; q < PARTS; ++q) {
+                const float sc = expf(s_part[(q * 4 + 0) * nj + tid] - M);
+                S = fmaf(s_part[(q * 4 + 1) * nj + tid], sc, S);
+                SX = fmaf(s_part[(q * 4 + 2) * nj + tid], sc, SX);
+                SY = fmaf(s_part[(q * 4 + 3) * nj + tid], sc, SY);
+            }
+            s_st[0 * nj + tid] = M;
+            s_st[1 * nj + tid] = S;
+            s_st[2 * nj + tid] = SX;
+            s_st[3 * nj + tid] = SY;
+        }
+    }
+    cluster_sync();                       // every CTA's s_st / s_hz is complete and visible cluster-wide
+    if (rank == 0) {
+        if (tid < C) {
+            float a = 0.f;
+            for (uint32_t r = 0; r < CL; ++r) a += ld_peer(s_hz + tid, r);
+            s_tot[tid] = a / (float)P;                                  // hz = mean over all pixels
+        }
+        __syncthreads();
+        if (tid < nj) {
+            float M = -FLT_MAX;
+            for (uint32_t r = 0; r < CL; ++r) M = fmaxf(M, ld_peer(s_st + 0 * nj + tid, r));
+            float S = 0.f, SX = 0.f, SY = 0.f;
+            for (uint32_t r = 0; r < CL; ++r) {
+                const float sc = expf(ld_peer(s_st + 0 * nj + tid, r) - M);
+                S = fmaf(ld_peer(s_st + 1 * nj + tid, r), sc, S);
+                SX = fmaf(ld_peer(s_st + 2 * nj + tid, r), sc, SX);
+                SY = fmaf(ld_peer(s_st + 3 * nj + tid, r), sc, SY);
+            }
+            const float den = fmaxf(S, 1e-7f);                          // activations.py:12 clip of the denominator
+            // zSAM: blocks.py:288-303 -- softmax over depth, grid (k + 0.5) / D (layers.py:141-146)
+            float zm = -FLT_MAX;
+            for (int d = 0; d < D; ++d) zm = fmaxf(zm, s_tot[d * nj + tid]);
+            const double start = 1.0 / (2.0 * D), step = D > 1 ? ((1.0 - start) - start) / (double)(D - 1) : 0.0;
+            float zs = 0.f, ze = 0.f;
+            for (int d = 0; d < D; ++d) {
+                const float e = expf(s_tot[d * nj + tid] - zm);
+                const float g = (D > 1 && d == D - 1) ? (float)(1.0 - start) : (float)(d * step + start);
+                zs += e;
+                ze = fmaf(e, g, ze);
+            }
+            float* o = p.out_pose + ((size_t)n * nj + tid) * 3;
+            o[0] = SX / den;
+            o[1] = SY / den;
+            o[2] = ze / zs;
+            p.out_vis[(size_t)n * nj + tid] = 1.f / (1.f + expf(-p.vis_scale * (M + zm)));   // max_p hxy == M
+        }
+    }
+    cluster_sync();                       // peers keep their shared memory alive until rank 0 has read it
+}
+
+}  // namespace sam3ds
+
+bool dh_sam3d_stream_supported(const dh_view* h, int nj, int depth_maps) {
+    using namespace sam3ds;
+    const int C = nj * depth_maps, P = h->h * h->w;
+    if (h->ld != h->c || (C & 3) || (reinterpret_cast<uintptr_t>(h->p) & 15)) return false;
+    if (P % (CL * PXC) != 0 || h->h < 2 || h->w < 2) return false;
+    if (PXC * nj > 480 || C > 480 || PARTS * nj > 480) return false;
+    return true;
+}
+
+int dh_sam3d_stream_launch(dh_ctx* ctx, const dh_view* h, int nj, int depth_maps, float vis_scale, float* out_pose,
+                           float* out_vis, void* stream) {
+    using namespace sam3ds;
+    Params p;
+    p.h = h->p; p.N = h->n; p.H = h->h; p.W = h->w; p.nj = nj; p.D = depth_maps; p.vis_scale = vis_scale;
+    p.out_pose = out_pose; p.out_vis = out_vis;
+    const int C = nj * depth_maps, PL = h->h * h->w / CL;
+    int need = PXC * nj > C ? PXC * nj : C;
+    if (PARTS * nj > need) need = PARTS * nj;
+    p.ncons = (need + 31) / 32 * 32;
+    const int threads = p.ncons + 32;
+    const size_t smem = ((size_t)STAGES * PXC * C + (size_t)PL * nj + 2 * C + 4 * nj + PARTS * 4 * nj + 2) * 4 + 2 * STAGES * 8 + 128;
+    static size_t cur = 0;
+    if (smem > cur) {
+        cudaError_t e = cudaFuncSetAttribute(sam3d_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            dh_set_error("dh_sam3d_stream_launch: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            return (int)e;
+        }
+        cur = smem;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(CL, h->n);
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, sam3d_stream_kernel, p);
+    if (e != cudaSuccess) {
+        dh_set_error("dh_sam3d_stream_launch: %s", cudaGetErrorString(e));
+        return (int)e;
+    }
+    DH_LAUNCH_EPILOGUE(ctx, 1);
+}

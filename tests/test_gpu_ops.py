@@ -7,6 +7,7 @@ import zlib
 import numpy as np
 import pytest
 
+from deephar_b200 import _ffi  # noqa: E402
 from oracle import ops_np
 from oracle import reception as oracle_reception
 
@@ -277,16 +278,42 @@ def test_softargmax2d_context(dev, shape, nj, nctx):
     _close(vo.cpu().numpy(), vis, 3e-6)
 
 
-@pytest.mark.parametrize('shape,nj,D', [((2, 32, 32, 272), 17, 16), ((3, 8, 8, 30), 5, 6)])
-def test_softargmax3d(dev, shape, nj, D):
+@pytest.mark.parametrize('shape,nj,D', [((2, 32, 32, 272), 17, 16), ((3, 8, 8, 30), 5, 6), ((5, 8, 8, 160), 20, 8),
+                                        ((3, 16, 16, 272), 17, 16)])
+@pytest.mark.parametrize('stream', [1, 0])
+def test_softargmax3d(dev, shape, nj, D, stream):
+    """stream = 1: the cluster-split streaming kernel (softargmax_stream.cu) where it applies (dense volumes whose
+    pixel count splits into 4 x 16-pixel chunks, C % 4 == 0); 0: the staged one-CTA-per-frame kernel."""
     rng = np.random.default_rng(13)
     h = rng.standard_normal(shape) * 3.0
+    h[0, 3, 5, 2 * nj + 1] += 40.0                       # a planted peak: joint 1 at depth slice 2, pixel (3, 5)
     pose, vis, _ = oracle_reception.pose_regression_3d(ops_np, h, nj, D)
     po, vo = dev.empty(shape[0], nj, 3), dev.empty(shape[0], nj, 1)
     hv = dev.view(dev.put(h))
-    dev.call('dh_softargmax3d_f32', C.byref(hv), nj, D, po.data_ptr(), vo.data_ptr())
+    _ffi.check(dev.lib.dh_set_option(dev.ctx.handle, b'sam3d_stream', stream))
+    try:
+        dev.call('dh_softargmax3d_f32', C.byref(hv), nj, D, po.data_ptr(), vo.data_ptr())
+    finally:
+        _ffi.check(dev.lib.dh_set_option(dev.ctx.handle, b'sam3d_stream', 1))
     _close(po.cpu().numpy(), pose, 3e-6)
     _close(vo.cpu().numpy(), vis, 3e-6)
+
+
+def test_softargmax3d_ex_merge_variant(dev):
+    """action.py:291-295: visible = sigmoid(2 * (max hxy + max hz)) and hs = channel_softmax_2d(hxy)."""
+    rng = np.random.default_rng(15)
+    nj, D = 20, 8
+    h = rng.standard_normal((3, 16, 16, nj * D)) * 2.0
+    pose, _, hxy = oracle_reception.pose_regression_3d(ops_np, h, nj, D)
+    h5 = h.reshape(3, 16, 16, D, nj)
+    vis = 1.0 / (1.0 + np.exp(-2.0 * (h5.mean(3).max((1, 2)) + h5.mean((1, 2)).max(1))))[..., None]
+    prob = ops_np.channel_softmax_2d(hxy)
+    po, vo, pr = dev.empty(3, nj, 3), dev.empty(3, nj, 1), dev.empty(3, 16, 16, nj)
+    hv, pv = dev.view(dev.put(h)), dev.view(pr)
+    dev.call('dh_softargmax3d_ex_f32', C.byref(hv), nj, D, C.c_float(2.0), po.data_ptr(), vo.data_ptr(), C.byref(pv))
+    _close(po.cpu().numpy(), pose, 3e-6)
+    _close(vo.cpu().numpy(), vis, 3e-6)
+    _close(pr.cpu().numpy(), prob, 3e-6)
 
 
 def test_kron_maxmin_softmax_mask(dev):

@@ -62,6 +62,12 @@ CONV_CASES = [
     (5, 8, 8, 480, 16, (1, 1), (1, 1), True),        # SPNet heat-map conv at 8x8: odd frame count, 64-pixel virtual rows
     (3, 8, 8, 64, 64, (3, 3), (1, 1), True),         # two frames per tile, tail tile, BN prologue mask
     (7, 4, 4, 96, 32, (3, 3), (1, 1), True),         # 4x4 maps are not taken by the patch kernel (falls to conv_tc)
+    # --- ragged channel counts: conv_tc.cu's scalar-gather producer (no CUDA-core fallback) ---
+    (1, 64, 64, 3, 64, (7, 7), (2, 2), False),       # SPNet first conv: 7x7 stride 2 on RGB
+    (2, 32, 32, 17, 288, (1, 1), (1, 1), True),      # heat-map re-injection, 17 joints
+    (1, 16, 16, 34, 384, (1, 1), (1, 1), True),      # heat-maps + depth maps
+    (2, 8, 10, 15, 160, (3, 3), (1, 1), True),       # action head on (frames, joints) maps
+    (1, 5, 7, 2, 8, (3, 1), (1, 1), False),          # PoseAR first conv: 2 input channels
 ]
 
 
@@ -223,6 +229,18 @@ def test_tc_channel_views(dev):
     got = cat.cpu().numpy()
     assert _err(got[..., 4:36], ref) <= TOL3
     assert np.all(got[..., :4] == 7.0) and np.all(got[..., 36:] == 7.0)
+    # a slice at a channel offset that is not 16-byte aligned (17-joint heat-maps inside a concat): the
+    # tensor-core kernel's scalar gather takes it, still no CUDA-core fallback
+    big = rng.standard_normal((2, 16, 16, 51))
+    wt = rng.standard_normal((1, 1, 34, 48)) / 6.0
+    ref = ops_np.conv2d(big[..., 17:51], wt)
+    out = dev.empty(2, 16, 16, 48)
+    pk = _packed(dev, wt.reshape(34, 48))
+    xv, ov = dev.view(dev.put(big), 17, 51), dev.view(out)
+    dev.lib.dh_fallback_count(dev.ctx.handle, 1)
+    dev.call('dh_conv2d_f32', C.byref(xv), dev.put(wt).data_ptr(), C.byref(pk), C.byref(d), C.byref(ov))
+    assert dev.lib.dh_last_conv_path(dev.ctx.handle) == 1 and dev.lib.dh_fallback_count(dev.ctx.handle, 0) == 0
+    assert _err(out.cpu().numpy(), ref) <= TOL3
 
 
 @pytest.mark.parametrize('share', [1, 0])
