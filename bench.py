@@ -47,6 +47,14 @@ METRIC = 'frames/sec (256x256, 16-frame clips, b32)'
 HEADLINE = 'reception2d_8blk_k5_j16 (BASELINE configs[1] model) x 32 clips x 16 frames'
 
 
+_T0 = time.time()
+
+
+def note(msg):
+    """progress line on stderr (the JSON line on stdout stays alone)"""
+    print('[bench %6.1fs] %s' % (time.time() - _T0, msg), file=sys.stderr, flush=True)
+
+
 def measured_peaks():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(path):
@@ -216,8 +224,15 @@ def cpu_port(iters_b32, iters_b1, warm_b32=1, warm_b1=3):
     from deephar_b200 import reception
     from oracle import ops_torch, synth
     from oracle import reception as oracle_reception
+    # all PHYSICAL cores, set explicitly: torchrun exports OMP_NUM_THREADS=1 (round 1's arm ran single-threaded under
+    # it), and one thread per hyper-thread (os.cpu_count() = 128 on the B200 hosts) makes oneDNN ~100x slower
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)                 # torchrun exports OMP_NUM_THREADS=1: undo it explicitly
+    try:
+        import psutil
+        threads = psutil.cpu_count(logical=False) or max(1, cores // 2)
+    except Exception:
+        threads = max(1, cores // 2)
+    torch.set_num_threads(threads)
     m = reception.build((256, 256, 3), **MODEL_KW).init_synthetic_weights(1234)
     table = m.get_weights()
 
@@ -363,6 +378,7 @@ def main():
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
 
     peaks = measured_peaks()
+    note('building %s' % args.workload)
     model, clip_model, wl_name = build_workload(args.workload)
     model.use_cuda_graph = not args.no_graph
     items_global = CLIPS
@@ -378,6 +394,7 @@ def main():
     n_frames = CLIPS * FRAMES                       # global frames per step (strong scaling: fixed)
     micro = run.micro_items * (FRAMES if clip_model else 1)
 
+    note('model built, shard %d frames, micro-batch %d' % (run.frames_local, micro))
     # ---- value: device-resident, CUDA events, max over ranks ------------------------------------------------------
     for _ in range(2):
         run.step(which)                             # first uses: plain launches, then the graph capture
@@ -389,6 +406,7 @@ def main():
     launches = int(getattr(model, 'launch_total', 0)) * args.steps // max(1, args.steps + args.warmup)
     value = n_frames / (ms_step / 1000.0)
 
+    note('value: %.1f frames/s (%.2f ms/step)' % (value, ms_step))
     # ---- e2e: public API, pinned host input, H2D + D2H inside the timed region ----------------------------------------
     x_np = run.x_host.numpy()
     bs = run.micro_items
@@ -409,6 +427,7 @@ def main():
     outs = outs if isinstance(outs, list) else [outs]
     d2h = sum(int(np.prod(o.shape)) * 4 for o in outs)
 
+    note('e2e: %.1f frames/s' % e2e_fps)
     # ---- per-kernel profile (CUDA events around every launch of one extra step) ------------------------------------
     xs = run.x_dev[run.spans[0][0]:run.spans[0][1]]
     prof = model.profile(xs)
@@ -449,6 +468,7 @@ def main():
                                  key=lambda r: -r[1])[:10],
     }
 
+    note('kernel profile done')
     # ---- secondary: soft-argmax micro-benchmarks, the other BASELINE configs, the weak-scaling number ---------------
     if not args.no_secondary:
         sec = {}
@@ -466,10 +486,11 @@ def main():
         model._bound = {}
         torch.cuda.empty_cache()
         if args.workload == 'reception2d':
-            for key, wl, items, per, note in (
+            for key, wl, items, per, desc in (
                     ('C3', 'reception3d', 32, 1, 'H36M 3-D pose, b32 frames (BASELINE configs[2])'),
                     ('C4', 'spnet_penn', 16, FRAMES, 'PennAction pose+action, 16 clips x 16 frames (BASELINE configs[3])'),
                     ('C5', 'spnet_ntu', 64, FRAMES, 'NTU 3-D pose+action, 64 clips x 16 frames, action all-gather (BASELINE configs[4])')):
+                note('secondary %s: building %s' % (key, wl))
                 m2, clip2, name2 = build_workload(wl)
                 m2.use_cuda_graph = not args.no_graph
                 r2 = Runner(torch, m2, clip2, items, per, rank, world, args.micro_batch, args.precision)
@@ -477,8 +498,9 @@ def main():
                 w2 = 'action' if clip2 else 'pose'
                 assert r2.items_local > 0, 'every rank needs a shard (the exchange step is a collective)'
                 ms = timed_steps(torch, dist, world, lambda: r2.step(w2), 3, 3)
+                note('secondary %s: %.2f ms/step' % (key, ms))
                 fr = items * per
-                sec[key] = {'config': note, 'model': name2, 'frames_per_step': fr, 'frames_per_gpu': r2.frames_local,
+                sec[key] = {'config': desc, 'model': name2, 'frames_per_step': fr, 'frames_per_gpu': r2.frames_local,
                             'value': fr / (ms / 1000.0), 'unit': 'frames/s', 'ms_per_step': ms,
                             'conv_tflops': m2.conv_flops_per_frame() * fr / (ms / 1000.0) / 1e12 / world,
                             'launches_per_forward': len(m2._bind(r2.micro_items * (FRAMES if clip2 else 1)).calls)}
@@ -487,6 +509,7 @@ def main():
         line['secondary'] = sec
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        note('cpu baseline (torch-CPU port, %d host CPUs)' % (os.cpu_count() or 1))
         r = cpu_port(iters_b32=3, iters_b1=5, warm_b32=1, warm_b1=2)
         med32, med1 = float(np.median(r['b32_times'])), float(np.median(r['b1_times']))
         line['cpu_baseline'] = {'value': 32.0 / med32, 'unit': 'frames/s', 'cores': r['threads'], 'kind': 'port',
@@ -494,6 +517,7 @@ def main():
                                           'median of 5 = %.3f s; torch-CPU fp32 port of the Keras graph (oracle/), '
                                           '%d threads on %d host CPUs' % (med32, med1, r['threads'], r['cores']),
                                 'c1_b1_latency_s': med1}
+    note('done')
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -23,62 +23,48 @@ def add_tensorlist(t):
 def residual_unit(x, kernel_size, strides=(1, 1), out_size=None,
                   convtype='depthwise', shortcut_act=True,
                   features_div=2, name=None):
-    """(Separable) Residual Unit -- common.py:25-67.  BatchNormalization here is the Keras
-    default (scale=True)."""
+    """(Separable) Residual Unit -- common.py:25-67.  BatchNormalization here is the Keras default
+    (scale=True).  Two shapes of the same unit:
+      * shape-preserving: shortcut = the raw input, body = BN -> ReLU -> conv;
+      * projecting (width or stride changes): BN first, shortcut = 1x1 conv of its (activated) output,
+        body = ReLU -> conv on the same normalised tensor.
+    convtype 'depthwise': one separable conv; 'normal': 1x1 bottleneck (width / features_div) -> BN -> ReLU -> kxk."""
     assert convtype in ['depthwise', 'normal'], 'Invalid convtype ({}).'.format(convtype)
+    width = x.channels
+    out_size = width if out_size is None else out_size
+    projecting = width != out_size or tuple(strides) != (1, 1)
 
-    num_filters = x.channels
-    if out_size is None:
-        out_size = num_filters
-
-    skip_conv = (num_filters != out_size) or (tuple(strides) != (1, 1))
-
-    if skip_conv:
-        x = BatchNormalization(x, name=appstr(name, '_bn1'))
-
-    shortcut = x
-    if skip_conv:
-        if shortcut_act:
-            shortcut = relu(shortcut, name=appstr(name, '_shortcut_act'))
-        shortcut = conv2d(shortcut, out_size, (1, 1), strides=strides,
-                          name=appstr(name, '_shortcut_conv'))
-
-    if not skip_conv:
-        x = BatchNormalization(x, name=appstr(name, '_bn1'))
-    x = relu(x, name=appstr(name, '_act1'))
-
-    if convtype == 'depthwise':
-        x = sepconv2d(x, out_size, kernel_size, strides=strides, name=appstr(name, '_conv1'))
+    normed = BatchNormalization(x, name=appstr(name, '_bn1'))
+    if projecting:
+        shortcut = relu(normed, name=appstr(name, '_shortcut_act')) if shortcut_act else normed
+        shortcut = conv2d(shortcut, out_size, (1, 1), strides=strides, name=appstr(name, '_shortcut_conv'))
     else:
-        x = conv2d(x, int(out_size / features_div), (1, 1), name=appstr(name, '_conv1'))
-        x = BatchNormalization(x, name=appstr(name, '_bn2'))
-        x = relu(x, name=appstr(name, '_act2'))
-        x = conv2d(x, out_size, kernel_size, strides=strides, name=appstr(name, '_conv2'))
+        shortcut = x
+    body = relu(normed, name=appstr(name, '_act1'))
+    if convtype == 'depthwise':
+        body = sepconv2d(body, out_size, kernel_size, strides=strides, name=appstr(name, '_conv1'))
+    else:
+        body = conv2d(body, int(out_size / features_div), (1, 1), name=appstr(name, '_conv1'))
+        body = relu(BatchNormalization(body, name=appstr(name, '_bn2')), name=appstr(name, '_act2'))
+        body = conv2d(body, out_size, kernel_size, strides=strides, name=appstr(name, '_conv2'))
+    return add([shortcut, body])
 
-    x = add([shortcut, x])
-    return x
+
+def _rescaling_unit(resample, x, cfg, out_size, name):
+    if cfg.downsampling_type != 'maxpooling':
+        raise NotImplementedError("downsampling_type='conv' is not used by the reference scripts")
+    return residual_unit(resample(x, (2, 2)), cfg.kernel_size, out_size=x.channels if out_size is None else out_size,
+                         name=appstr(name, '_r0'))
 
 
 def downscaling_unit(x, cfg, out_size=None, name=None):
     """common.py:70-86 (downsampling_type 'maxpooling'; 'conv' is never used by a shipped script)."""
-    if cfg.downsampling_type != 'maxpooling':
-        raise NotImplementedError("downsampling_type='conv' is not used by the reference scripts")
-    if out_size is None:
-        out_size = x.channels
-    x = maxpooling2d(x, (2, 2))
-    x = residual_unit(x, cfg.kernel_size, out_size=out_size, strides=(1, 1), name=appstr(name, '_r0'))
-    return x
+    return _rescaling_unit(maxpooling2d, x, cfg, out_size, name)
 
 
 def upscaling_unit(x, cfg, out_size=None, name=None):
     """common.py:89-108."""
-    if cfg.downsampling_type != 'maxpooling':
-        raise NotImplementedError("downsampling_type='conv' is not used by the reference scripts")
-    if out_size is None:
-        out_size = x.channels
-    x = upsampling2d(x, (2, 2))
-    x = residual_unit(x, cfg.kernel_size, out_size=out_size, name=appstr(name, '_r0'))
-    return x
+    return _rescaling_unit(upsampling2d, x, cfg, out_size, name)
 
 
 # Aliases (common.py:159-162).

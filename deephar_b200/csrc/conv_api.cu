@@ -12,6 +12,11 @@ extern "C" int dh_conv2d_f32(dh_ctx* ctx, const dh_view* x, const float* w_hwio,
     if (rc) return rc;
     p.w = w_hwio;
     cudaStream_t s = (cudaStream_t)stream;
+    if (dh_conv_smallk_ok(p)) {          // the 3x3x3 first conv of the stem: direct small-K kernel (conv_simt.cu)
+        ctx->last_conv_path = 0;
+        dh_launch_conv_simt(p, s);
+        DH_LAUNCH_EPILOGUE(ctx, 1);
+    }
     if (ctx->pw_smallk && dh_pw_smallk_supported(p)) {
         rc = dh_launch_pw_smallk(p, ctx->num_sms, s);
         if (rc) return rc;

@@ -12,76 +12,56 @@ from .layers import (MaxPooling2D, UpSampling2D, act_conv, act_conv_bn, add, con
 
 
 def _sepconv_residual(x, out_size, name, kernel_size=(3, 3)):
-    """reception.py:43-59."""
-    shortcut_name = name + '_shortcut'
-    reduce_name = name + '_reduce'
+    """reception.py:43-59: pre-activated separable residual unit.  The shortcut is the input itself when the
+    width is kept, else a 1x1 projection; a narrowing unit first reduces the width with another 1x1."""
+    width = x.channels
+    ident = x if width == out_size else act_conv_bn(x, out_size, (1, 1), name=name + '_shortcut')
+    if out_size < width:
+        x = act_conv_bn(x, out_size, (1, 1), name=name + '_reduce')
+    return add([ident, separable_act_conv_bn(x, out_size, kernel_size, name=name)])
 
-    num_filters = x.channels
-    if num_filters == out_size:
-        ident = x
-    else:
-        ident = act_conv_bn(x, out_size, (1, 1), name=shortcut_name)
 
-    if out_size < num_filters:
-        x = act_conv_bn(x, out_size, (1, 1), name=reduce_name)
-
-    x = separable_act_conv_bn(x, out_size, kernel_size, name=name)
-    x = add([ident, x])
+def _chain(x, steps):
+    """Apply [(layer helper, filters, kernel size[, strides])...] in sequence (layers are created in list order,
+    which is what numbers keras' auto-named conv2d_N / batch_normalization_N layers)."""
+    for step in steps:
+        fn, filters, size = step[:3]
+        x = fn(x, filters, size, strides=step[3]) if len(step) > 3 else fn(x, filters, size)
     return x
 
 
 def _stem(inp, old_model=False):
-    """reception.py:61-98."""
+    """reception.py:61-98 (Inception-v4 style stem, 256x256x3 -> 32x32x576): three 3x3 convs, then three
+    two-branch stages whose branches are concatenated, then a widening separable residual."""
     assert not old_model, 'old_model=True is not used by any shipped script and is not supported'
-    g = inp.g
-    with g.scope('Stem'):
-        x = conv_bn_act(inp, 32, (3, 3), strides=(2, 2))
-        x = conv_bn_act(x, 32, (3, 3))
-        x = conv_bn_act(x, 64, (3, 3))
-
-        a = conv_bn_act(x, 96, (3, 3), strides=(2, 2))
-        b = MaxPooling2D(x, (3, 3), strides=(2, 2), padding='same')
-        x = concatenate([a, b])
-
-        a = conv_bn_act(x, 64, (1, 1))
-        a = conv_bn(a, 96, (3, 3))
-        b = conv_bn_act(x, 64, (1, 1))
-        b = conv_bn_act(b, 64, (5, 1))
-        b = conv_bn_act(b, 64, (1, 5))
-        b = conv_bn(b, 96, (3, 3))
-        x = concatenate([a, b])
-
-        a = act_conv_bn(x, 192, (3, 3), strides=(2, 2))
-        b = MaxPooling2D(x, (2, 2), strides=(2, 2))
-        x = concatenate([a, b])
-
-        x = _sepconv_residual(x, 3 * 192, name='sepconv1')
-    return x
+    with inp.g.scope('Stem'):
+        x = _chain(inp, [(conv_bn_act, 32, (3, 3), (2, 2)), (conv_bn_act, 32, (3, 3)), (conv_bn_act, 64, (3, 3))])
+        x = concatenate([conv_bn_act(x, 96, (3, 3), strides=(2, 2)),
+                         MaxPooling2D(x, (3, 3), strides=(2, 2), padding='same')])
+        x = concatenate([_chain(x, [(conv_bn_act, 64, (1, 1)), (conv_bn, 96, (3, 3))]),
+                         _chain(x, [(conv_bn_act, 64, (1, 1)), (conv_bn_act, 64, (5, 1)), (conv_bn_act, 64, (1, 5)),
+                                    (conv_bn, 96, (3, 3))])])
+        x = concatenate([act_conv_bn(x, 192, (3, 3), strides=(2, 2)), MaxPooling2D(x, (2, 2), strides=(2, 2))])
+        return _sepconv_residual(x, 3 * 192, name='sepconv1')
 
 
 def build_reception_block(inp, name, ksize=(3, 3)):
-    """reception.py:101-131."""
-    size = inp.channels
+    """reception.py:101-131: three-level hourglass.  Level 1 keeps the input width, levels 2 and 3 run at half
+    the width on 2x / 4x pooled maps; each level's result is upsampled and added to the level above."""
+    full, half = inp.channels, int(inp.channels / 2)
+
+    def unit(t, width, tag):
+        return _sepconv_residual(t, width, name='sepconv_' + tag, kernel_size=ksize)
+
     with inp.g.scope(name):
-        xi = inp
-        a = _sepconv_residual(xi, size, name='sepconv_l1', kernel_size=ksize)
-
-        low1 = MaxPooling2D(xi, (2, 2))
-        low1 = act_conv_bn(low1, int(size / 2), (1, 1))
-        low1 = _sepconv_residual(low1, int(size / 2), name='sepconv_l2_1', kernel_size=ksize)
-        b = _sepconv_residual(low1, int(size / 2), name='sepconv_l2_2', kernel_size=ksize)
-
-        c = MaxPooling2D(low1, (2, 2))
-        c = _sepconv_residual(c, int(size / 2), name='sepconv_l3_1', kernel_size=ksize)
-        c = _sepconv_residual(c, int(size / 2), name='sepconv_l3_2', kernel_size=ksize)
-        c = _sepconv_residual(c, int(size / 2), name='sepconv_l3_3', kernel_size=ksize)
-        c = UpSampling2D(c, (2, 2))
-
-        b = add([b, c])
-        b = _sepconv_residual(b, size, name='sepconv_l2_3', kernel_size=ksize)
-        b = UpSampling2D(b, (2, 2))
-        x = add([a, b])
-    return x
+        top = unit(inp, full, 'l1')
+        mid_in = unit(act_conv_bn(MaxPooling2D(inp, (2, 2)), half, (1, 1)), half, 'l2_1')
+        mid = unit(mid_in, half, 'l2_2')
+        low = MaxPooling2D(mid_in, (2, 2))
+        for tag in ('l3_1', 'l3_2', 'l3_3'):
+            low = unit(low, half, tag)
+        mid = unit(add([mid, UpSampling2D(low, (2, 2))]), full, 'l2_3')
+        return add([top, UpSampling2D(mid, (2, 2))])
 
 
 def build_sconv_block(inp, name=None, ksize=(3, 3)):
@@ -156,45 +136,29 @@ def build(input_shape, num_joints, dim,
         raise NotImplementedError('export_heatmaps with dim=3 (hxy marginal) is not exported')
 
     g = Graph('ReceptionNet')
-    inp = g.input(tuple(input_shape))
-    outputs = []
-    vfeat = None
+    x = _stem(g.input(tuple(input_shape)), old_model=old_model)
+    width = x.channels
+    outputs, vfeat = [], None
+    for block in range(1, num_blocks + 1):
+        trunk = build_reception_block(x, name='rBlock%d' % block, ksize=ksize)
+        if export_vfeat_block == block:
+            vfeat = trunk
+        feat = build_sconv_block(trunk, name='SepConv%d' % block, ksize=ksize)
+        h = build_regmap_block(feat, num_heatmaps, name='RegMap%d' % block)
 
-    x = _stem(inp, old_model=old_model)
-
-    for bidx in range(num_blocks):
-        block_shape = x.shape
-        x = build_reception_block(x, name='rBlock%d' % (bidx + 1), ksize=ksize)
-
-        if export_vfeat_block == (bidx + 1):
-            vfeat = x
-
-        ident_map = x
-        x = build_sconv_block(x, name='SepConv%d' % (bidx + 1), ksize=ksize)
-        h = build_regmap_block(x, num_heatmaps, name='RegMap%d' % (bidx + 1))
-
-        if dim == 2:
-            if num_context_per_joint is not None:
-                pose, visible, hm = pose_regression_2d_context(h, num_joints,
-                                                               num_context_per_joint, alpha)
-            else:
-                pose, visible, hm = pose_regression_2d(h)
-        else:
+        # parameter-free regression head on the heat-maps (one kernel)
+        if dim == 3:
             pose, visible, hm = pose_regression_3d(h, num_joints, depth_maps)
-
-        if concat_pose_confidence:
-            outputs.append(concatenate([pose, visible]))
+        elif num_context_per_joint is not None:
+            pose, visible, hm = pose_regression_2d_context(h, num_joints, num_context_per_joint, alpha)
         else:
-            outputs.append(pose)
-            outputs.append(visible)
-
+            pose, visible, hm = pose_regression_2d(h)
+        outputs += [concatenate([pose, visible])] if concat_pose_confidence else [pose, visible]
         if export_heatmaps:
             outputs.append(hm)
 
-        if bidx < num_blocks - 1:
-            h = build_fremap_block(h, block_shape[-1], name='fReMap%d' % (bidx + 1))
-            x = add([ident_map, x, h])
-
+        if block < num_blocks:      # re-inject the heat-maps into the feature stream of the next block
+            x = add([trunk, feat, build_fremap_block(h, width, name='fReMap%d' % block)])
     if vfeat is not None:
         outputs.append(vfeat)
 
