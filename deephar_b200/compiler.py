@@ -108,6 +108,19 @@ class _LiveGraph(object):
         self.dead = len(g.nodes) - len(self.nodes)
 
 
+def _up_fusable(ch):
+    """Can this conv chain take one more residual that is upsampled 2x in its epilogue?  Mirrors the C side:
+    TMA-staged separable kernel (conv_sep.cu), output width a multiple of 32, at most one residual so far, and no
+    residual already flagged."""
+    n = ch['conv']
+    if n.op != 'sepconv' or len(ch['res']) > 1 or ch.get('res_up2x'):
+        return False
+    h, w, cin = n.inputs[0].shape
+    a = n.attrs
+    return (a['size'] in ((3, 3), (5, 5)) and a['strides'] == (1, 1) and a['padding'] == 'same' and w == 32 and h % 4 == 0
+            and cin % 32 == 0)
+
+
 def compile_graph(g_full):
     g = _LiveGraph(g_full)
     cons = _consumers(g.nodes)
@@ -152,12 +165,30 @@ def compile_graph(g_full):
     # end tensor feeds it -- also chained adds (residual add followed by a lateral add), as long as
     # the epilogue carries at most two residual operands.
     chain_end = {ch['end'].id: cid for cid, ch in chains.items()}
+    up_claimed = set()     # upsample nodes absorbed by a conv epilogue
     for n in g.nodes:
         if n.op != 'add':
             continue
         if len(n.inputs) == 2 and any(t.node.op == 'upsample' and len(cons[t.id]) == 1 and t.id not in out_ids
                                       for t in n.inputs):
-            continue        # UpSampling2D + add is one kernel of its own (upsample_add)
+            # keras `add([a, UpSampling2D(b)])` (reception.py:122-127).  If `a` is the end of a fused separable conv on
+            # maps whose width is a multiple of 32, the half-resolution `b` becomes the conv's LAST residual operand,
+            # upsampled on the fly by the epilogue (dh_conv_desc.res_up2x) -- otherwise it is a kernel of its own.
+            up = [t for t in n.inputs if t.node.op == 'upsample' and len(cons[t.id]) == 1 and t.id not in out_ids][-1]
+            other = n.inputs[0] if n.inputs[1] is up else n.inputs[1]
+            cid = chain_end.get(other.id)
+            if cid is not None and other.id not in out_ids and len(cons[other.id]) == 1 and _up_fusable(chains[cid]):
+                ch = chains[cid]
+                ch['res'].append(up.node.inputs[0])
+                ch['res_up2x'] = 1 << (len(ch['res']) - 1)
+                up_claimed.add(up.node.id)
+                add_claim[n.id] = cid
+                fused_into[n.id] = cid
+                del chain_end[other.id]
+                chain_end[n.out.id] = cid
+                ch['pos'] = max(ch['pos'], n.id)
+                ch['end'] = n.out
+            continue        # else: UpSampling2D + add is one kernel of its own (upsample_add)
         best = None
         for t in n.inputs:
             cid = chain_end.get(t.id)
@@ -242,7 +273,7 @@ def compile_graph(g_full):
             attrs = dict(n.attrs)
             attrs.update({'pre_relu': ch['pre_relu'], 'pre_bn': ch['pre_bn'].attrs if ch['pre_bn'] else None,
                           'post_bn': ch['post_bn'].attrs if ch['post_bn'] else None,
-                          'post_relu': bool(ch['post_relu']), 'n_res': len(res)})
+                          'post_relu': bool(ch['post_relu']), 'n_res': len(res), 'res_up2x': ch.get('res_up2x', 0)})
             emit(op, [ch['src']] + res, [ch['end']], attrs, ch['pos'])
             continue
         if op in ('bn', 'relu'):
@@ -271,6 +302,8 @@ def compile_graph(g_full):
             continue
         if op == 'upsample':
             # decided when its consumer add is visited; emit lazily below if not fused
+            if n.id in up_claimed:
+                continue
             emit('upsample?', [n.inputs[0]], [n.out], {'node': n.id}, n.id)
             continue
         if op in ('slice', 'concat', 'to_clip'):

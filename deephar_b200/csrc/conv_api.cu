@@ -12,12 +12,12 @@ extern "C" int dh_conv2d_f32(dh_ctx* ctx, const dh_view* x, const float* w_hwio,
     if (rc) return rc;
     p.w = w_hwio;
     cudaStream_t s = (cudaStream_t)stream;
-    if (dh_conv_smallk_ok(p)) {          // the 3x3x3 first conv of the stem: direct small-K kernel (conv_simt.cu)
+    if (!p.up1 && dh_conv_smallk_ok(p)) {          // the 3x3x3 first conv of the stem: direct small-K kernel (conv_simt.cu)
         ctx->last_conv_path = 0;
         dh_launch_conv_simt(p, s);
         DH_LAUNCH_EPILOGUE(ctx, 1);
     }
-    if (ctx->pw_smallk && dh_pw_smallk_supported(p)) {
+    if (ctx->pw_smallk && !p.up1 && dh_pw_smallk_supported(p)) {
         rc = dh_launch_pw_smallk(p, ctx->num_sms, s);
         if (rc) return rc;
         ctx->last_conv_path = 3;
@@ -35,6 +35,7 @@ extern "C" int dh_conv2d_f32(dh_ctx* ctx, const dh_view* x, const float* w_hwio,
         ctx->last_conv_path = 1;
         DH_LAUNCH_EPILOGUE(ctx, 1);
     }
+    DH_CHECK_ARG(!p.up1, "dh_conv2d_f32: an upsampled residual needs a tcgen05 kernel; none takes this shape");
     ctx->last_conv_path = 0;
     if (!dh_conv_smallk_ok(p)) ctx->fallbacks += 1;      // the direct K <= 32 kernel is a specialised path, not a fallback
     dh_launch_conv_simt(p, s);
@@ -65,6 +66,7 @@ extern "C" int dh_sepconv2d_f32(dh_ctx* ctx, const dh_view* x, const float* w_dw
         ctx->last_conv_path = 1;
         DH_LAUNCH_EPILOGUE(ctx, 1);
     }
+    DH_CHECK_ARG(!p.up1, "dh_sepconv2d_f32: an upsampled residual needs a tcgen05 kernel; none takes this shape");
     ctx->last_conv_path = 0;
     ctx->fallbacks += 1;
     // Two-kernel CUDA-core path: depthwise (with the fused pre-ops) into the caller's

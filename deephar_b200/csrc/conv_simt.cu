@@ -199,9 +199,12 @@ int dh_fill_conv_params(ConvParams* p, const dh_view* x, const dh_conv_desc* d, 
                  "%s: output view is (%d,%d,%d,%d), expected (%d,%d,%d,%d)", who, out->n, out->h, out->w,
                  out->c, x->n, ho, wo, cout);
     DH_CHECK_ARG(x->ld >= x->c && out->ld >= out->c, "%s: ld smaller than c", who);
+    DH_CHECK_ARG((d->res_up2x & ~3) == 0 && (d->res_up2x == 0 || d->res_up2x == (1 << (d->n_res - 1))),
+                 "%s: res_up2x may only flag the LAST residual", who);
     for (int i = 0; i < d->n_res; ++i) {
-        DH_CHECK_ARG(d->res[i].p && d->res[i].n == out->n && d->res[i].h == ho && d->res[i].w == wo &&
-                         d->res[i].c == cout,
+        const int up = (d->res_up2x >> i) & 1;
+        DH_CHECK_ARG(d->res[i].p && d->res[i].n == out->n && d->res[i].h * (up ? 2 : 1) == ho &&
+                         d->res[i].w * (up ? 2 : 1) == wo && d->res[i].c == cout,
                      "%s: residual %d shape mismatch", who, i);
     }
     p->x = x->p; p->N = x->n; p->H = x->h; p->W = x->w; p->Cin = x->c; p->ldx = x->ld;
@@ -213,6 +216,12 @@ int dh_fill_conv_params(ConvParams* p, const dh_view* x, const dh_conv_desc* d, 
     p->pre_relu = d->pre_relu; p->post_relu = d->post_relu;
     p->res0 = d->n_res > 0 ? d->res[0].p : nullptr; p->ldr0 = d->n_res > 0 ? d->res[0].ld : 0;
     p->res1 = d->n_res > 1 ? d->res[1].p : nullptr; p->ldr1 = d->n_res > 1 ? d->res[1].ld : 0;
+    p->up1 = 0;
+    if (d->res_up2x) {                  // the upsampled residual always travels in slot 1
+        if (d->n_res == 1) { p->res1 = p->res0; p->ldr1 = p->ldr0; p->res0 = nullptr; p->ldr0 = 0; }
+        p->up1 = 1;
+        DH_CHECK_ARG((wo % 32) == 0 && (ho % 2) == 0, "%s: an upsampled residual needs Wo %% 32 == 0 (got %dx%d)", who, ho, wo);
+    }
     int64_t m = (int64_t)x->n * ho * wo;
     DH_CHECK_ARG(m < (1ll << 31) && (int64_t)x->n * x->h * x->w < (1ll << 31), "%s: too many pixels for int32 indexing", who);
     p->M = (int)m;

@@ -308,13 +308,26 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& P, uint32_t tile_s
     const int b4 = lane & 7, r0 = lane >> 3;
     const int m0 = mbase + r0;
     const int M = c.M, Cout = c.Cout;
-    const size_t ldo4 = (size_t)c.ldo * 4, ldr04 = (size_t)c.ldr0 * 4, ldr14 = (size_t)c.ldr1 * 4;
+    // res1 may be a HALF-resolution tensor added through a nearest 2x upsampling (keras `add([a, UpSampling2D(b)])`,
+    // reception.py:122-127): the 32 pixels of a warp-chunk lie in one image row (Wo % 32 == 0), pixels m0 + 4 i map to
+    // source pixels s0 + 2 i -- only the row base and the row stride change
+    const size_t ldo4 = (size_t)c.ldo * 4, ldr04 = (size_t)c.ldr0 * 4, ldr14 = (size_t)c.ldr1 * (c.up1 ? 2 : 4);
     const uint32_t st_a = tile_s + (uint32_t)lane * 128u;                  // transpose: write row = lane
     const uint32_t ld_a0 = tile_s + (uint32_t)(r0 * 128 + ((b4 ^ r0) << 4));   // read rows r0, r0 + 8, ...
     const uint32_t ld_a1 = tile_s + (uint32_t)((r0 + 4) * 128 + ((b4 ^ (r0 + 4)) << 4));   // rows r0 + 4, ...
     float* out_row = c.out + (size_t)m0 * c.ldo;
     const float* res0_row = c.res0 ? c.res0 + (size_t)m0 * c.ldr0 : nullptr;
-    const float* res1_row = c.res1 ? c.res1 + (size_t)m0 * c.ldr1 : nullptr;
+    const float* res1_row = nullptr;
+    if (c.res1) {
+        size_t src = (size_t)m0;
+        if (c.up1) {
+            const int hw = c.Ho * c.Wo;
+            const int n = m0 / hw, rem = m0 - n * hw;
+            const int y = rem / c.Wo, x = rem - y * c.Wo;
+            src = ((size_t)n * (c.Ho >> 1) + (y >> 1)) * (size_t)(c.Wo >> 1) + (size_t)(x >> 1);
+        }
+        res1_row = c.res1 + src * c.ldr1;
+    }
     const float* post_scale = c.post_scale;
     const float* post_shift = c.post_shift;
     const bool has_post = c.post_scale != nullptr, relu = c.post_relu != 0;
@@ -436,7 +449,16 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& P, uint32_t tile_s
                         float tt = fmaf(tv, scs, shs);
                         if (relu) tt = fmaxf(tt, 0.f);
                         if (c.res0) tt += __ldg(c.res0 + (size_t)m * c.ldr0 + cos);
-                        if (c.res1) tt += __ldg(c.res1 + (size_t)m * c.ldr1 + cos);
+                        if (c.res1) {
+                            size_t src = (size_t)m;
+                            if (c.up1) {
+                                const int hw = c.Ho * c.Wo;
+                                const int n_ = m / hw, rem_ = m - n_ * hw;
+                                const int y_ = rem_ / c.Wo, x_ = rem_ - y_ * c.Wo;
+                                src = ((size_t)n_ * (c.Ho >> 1) + (y_ >> 1)) * (size_t)(c.Wo >> 1) + (size_t)(x_ >> 1);
+                            }
+                            tt += __ldg(c.res1 + src * c.ldr1 + cos);
+                        }
                         c.out[(size_t)m * c.ldo + cos] = tt;
                     }
                 }
@@ -487,7 +509,7 @@ __device__ __forceinline__ void run_epilogue(const TcParams& P, uint8_t* epi_sta
                     const int cols = min(P.bn_cta, c.Cout - n0);
                     for (int cb = 0; cb < cols; cb += 32) {
                         if (c.res0) asm volatile("prefetch.global.L2 [%0];" ::"l"(c.res0 + (size_t)m * c.ldr0 + n0 + cb));
-                        if (c.res1) asm volatile("prefetch.global.L2 [%0];" ::"l"(c.res1 + (size_t)m * c.ldr1 + n0 + cb));
+                        if (c.res1 && !c.up1) asm volatile("prefetch.global.L2 [%0];" ::"l"(c.res1 + (size_t)m * c.ldr1 + n0 + cb));
                     }
                 }
             }

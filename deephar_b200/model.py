@@ -319,6 +319,7 @@ class Model(object):
                 d.post_scale = P['fold:' + a['post_bn']['name']]
                 d.post_shift = P['shift:' + a['post_bn']['name']]
             d.n_res = a['n_res']
+            d.res_up2x = a.get('res_up2x', 0)
             for i in range(a['n_res']):
                 d.res[i] = view(k.ins[1 + i])
             d.precision = self.precision

@@ -256,3 +256,37 @@ def test_sepconv_cluster_share_matches(dev, share):
     finally:
         _ffi.check(dev.lib.dh_set_option(dev.ctx.handle, b'share_a', 1))
         _ffi.check(dev.lib.dh_set_option(dev.ctx.handle, b'sep_tma', 1))
+
+
+@pytest.mark.parametrize('case', [(2, 32, 32, 576, 576, 5, 2), (3, 32, 32, 64, 96, 3, 1), (1, 64, 32, 32, 32, 3, 2)])
+def test_sepconv_upsampled_residual(dev, case):
+    """keras `add([a, UpSampling2D(b)])` (reception.py:122-127) folded into the epilogue of the conv that produces a:
+    the LAST residual is a half-resolution tensor (dh_conv_desc.res_up2x); n_res = 2: identity shortcut + upsampled."""
+    n, h, w, cin, cout, k, n_res = case
+    rng = np.random.default_rng(zlib.crc32(repr(case).encode()))
+    x = rng.standard_normal((n, h, w, cin))
+    dw = rng.standard_normal((k, k, cin, 1)) / k
+    pw = rng.standard_normal((1, 1, cin, cout)) / np.sqrt(cin)
+    post = (rng.uniform(0.5, 1.5, cout), rng.standard_normal(cout) * 0.3)
+    r_full = rng.standard_normal((n, h, w, cout))
+    r_half = rng.standard_normal((n, h // 2, w // 2, cout))
+    ref = ops_np.separable_conv2d(np.maximum(x, 0), dw, pw, (1, 1), 'same') * post[0] + post[1]
+    ref = ref + np.repeat(np.repeat(r_half, 2, axis=1), 2, axis=2)
+    res = [dev.view(dev.put(r_half))]
+    if n_res == 2:
+        ref = ref + r_full
+        res = [dev.view(dev.put(r_full))] + res
+    out = dev.empty(*ref.shape)
+    d = conv_desc(dev, (k, k), (1, 1), 'same', pre_relu=True, post=post, res=res, precision=3)
+    d.res_up2x = 1 << (n_res - 1)
+    pk = _packed(dev, pw.reshape(cin, cout))
+    xv, ov = dev.view(dev.put(x)), dev.view(out)
+    dev.call('dh_sepconv2d_f32', C.byref(xv), dev.put(dw).data_ptr(), dev.put(pw).data_ptr(), C.byref(pk),
+             C.byref(d), C.byref(ov))
+    assert dev.lib.dh_last_conv_path(dev.ctx.handle) == 2
+    assert _err(out.cpu().numpy(), ref) <= TOL3
+    # a residual flagged as upsampled must have half the output's size
+    d.res[n_res - 1] = dev.view(dev.put(r_full))
+    rc = dev.lib.dh_sepconv2d_f32(dev.ctx.handle, C.byref(xv), dev.put(dw).data_ptr(), dev.put(pw).data_ptr(), C.byref(pk),
+                                  C.byref(d), C.byref(ov), dev.stream())
+    assert rc < 0 and b'shape mismatch' in dev.lib.dh_last_error()
