@@ -348,6 +348,31 @@ def softargmax3d_microbench(torch, model, peaks):
             'frac': gbs / peaks['hbm_gbs'], 'us_per_launch': ms * 1000.0, 'peak_source': peaks['source']}
 
 
+def preprocess_microbench(torch):
+    """32 decoded 480x640 uint8 frames -> crop -> bilinear 256x256 -> normalize, through
+    deephar_b200.preprocess.FramePipeline with HOST images (pinned upload inside the timed region)."""
+    import time
+    from deephar_b200 import preprocess
+    rng = np.random.default_rng(0)
+    imgs = [rng.integers(0, 256, (480, 640, 3), dtype=np.uint8) for _ in range(32)]
+    objpos = rng.uniform(200, 300, (32, 2))
+    wins = rng.uniform(250, 500, 32)
+    pipe = preprocess.FramePipeline((256, 256))
+    out = torch.empty(32, 256, 256, 3, device='cuda')
+    for _ in range(3):
+        pipe(imgs, objpos, wins, out=out)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    reps = 10
+    for _ in range(reps):
+        pipe(imgs, objpos, wins, out=out)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / reps
+    return {'workload': '32 x 480x640x3 uint8 -> 256x256x3 fp32 (crop + Pillow-exact bilinear + normalize)',
+            'value': 32.0 / dt, 'unit': 'frames/s', 'ms_per_batch': dt * 1000.0, 'h2d_bytes_per_batch': pipe.h2d_bytes,
+            'launches_per_batch': 2, 'timing': 'wall clock around the public call incl. host planning + upload'}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -361,6 +386,8 @@ def main():
     ap.add_argument('--no-secondary', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='plain launches instead of CUDA-graph replays')
     ap.add_argument('--precision', type=int, default=3)
+    ap.add_argument('--emulate-world', type=int, default=0,
+                    help='analysis only (1 GPU): run rank 0 shard of a W-GPU strong-scaling job without the exchange step')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
@@ -383,7 +410,12 @@ def main():
     model.use_cuda_graph = not args.no_graph
     items_global = CLIPS
     item_frames = FRAMES
-    run = Runner(torch, model, clip_model, items_global, item_frames, rank, world, args.micro_batch, args.precision)
+    if args.emulate_world > 1:
+        assert world == 1, '--emulate-world is a single-process analysis mode'
+        run = Runner(torch, model, clip_model, items_global, item_frames, 0, args.emulate_world, args.micro_batch, args.precision)
+        run.world = 1
+    else:
+        run = Runner(torch, model, clip_model, items_global, item_frames, rank, world, args.micro_batch, args.precision)
     comm = None
     if world > 1:               # the exchange step goes through the C ABI (dh_comm_init / dh_allgather_f32)
         from deephar_b200.dist import Comm
@@ -458,6 +490,9 @@ def main():
         'config': headline_config(world, run.frames_local, micro) if args.workload == 'reception2d' else
         dict(headline_config(world, run.frames_local, micro), workload=wl_name + ' x 32 clips'),
         'clocks': clocks,
+        **({'emulated_world': args.emulate_world, 'shard_ms': ms_step,
+            'note': 'ANALYSIS ONLY: rank-0 shard of a %d-GPU job on one GPU, no exchange step; value = predicted aggregate'
+                    % args.emulate_world} if args.emulate_world > 1 else {}),
         'e2e': {'value': e2e_fps, 'unit': 'frames/s', 'h2d_bytes_per_step': n_frames * 256 * 256 * 3 * 4,
                 'd2h_bytes_per_step': d2h * world},
         'gpu_launches': launches * world,
@@ -475,6 +510,7 @@ def main():
         if rank == 0:
             line['softargmax'] = softargmax_microbench(torch, model, peaks)
             sec['softargmax3d'] = softargmax3d_microbench(torch, model, peaks)
+            sec['input_pipeline'] = preprocess_microbench(torch)
         if world > 1:       # weak scaling: the full 512 frames on every GPU (round-1 mode), device-resident
             wrun = Runner(torch, model, clip_model, CLIPS * world, FRAMES, rank, world, args.micro_batch, args.precision)
             wrun.comm = comm

@@ -25,7 +25,14 @@ class dh_conv_desc(C.Structure):
                 ('pre_scale', C.c_void_p), ('pre_shift', C.c_void_p),
                 ('post_scale', C.c_void_p), ('post_shift', C.c_void_p),
                 ('res', dh_view * 2),
-                ('precision', C.c_int32), ('reserved', C.c_int32)]
+                ('precision', C.c_int32), ('res_up2x', C.c_int32)]
+
+
+class dh_frame_src(C.Structure):
+    _fields_ = [('data', C.c_uint64), ('h', C.c_int32), ('w', C.c_int32), ('stride', C.c_int32),   # data: device pointer
+                ('x0', C.c_int32), ('y0', C.c_int32), ('cw', C.c_int32), ('ch', C.c_int32), ('hflip', C.c_int32),
+                ('kx_off', C.c_int32), ('ky_off', C.c_int32), ('kx_coef_off', C.c_int32), ('ky_coef_off', C.c_int32),
+                ('ksx', C.c_int32), ('ksy', C.c_int32)]
 
 
 class dh_packed_w(C.Structure):
@@ -63,6 +70,8 @@ SIGNATURES = {
     'dh_softargmax2d_ctx_f32': (C.c_int, [C.c_void_p, _VP, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     'dh_softargmax3d_f32': (C.c_int, [C.c_void_p, _VP, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     'dh_softargmax3d_ex_f32': (C.c_int, [C.c_void_p, _VP, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, _VP, C.c_void_p]),
+    'dh_crop_resize_norm_u8': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                         C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     'dh_pose_eval_f32': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                    C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'dh_kron_pool_f32': (C.c_int, [C.c_void_p, _VP, _VP, C.c_void_p, C.c_void_p]),

@@ -42,7 +42,8 @@ typedef struct dh_view {
  *   y   = conv(a)
  *   y   = y * post_scale[co] + post_shift[co] if post_scale     (BatchNormalization after the conv)
  *   y   = max(y, 0)                           if post_relu
- *   y  += res[0] (+ res[1])                   keras `add([...])`
+ *   y  += res[0] (+ res[1])                   keras `add([...])`; the LAST residual may be a half-resolution tensor
+ *                                             added through UpSampling2D((2,2)) (`res_up2x`; reception.py:122-127)
  * replaces: layers.py:202-325 (conv_bn, conv_bn_act, act_conv_bn, act_conv,
  * separable_act_conv_bn, ...), models/common.py:25-67 residual_unit,
  * models/reception.py:43-59 _sepconv_residual. */
@@ -58,7 +59,8 @@ typedef struct dh_conv_desc {
     const float* post_shift;     /* [Cout] or NULL */
     dh_view res[2];
     int32_t precision;           /* tensor-core path: 1 = bf16 x1, 3 = bf16 x3 split (~fp32); 0 = library default */
-    int32_t reserved;
+    int32_t res_up2x;            /* bit i: res[i] is (N, Ho/2, Wo/2, Cout) and is nearest-upsampled 2x before the add
+                                    (only the last residual; tensor-core kernels, Wo % 32 == 0) */
 } dh_conv_desc;
 
 /* Packed weights for the tensor-core path (built once at load time). */
@@ -168,6 +170,26 @@ int dh_global_maxmin_softmax_f32(dh_ctx* ctx, const dh_view* x, float* out, void
 /* out[b,t,j,:] = p[b,t,j,:] * c[b,t,j,0]   (spnet.py:110-111) */
 int dh_mask_mul_f32(dh_ctx* ctx, const float* p, const float* c, int64_t rows, int dim, float* out,
                     void* stream);
+
+/* --- evaluation-time input pipeline -----------------------------------
+ * deephar/utils/transform.py:60-134 (T.rotate_crop with angle 0 -> crop -> resize(BILINEAR) [-> horizontal_flip]) and
+ * :212-231 normalize_channels, as deephar/data/mpii.py:91-122 drives them for evaluation.  One frame: */
+typedef struct dh_frame_src {
+    const uint8_t* data;          /* decoded RGB image, uint8 HWC, device memory */
+    int32_t h, w, stride;         /* size and bytes per row */
+    int32_t x0, y0, cw, ch;       /* crop box origin (may lie outside the image: zeros, as PIL) and size */
+    int32_t hflip;                /* 1 = Image.transpose(FLIP_LEFT_RIGHT) after the resize */
+    int32_t kx_off, ky_off;       /* offsets (in int32) of this frame's (first, count) pairs in `bounds` */
+    int32_t kx_coef_off, ky_coef_off;   /* offsets (in int32) of its weight rows in `coefs` */
+    int32_t ksx, ksy;             /* taps per output index (row pitch of the weight tables) */
+} dh_frame_src;
+/* Pillow's two-pass fixed-point bilinear resampler, bit-exact: the weight tables (22-bit fixed point, computed in
+ * double on the host exactly like libImaging/Resample.c: deephar_b200/preprocess.py) come in `bounds` / `coefs`;
+ * tmp: uint8 scratch of n * tmp_stride bytes (tmp_stride >= max_crop_h * out_w * 3); out: (n, out_h, out_w, 3) fp32
+ * = ((u8 / 255) ** chpower - 0.5) * 2, i.e. the NHWC input tensor of the network.  chpower3 may be NULL (= 1). */
+int dh_crop_resize_norm_u8(dh_ctx* ctx, const dh_frame_src* frames_dev, int n, int max_crop_h,
+                           const int32_t* bounds_dev, const int32_t* coefs_dev, int out_h, int out_w,
+                           const float* chpower3, uint8_t* tmp_dev, int64_t tmp_stride, float* out_dev, void* stream);
 
 /* --- evaluator-side post-processing ------------------------------
  * deephar/utils/transform.py:136-209 transform_pose_sequence(A, poses, inverse) + deephar/measures.py:5-93

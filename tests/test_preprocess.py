@@ -1,0 +1,129 @@
+"""evaluation input pipeline (crop -> Pillow bilinear resize -> flip -> normalize_channels).
+
+CPU: the oracle (oracle/preprocess.py) against the REFERENCE's own pipeline output (tests/golden/ref_preprocess.npz,
+made by tests/golden/make_preprocess_golden.py) and, where Pillow is importable, against Pillow itself; the product's
+host-side tables / boxes / affine maps against the oracle and the golden afmat.
+GPU: dh_crop_resize_norm_u8 bit-exact against the golden frames and the oracle on ragged batches."""
+import os
+
+import numpy as np
+import pytest
+
+from deephar_b200 import preprocess
+from oracle import preprocess as opre
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = np.load(os.path.join(HERE, 'golden', 'ref_preprocess.npz'))
+CASES = ['down', 'down_flip', 'up', 'rect']
+
+
+def _case(name):
+    cx, cy, win, rw, rh, hflip = GOLD[name + '_args']
+    return GOLD[name + '_src'], (cx, cy), win, (int(rw), int(rh)), int(hflip), GOLD[name + '_frame'], GOLD[name + '_afmat']
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_oracle_matches_reference_frames(name):
+    src, objpos, win, res, hflip, frame, _ = _case(name)
+    box = np.array([objpos[0] - win / 2, objpos[1] - win / 2, objpos[0] + win / 2, objpos[1] + win / 2], dtype=int)
+    got = opre.eval_frame(src, box, res, hflip=bool(hflip))
+    assert got.dtype == np.float32 and got.shape == frame.shape
+    assert np.array_equal(got, frame)                                  # bit-exact float32
+
+
+def test_oracle_matches_pillow():
+    Image = pytest.importorskip('PIL.Image')
+    rng = np.random.default_rng(5)
+    for (h, w), size in [((97, 131), (64, 64)), ((40, 30), (96, 80)), ((256, 256), (256, 256)), ((300, 17), (17, 64)),
+                         ((33, 500), (256, 8)), ((2, 2), (7, 5))]:
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        want = np.asarray(Image.fromarray(img).resize(size, Image.BILINEAR))
+        assert np.array_equal(opre.resize_bilinear(img, size), want), ((h, w), size)
+    img = rng.integers(0, 256, (50, 60, 3), dtype=np.uint8)
+    for box in [(-10, -5, 30, 40), (20, 10, 90, 70), (5, 5, 25, 45)]:
+        assert np.array_equal(opre.crop(img, box), np.asarray(Image.fromarray(img).crop(box)))
+
+
+def test_product_tables_match_oracle():
+    for a, b in [(150, 64), (40, 96), (7, 7), (1, 5), (513, 256), (180, 48), (3, 200), (1000, 3)]:
+        pb, pc = preprocess.resample_tables(a, b)
+        ob, oc = opre.resample_coefficients(a, b)
+        assert np.array_equal(pb, ob) and np.array_equal(pc, oc), (a, b)
+        assert pb.dtype == np.int32 and pc.dtype == np.int32
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_product_box_and_afmat_match_reference(name):
+    _, objpos, win, res, hflip, _, afmat = _case(name)
+    box = preprocess.crop_box(objpos, win)
+    got = preprocess.affine_map(box, res, hflip == 1)
+    assert np.allclose(got, afmat, rtol=0, atol=1e-12)
+
+
+def test_plan_shares_tables_and_rejects_bad_input():
+    pipe = preprocess.FramePipeline((64, 64))
+    frames, bounds, coefs, boxes, afmat, max_ch = pipe.plan([(100, 120)] * 3 + [(80, 90)], [[50, 50]] * 4,
+                                                            [40.0, 40.0, 60.0, 40.0], hflip=[0, 1, 0, 0])
+    assert frames[0].kx_off == frames[1].kx_off == frames[3].kx_off != frames[2].kx_off
+    assert frames[0].kx_off == frames[0].ky_off                       # square window: one table for both axes
+    assert max_ch == 60 and boxes.shape == (4, 4) and afmat.shape == (4, 3, 3)
+    assert frames[1].hflip == 1 and frames[3].data == 3 * 100 * 120 * 3
+    with pytest.raises(ValueError):
+        pipe.plan([(10, 10)], [[5.5, 5.5]], [0.2])                      # truncates to an empty box
+    with pytest.raises(NotImplementedError):
+        pipe([np.zeros((8, 8, 3), np.uint8)], [[4, 4]], 4.0, angle=10)
+    with pytest.raises(ValueError):
+        pipe([np.zeros((8, 8, 3), np.float32)], [[4, 4]], 4.0)
+
+
+@pytest.mark.gpu
+def test_gpu_pipeline_matches_reference_golden(cuda):
+    for name in CASES:
+        src, objpos, win, res, hflip, frame, afmat = _case(name)
+        pipe = preprocess.FramePipeline(res)
+        out, a = pipe([src], [objpos], win, hflip=hflip)
+        assert np.array_equal(out.cpu().numpy()[0], frame), name
+        assert np.allclose(a[0], afmat, rtol=0, atol=1e-12)
+        assert pipe.launches == 2
+
+
+@pytest.mark.gpu
+def test_gpu_pipeline_ragged_batch_matches_oracle(cuda):
+    rng = np.random.default_rng(11)
+    shapes = [(120, 160), (90, 70), (256, 256), (33, 200), (64, 64), (300, 180), (17, 19)]
+    imgs = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for h, w in shapes]
+    objpos = [[w * rng.uniform(0.1, 0.9), h * rng.uniform(0.1, 0.9)] for h, w in shapes]
+    wins = [[rng.uniform(10, 1.5 * w), rng.uniform(10, 1.5 * h)] for h, w in shapes]
+    wins[4] = [64.0, 64.0]
+    objpos[4] = [32.0, 32.0]                                           # identity resize
+    hflip = [0, 1, 0, 1, 0, 1, 0]
+    for res, power in [((64, 64), 1), ((48, 80), (1.0, 0.9, 1.2))]:
+        pipe = preprocess.FramePipeline(res)
+        out, afmat = pipe(imgs, objpos, wins, hflip=hflip, channel_power=power)
+        out = out.cpu().numpy()
+        for i, im in enumerate(imgs):
+            box = preprocess.crop_box(objpos[i], wins[i])
+            want = opre.eval_frame(im, box, res, hflip=bool(hflip[i]), channel_power=power if power == 1 else list(power))
+            if power == 1:
+                assert np.array_equal(out[i], want), (i, res)
+            else:                                                      # powf vs numpy.power: float32 ulps
+                assert np.abs(out[i] - want).max() <= 4e-6, (i, res)
+    if True:
+        pipe = preprocess.FramePipeline((64, 64))
+        out, afmat = pipe([], np.zeros((0, 2)), np.zeros((0,)))
+        assert tuple(out.shape) == (0, 64, 64, 3) and afmat.shape == (0, 3, 3)
+
+
+@pytest.mark.gpu
+def test_gpu_pipeline_feeds_the_network_input_size(cuda):
+    """256x256 evaluation resolution from larger images, batch of 32: output is the NHWC tensor predict() takes."""
+    rng = np.random.default_rng(3)
+    imgs = [rng.integers(0, 256, (480, 640, 3), dtype=np.uint8) for _ in range(32)]
+    objpos = rng.uniform(200, 300, (32, 2))
+    wins = rng.uniform(250, 500, 32)
+    pipe = preprocess.FramePipeline((256, 256))
+    out, afmat = pipe(imgs, objpos, wins)
+    assert tuple(out.shape) == (32, 256, 256, 3) and out.is_contiguous()
+    for i in (0, 13, 31):
+        want = opre.eval_frame(imgs[i], preprocess.crop_box(objpos[i], wins[i]), (256, 256))
+        assert np.array_equal(out[i].cpu().numpy(), want)
