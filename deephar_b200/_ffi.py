@@ -25,7 +25,7 @@ class dh_conv_desc(C.Structure):
                 ('pre_scale', C.c_void_p), ('pre_shift', C.c_void_p),
                 ('post_scale', C.c_void_p), ('post_shift', C.c_void_p),
                 ('res', dh_view * 2),
-                ('precision', C.c_int32), ('res_up2x', C.c_int32)]
+                ('precision', C.c_int32), ('res_up2x', C.c_int32), ('pool_out', dh_view)]
 
 
 class dh_frame_src(C.Structure):

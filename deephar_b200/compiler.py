@@ -110,15 +110,29 @@ class _LiveGraph(object):
 
 def _up_fusable(ch):
     """Can this conv chain take one more residual that is upsampled 2x in its epilogue?  Mirrors the C side:
-    TMA-staged separable kernel (conv_sep.cu), output width a multiple of 32, at most one residual so far, and no
+    TMA-staged separable kernel (conv_sep.cu), output width 16 or 32, at most one residual so far, and no
     residual already flagged."""
     n = ch['conv']
     if n.op != 'sepconv' or len(ch['res']) > 1 or ch.get('res_up2x'):
         return False
     h, w, cin = n.inputs[0].shape
     a = n.attrs
-    return (a['size'] in ((3, 3), (5, 5)) and a['strides'] == (1, 1) and a['padding'] == 'same' and w == 32 and h % 4 == 0
+    return (a['size'] in ((3, 3), (5, 5)) and a['strides'] == (1, 1) and a['padding'] == 'same' and w in (16, 32) and h % 4 == 0
             and cin % 32 == 0)
+
+
+def _pool_fusable(ch, pool):
+    """MaxPooling2D((2,2)) of a conv chain's result as the conv's SECOND output (dh_conv_desc.pool_out).  Mirrors the C
+    side (conv_simt.cu, dh_pw_smallk_supported): the wide pointwise CUDA-core kernel -- 1x1 stride 1, Cin <= 64 and
+    a multiple of 4, Cout >= 128 and a multiple of 4, 32-pixel-wide maps of even height, no upsampled residual."""
+    n = ch['conv']
+    a, pa = n.attrs, pool.attrs
+    if n.op != 'conv' or ch.get('res_up2x') or 'pool' in ch:
+        return False
+    h, w, cin = n.inputs[0].shape
+    cout = n.out.shape[2]
+    return (a['size'] == (1, 1) and a['strides'] == (1, 1) and w == 32 and h % 2 == 0 and cin <= 64 and cin % 4 == 0
+            and cout >= 128 and cout % 4 == 0 and pa['pool'] == (2, 2) and pa['strides'] == (2, 2))
 
 
 def compile_graph(g_full):
@@ -245,6 +259,17 @@ def compile_graph(g_full):
             return True
         return False
 
+    # MaxPooling2D((2,2)) of a chain's final tensor (the hourglass pools the block-end add, reception.py:108-110): a
+    # second output of the conv kernel when that kernel is the wide pointwise one
+    pool_claimed = set()
+    end_chain = {ch['end'].id: cid for cid, ch in chains.items()}
+    for n in g.nodes:
+        if n.op == 'maxpool':
+            cid = end_chain.get(n.inputs[0].id)
+            if cid is not None and _pool_fusable(chains[cid], n):
+                chains[cid]['pool'] = n.out
+                pool_claimed.add(n.id)
+
     # ---- phase 3: emit kernel ops in schedule order --------------------------------
     plan = Plan()
     emitted = []           # (pos, seq, KOp)
@@ -273,8 +298,9 @@ def compile_graph(g_full):
             attrs = dict(n.attrs)
             attrs.update({'pre_relu': ch['pre_relu'], 'pre_bn': ch['pre_bn'].attrs if ch['pre_bn'] else None,
                           'post_bn': ch['post_bn'].attrs if ch['post_bn'] else None,
-                          'post_relu': bool(ch['post_relu']), 'n_res': len(res), 'res_up2x': ch.get('res_up2x', 0)})
-            emit(op, [ch['src']] + res, [ch['end']], attrs, ch['pos'])
+                          'post_relu': bool(ch['post_relu']), 'n_res': len(res), 'res_up2x': ch.get('res_up2x', 0),
+                          'pool_out': 'pool' in ch})
+            emit(op, [ch['src']] + res, [ch['end']] + ([ch['pool']] if 'pool' in ch else []), attrs, ch['pos'])
             continue
         if op in ('bn', 'relu'):
             if needs_materialise(n):
@@ -358,6 +384,8 @@ def compile_graph(g_full):
         if op == 'softmax':
             if n.inputs[0].node.op != 'global_maxmin':
                 raise NotImplementedError('Activation(softmax) is only supported right after global_max_min_pooling')
+            continue
+        if op == 'maxpool' and n.id in pool_claimed:
             continue
         # everything else maps 1:1 onto a kernel op
         if op not in KERNEL_OPS:

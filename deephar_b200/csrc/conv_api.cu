@@ -23,6 +23,8 @@ extern "C" int dh_conv2d_f32(dh_ctx* ctx, const dh_view* x, const float* w_hwio,
         ctx->last_conv_path = 3;
         DH_LAUNCH_EPILOGUE(ctx, 1);
     }
+    DH_CHECK_ARG(!p.pool, "dh_conv2d_f32: pool_out is written by the wide pointwise kernel only (1x1, stride 1, Cin <= 64, "
+                          "Cout >= 128, Wo == 32, even Ho); this layer is not one");
     if (packed && packed->hi && dh_patch_supported(ctx, p, packed)) {
         rc = dh_launch_patch(ctx, p, packed, d->precision, s);
         if (rc) return rc;
@@ -51,6 +53,7 @@ extern "C" int dh_sepconv2d_f32(dh_ctx* ctx, const dh_view* x, const float* w_dw
     if (rc) return rc;
     p.w = w_pw;
     p.w_dw = w_dw;
+    DH_CHECK_ARG(!p.pool, "dh_sepconv2d_f32: pool_out is not supported by the separable kernels");
     cudaStream_t s = (cudaStream_t)stream;
     if (packed_pw && packed_pw->hi && dh_tc_supported(p, packed_pw, true) && dh_sep_tma_supported(ctx, p, packed_pw)) {
         p.K = p.Cin;

@@ -220,7 +220,14 @@ int dh_fill_conv_params(ConvParams* p, const dh_view* x, const dh_conv_desc* d, 
     if (d->res_up2x) {                  // the upsampled residual always travels in slot 1
         if (d->n_res == 1) { p->res1 = p->res0; p->ldr1 = p->ldr0; p->res0 = nullptr; p->ldr0 = 0; }
         p->up1 = 1;
-        DH_CHECK_ARG((wo % 32) == 0 && (ho % 2) == 0, "%s: an upsampled residual needs Wo %% 32 == 0 (got %dx%d)", who, ho, wo);
+        DH_CHECK_ARG(((wo % 32) == 0 || wo == 16) && (ho % 2) == 0, "%s: an upsampled residual needs Wo == 16 or Wo %% 32 == 0 (got %dx%d)", who, ho, wo);
+    }
+    p->pool = nullptr; p->ldp = 0;
+    if (d->pool_out.p) {
+        const dh_view& q = d->pool_out;
+        DH_CHECK_ARG((ho % 2) == 0 && (wo % 2) == 0 && q.n == out->n && q.h == ho / 2 && q.w == wo / 2 && q.c == cout && q.ld >= q.c,
+                     "%s: pool_out must be (%d,%d,%d,%d)", who, out->n, ho / 2, wo / 2, cout);
+        p->pool = q.p; p->ldp = q.ld;
     }
     int64_t m = (int64_t)x->n * ho * wo;
     DH_CHECK_ARG(m < (1ll << 31) && (int64_t)x->n * x->h * x->w < (1ll << 31), "%s: too many pixels for int32 indexing", who);
@@ -309,9 +316,12 @@ static bool smallk_ok(const ConvParams& p) {
 // channels (x ceil(Cout/128) passes); the residual float4 loads of a pass are issued BEFORE its
 // k-loop (64 KB in flight per SM), packed FFMA2 accumulate, 512-byte coalesced rows out.
 // ---------------------------------------------------------------------------------------------
-template <int PW_PX, int PW_NT, bool PRE1>   // pixels per warp, threads per CTA, prefetch the 2nd residual before the k-loop
+// POOL: the tile is two image rows of 32 pixels and a warp takes a 2x2 pixel block of them (instead of 4 pixels of
+// one row), so the MaxPooling2D((2,2)) of the result is a max over the thread's own four pixels: second output.
+template <int PW_PX, int PW_NT, bool PRE1, bool POOL>   // pixels per warp, threads per CTA, prefetch the 2nd residual before the k-loop
 __global__ void __launch_bounds__(PW_NT, 1) conv_pw_smallk_kernel(const ConvParams p) {
     constexpr int PW_TILE = (PW_NT / 32) * PW_PX;
+    static_assert(!POOL || (PW_PX == 4 && PW_TILE == 64), "POOL: 16 warps x (2x2 pixels) = two rows of 32");
     extern __shared__ __align__(16) float pw_smem[];
     const int K = p.Cin, Cout = p.Cout, CQ = Cout >> 2, K4 = K >> 2;
     float* w_s = pw_smem;                       // [K][Cout]
@@ -350,8 +360,8 @@ __global__ void __launch_bounds__(PW_NT, 1) conv_pw_smallk_kernel(const ConvPara
             reinterpret_cast<float4*>(h_s)[i] = v;
         }
         __syncthreads();
-        const int mw = m0 + warp * PW_PX;        // this warp's first pixel
-        const float* hw = h_s + warp * PW_PX * K;
+        // local index of this warp's pixel q inside the tile
+        auto lidx = [&](int q) { return POOL ? ((q >> 1) * 32 + warp * 2 + (q & 1)) : (warp * PW_PX + q); };
         for (int cq = lane; cq < CQ; cq += 32) {
             const int co = cq * 4;
             float4 r0[PW_PX], r1[PW_PX];
@@ -359,9 +369,10 @@ __global__ void __launch_bounds__(PW_NT, 1) conv_pw_smallk_kernel(const ConvPara
             for (int q = 0; q < PW_PX; ++q) {
                 r0[q] = make_float4(0.f, 0.f, 0.f, 0.f);
                 r1[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (mw + q < p.M) {
-                    if (p.res0) r0[q] = __ldg(reinterpret_cast<const float4*>(p.res0 + (size_t)(mw + q) * p.ldr0 + co));
-                    if (PRE1 && p.res1) r1[q] = __ldg(reinterpret_cast<const float4*>(p.res1 + (size_t)(mw + q) * p.ldr1 + co));
+                const int m = m0 + lidx(q);
+                if (m < p.M) {
+                    if (p.res0) r0[q] = __ldg(reinterpret_cast<const float4*>(p.res0 + (size_t)m * p.ldr0 + co));
+                    if (PRE1 && p.res1) r1[q] = __ldg(reinterpret_cast<const float4*>(p.res1 + (size_t)m * p.ldr1 + co));
                 }
             }
             float2 a01[PW_PX], a23[PW_PX];
@@ -374,7 +385,7 @@ __global__ void __launch_bounds__(PW_NT, 1) conv_pw_smallk_kernel(const ConvPara
                 const float4 w3 = *reinterpret_cast<const float4*>(w_s + (k + 3) * Cout + co);
 #pragma unroll
                 for (int q = 0; q < PW_PX; ++q) {
-                    const float4 h = *reinterpret_cast<const float4*>(hw + q * K + k);     // broadcast
+                    const float4 h = *reinterpret_cast<const float4*>(h_s + lidx(q) * K + k);     // broadcast
                     a01[q] = __ffma2_rn(make_float2(h.x, h.x), make_float2(w0.x, w0.y), a01[q]);
                     a23[q] = __ffma2_rn(make_float2(h.x, h.x), make_float2(w0.z, w0.w), a23[q]);
                     a01[q] = __ffma2_rn(make_float2(h.y, h.y), make_float2(w1.x, w1.y), a01[q]);
@@ -390,11 +401,12 @@ __global__ void __launch_bounds__(PW_NT, 1) conv_pw_smallk_kernel(const ConvPara
             if (!PRE1 && p.res1) {
 #pragma unroll
                 for (int q = 0; q < PW_PX; ++q)
-                    if (mw + q < p.M) r1[q] = __ldg(reinterpret_cast<const float4*>(p.res1 + (size_t)(mw + q) * p.ldr1 + co));
+                    if (m0 + lidx(q) < p.M) r1[q] = __ldg(reinterpret_cast<const float4*>(p.res1 + (size_t)(m0 + lidx(q)) * p.ldr1 + co));
             }
+            float4 pm = make_float4(-3.402823466e38f, -3.402823466e38f, -3.402823466e38f, -3.402823466e38f);
 #pragma unroll
             for (int q = 0; q < PW_PX; ++q) {
-                if (mw + q < p.M) {
+                if (m0 + lidx(q) < p.M) {
                     float4 t;
                     t.x = fmaf(a01[q].x, sc.x, sh.x); t.y = fmaf(a01[q].y, sc.y, sh.y);
                     t.z = fmaf(a23[q].x, sc.z, sh.z); t.w = fmaf(a23[q].y, sc.w, sh.w);
@@ -403,9 +415,12 @@ __global__ void __launch_bounds__(PW_NT, 1) conv_pw_smallk_kernel(const ConvPara
                     }
                     t.x += r0[q].x + r1[q].x; t.y += r0[q].y + r1[q].y;
                     t.z += r0[q].z + r1[q].z; t.w += r0[q].w + r1[q].w;
-                    *reinterpret_cast<float4*>(p.out + (size_t)(mw + q) * p.ldo + co) = t;
+                    *reinterpret_cast<float4*>(p.out + (size_t)(m0 + lidx(q)) * p.ldo + co) = t;
+                    if (POOL) { pm.x = fmaxf(pm.x, t.x); pm.y = fmaxf(pm.y, t.y); pm.z = fmaxf(pm.z, t.z); pm.w = fmaxf(pm.w, t.w); }
                 }
             }
+            // tile = row pair `tile` of the batch (M % 64 == 0): pooled pixel tile * 16 + warp
+            if (POOL) *reinterpret_cast<float4*>(p.pool + ((size_t)tile * 16 + warp) * p.ldp + co) = pm;
         }
     }
 }
@@ -421,21 +436,22 @@ bool dh_pw_smallk_supported(const ConvParams& p) {
     if ((p.ldx & 3) || (p.ldo & 3) || !a16(p.x) || !a16(p.out) || !a16(p.w)) return false;
     if (p.res0 && ((p.ldr0 & 3) || !a16(p.res0))) return false;
     if (p.res1 && ((p.ldr1 & 3) || !a16(p.res1))) return false;
+    if (p.pool && !(p.Wo == 32 && (p.Ho & 1) == 0 && (p.ldp & 3) == 0 && a16(p.pool))) return false;
     return pw_smallk_smem(p, 64) <= 200 * 1024;
 }
 
-template <int PX, int NT, bool PRE1>
+template <int PX, int NT, bool PRE1, bool POOL>
 static int pw_launch(const ConvParams& p, int num_sms, cudaStream_t s) {
     constexpr int tile = (NT / 32) * PX;
     const size_t smem = pw_smallk_smem(p, tile);
-    cudaError_t e = cudaFuncSetAttribute(conv_pw_smallk_kernel<PX, NT, PRE1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(conv_pw_smallk_kernel<PX, NT, PRE1, POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
         dh_set_error("dh_launch_pw_smallk: %s", cudaGetErrorString(e));
         return (int)e;
     }
     int blocks = (p.M + tile - 1) / tile;
     if (blocks > num_sms) blocks = num_sms;
-    conv_pw_smallk_kernel<PX, NT, PRE1><<<blocks, NT, smem, s>>>(p);
+    conv_pw_smallk_kernel<PX, NT, PRE1, POOL><<<blocks, NT, smem, s>>>(p);
     return 0;
 }
 
@@ -443,7 +459,8 @@ static int pw_launch(const ConvParams& p, int num_sms, cudaStream_t s) {
 // 8 px x 256 threads 298 us, 8 px x 384 threads 300 us, 4 px x 768 threads 295 us -- the kernel is bound by the
 // fp32 FMA pipe (7.2 GFLOP at ~26 TFLOP/s), not by occupancy.
 int dh_launch_pw_smallk(const ConvParams& p, int num_sms, cudaStream_t s) {
-    return pw_launch<4, 512, true>(p, num_sms, s);
+    if (p.pool) return pw_launch<4, 512, true, true>(p, num_sms, s);
+    return pw_launch<4, 512, true, false>(p, num_sms, s);
 }
 
 // true if dh_launch_conv_simt serves `p` with the direct small-K kernel (not the generic implicit-GEMM fallback)

@@ -278,12 +278,14 @@ __device__ __forceinline__ float4 lds128(uint32_t a) {
 }
 
 // residual rows of one 32-column chunk: lane = (row lane/8 + 4 i, columns 4 (lane%8) ..+3)
+// imask: 7, or 3 when the rows are the half-resolution source of a 16-pixel-wide output (rows i and i + 4 lie in
+// two image rows that share one source row)
 template <bool FULL>
-__device__ __forceinline__ void epi_load_res(ResRows& r, const float* p, size_t ld4, int m0, int M, bool on) {
+__device__ __forceinline__ void epi_load_res(ResRows& r, const float* p, size_t ld4, int m0, int M, bool on, int imask = 7) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         r.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (on && (FULL || m0 + 4 * i < M)) r.v[i] = __ldg(reinterpret_cast<const float4*>(p + i * ld4));
+        if (on && (FULL || m0 + 4 * i < M)) r.v[i] = __ldg(reinterpret_cast<const float4*>(p + (i & imask) * ld4));
     }
 }
 
@@ -310,7 +312,8 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& P, uint32_t tile_s
     const int M = c.M, Cout = c.Cout;
     // res1 may be a HALF-resolution tensor added through a nearest 2x upsampling (keras `add([a, UpSampling2D(b)])`,
     // reception.py:122-127): the 32 pixels of a warp-chunk lie in one image row (Wo % 32 == 0), pixels m0 + 4 i map to
-    // source pixels s0 + 2 i -- only the row base and the row stride change
+    // source pixels s0 + 2 i -- only the row base and the row stride change; with Wo == 16 they are the image rows
+    // 2k and 2k + 1, which share ONE source row: pixels m0 + 4 i -> s0 + 2 (i & 3)
     const size_t ldo4 = (size_t)c.ldo * 4, ldr04 = (size_t)c.ldr0 * 4, ldr14 = (size_t)c.ldr1 * (c.up1 ? 2 : 4);
     const uint32_t st_a = tile_s + (uint32_t)lane * 128u;                  // transpose: write row = lane
     const uint32_t ld_a0 = tile_s + (uint32_t)(r0 * 128 + ((b4 ^ r0) << 4));   // read rows r0, r0 + 8, ...
@@ -318,6 +321,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& P, uint32_t tile_s
     float* out_row = c.out + (size_t)m0 * c.ldo;
     const float* res0_row = c.res0 ? c.res0 + (size_t)m0 * c.ldr0 : nullptr;
     const float* res1_row = nullptr;
+    const int imask1 = (c.up1 && c.Wo == 16) ? 3 : 7;
     if (c.res1) {
         size_t src = (size_t)m0;
         if (c.up1) {
@@ -342,7 +346,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& P, uint32_t tile_s
         const int co = n0 + first0 * 32 + b4 * 4;
         const bool ok0 = first0 < nch && (b4 * 4 < width) && (co < Cout);
         epi_load_res<FULL>(ra, res0_row + co, ldr04, m0, M, pipe0 && ok0);
-        if (RES1) epi_load_res<FULL>(rb, res1_row + co, ldr14, m0, M, pipe1 && ok0);
+        if (RES1) epi_load_res<FULL>(rb, res1_row + co, ldr14, m0, M, pipe1 && ok0, imask1);
     }
     for (int sb = 0; sb < nsub; ++sb) {
         const uint32_t u = u0 + (uint32_t)sb;
@@ -428,7 +432,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& P, uint32_t tile_s
                         const float* nres1 = res1_row + nco;
 #pragma unroll
                         for (int i = 0; i < 8; ++i)
-                            if (FULL || m0 + 4 * i < M) rb.v[i] = __ldg(reinterpret_cast<const float4*>(nres1 + i * ldr14));
+                            if (FULL || m0 + 4 * i < M) rb.v[i] = __ldg(reinterpret_cast<const float4*>(nres1 + (i & imask1) * ldr14));
                     }
                 }
             } else {
@@ -507,9 +511,19 @@ __device__ __forceinline__ void run_epilogue(const TcParams& P, uint8_t* epi_sta
                 const int m = tt * BM + q * 32 + lane;
                 if (m < c.M) {
                     const int cols = min(P.bn_cta, c.Cout - n0);
+                    // row of the second residual: the pixel itself, or (fused UpSampling2D) its half-resolution
+                    // source -- fetched once, by the even-x / even-y pixel of every 2x2 group
+                    long long m1 = c.res1 ? (long long)m : -1;
+                    if (c.res1 && c.up1) {
+                        const int hw = c.Ho * c.Wo;
+                        const int n_ = m / hw, rem_ = m - n_ * hw;
+                        const int y_ = rem_ / c.Wo, x_ = rem_ - y_ * c.Wo;
+                        m1 = ((y_ | x_) & 1) ? -1
+                                             : ((long long)n_ * (c.Ho >> 1) + (y_ >> 1)) * (long long)(c.Wo >> 1) + (x_ >> 1);
+                    }
                     for (int cb = 0; cb < cols; cb += 32) {
                         if (c.res0) asm volatile("prefetch.global.L2 [%0];" ::"l"(c.res0 + (size_t)m * c.ldr0 + n0 + cb));
-                        if (c.res1 && !c.up1) asm volatile("prefetch.global.L2 [%0];" ::"l"(c.res1 + (size_t)m * c.ldr1 + n0 + cb));
+                        if (m1 >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(c.res1 + (size_t)m1 * c.ldr1 + n0 + cb));
                     }
                 }
             }

@@ -320,6 +320,8 @@ class Model(object):
                 d.post_shift = P['shift:' + a['post_bn']['name']]
             d.n_res = a['n_res']
             d.res_up2x = a.get('res_up2x', 0)
+            if a.get('pool_out'):
+                d.pool_out = view(k.outs[1])
             for i in range(a['n_res']):
                 d.res[i] = view(k.ins[1 + i])
             d.precision = self.precision

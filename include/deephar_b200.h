@@ -60,7 +60,10 @@ typedef struct dh_conv_desc {
     dh_view res[2];
     int32_t precision;           /* tensor-core path: 1 = bf16 x1, 3 = bf16 x3 split (~fp32); 0 = library default */
     int32_t res_up2x;            /* bit i: res[i] is (N, Ho/2, Wo/2, Cout) and is nearest-upsampled 2x before the add
-                                    (only the last residual; tensor-core kernels, Wo % 32 == 0) */
+                                    (only the last residual; tensor-core kernels, Wo == 16 or Wo % 32 == 0) */
+    dh_view pool_out;            /* p != NULL: ALSO write MaxPooling2D((2,2)) of y, (N, Ho/2, Wo/2, Cout) -- the hourglass
+                                    pools the tensor the block-end add produces (reception.py:108-110); taken by the wide
+                                    pointwise kernel only (1x1, Cin <= 64, Wo == 32), an error elsewhere */
 } dh_conv_desc;
 
 /* Packed weights for the tensor-core path (built once at load time). */

@@ -125,6 +125,43 @@ def test_conv2d_pointwise_smallk(dev, case):
     assert np.all(got[..., :8] == 3.0) and np.all(got[..., 8 + cout:] == 3.0)
 
 
+@pytest.mark.parametrize('case', [(3, 32, 32, 48, 576, 2), (2, 6, 32, 16, 128, 0)])
+def test_conv2d_pointwise_pooled_second_output(dev, case):
+    """dh_conv_desc.pool_out: the hourglass max-pools the tensor the block-end add produces (reception.py:108-110,
+    194-196) -- the wide pointwise kernel writes MaxPooling2D((2,2)) of its result as a second output."""
+    n, h, w, cin, cout, nres = case
+    rng = np.random.default_rng(zlib.crc32(repr(case).encode()))
+    x = rng.standard_normal((n, h, w, cin))
+    wt = rng.standard_normal((1, 1, cin, cout)) / np.sqrt(cin)
+    post = (rng.uniform(0.5, 1.5, cout), rng.standard_normal(cout) * 0.3)
+    ref = ops_np.conv2d(np.maximum(x, 0), wt) * post[0] + post[1]
+    rs = [rng.standard_normal(ref.shape) for _ in range(nres)]
+    for r in rs:
+        ref = ref + r
+    pooled = ref.reshape(n, h // 2, 2, w // 2, 2, cout).max(axis=(2, 4))
+    out, pout = dev.empty(*ref.shape), dev.empty(*pooled.shape)
+    d = conv_desc(dev, (1, 1), pre_relu=True, post=post, res=[dev.view(dev.put(r)) for r in rs])
+    d.pool_out = dev.view(pout)
+    xv, ov = dev.view(dev.put(x)), dev.view(out)
+    dev.call('dh_conv2d_f32', C.byref(xv), dev.put(wt).data_ptr(), NULLP, C.byref(d), C.byref(ov))
+    assert dev.lib.dh_last_conv_path(dev.ctx.handle) == 3
+    _close(out.cpu().numpy(), ref)
+    got = pout.cpu().numpy()
+    _close(got, pooled)
+    assert np.array_equal(got, out.cpu().numpy().reshape(n, h // 2, 2, w // 2, 2, cout).max(axis=(2, 4)))   # exact max
+    # wrong pooled shape, and a layer no pooling kernel takes: loud errors
+    d.pool_out = dev.view(dev.empty(n, h // 2, w // 2, cout + 4))
+    rc = dev.lib.dh_conv2d_f32(dev.ctx.handle, C.byref(xv), dev.put(wt).data_ptr(), NULLP, C.byref(d), C.byref(ov), dev.stream())
+    assert rc < 0 and b'pool_out must be' in dev.lib.dh_last_error()
+    x16 = dev.put(rng.standard_normal((n, 16, 16, cin)))
+    o16, p16 = dev.empty(n, 16, 16, cout), dev.empty(n, 8, 8, cout)
+    d2 = conv_desc(dev, (1, 1), pre_relu=True, post=post)
+    d2.pool_out = dev.view(p16)
+    xv16, ov16 = dev.view(x16), dev.view(o16)
+    rc = dev.lib.dh_conv2d_f32(dev.ctx.handle, C.byref(xv16), dev.put(wt).data_ptr(), NULLP, C.byref(d2), C.byref(ov16), dev.stream())
+    assert rc < 0 and b'wide pointwise kernel only' in dev.lib.dh_last_error()
+
+
 SEP_CASES = [
     (2, 16, 16, 32, 48, (5, 5), (1, 1)),
     (1, 8, 8, 24, 24, (3, 3), (1, 1)),
