@@ -348,6 +348,28 @@ def softargmax3d_microbench(torch, model, peaks):
             'frac': gbs / peaks['hbm_gbs'], 'us_per_launch': ms * 1000.0, 'peak_source': peaks['source']}
 
 
+def single_frame_latency(torch, model):
+    """BASELINE configs[0] (C1): one 256x256 frame through the 8-block ReceptionNet -- the reference's own CPU-runnable
+    case.  Device-resident latency (CUDA events over 50 graph replays) and end-to-end latency of the public call
+    (host frame in, host pose out)."""
+    import time
+    g = torch.Generator().manual_seed(7)
+    x_host = torch.empty(1, 256, 256, 3).uniform_(-1.0, 1.0, generator=g).pin_memory()
+    x_dev = x_host.cuda()
+    ms = _time_launch(torch, lambda: model.forward_device(x_dev), reps=50)
+    x_np = x_host.numpy()
+    for _ in range(3):
+        model.predict(x_np, batch_size=1)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(20):
+        model.predict(x_np, batch_size=1)
+    torch.cuda.synchronize()
+    e2e = (time.perf_counter() - t0) / 20
+    return {'config': 'MPII single-person 2-D pose, 1 frame (BASELINE configs[0])', 'latency_ms': ms,
+            'frames_per_s': 1000.0 / ms, 'e2e_latency_ms': e2e * 1000.0, 'e2e_frames_per_s': 1.0 / e2e}
+
+
 def preprocess_microbench(torch):
     """32 decoded 480x640 uint8 frames -> crop -> bilinear 256x256 -> normalize, through
     deephar_b200.preprocess.FramePipeline with HOST images (pinned upload inside the timed region)."""
@@ -511,6 +533,7 @@ def main():
             line['softargmax'] = softargmax_microbench(torch, model, peaks)
             sec['softargmax3d'] = softargmax3d_microbench(torch, model, peaks)
             sec['input_pipeline'] = preprocess_microbench(torch)
+            sec['C1'] = single_frame_latency(torch, model)
         if world > 1:       # weak scaling: the full 512 frames on every GPU (round-1 mode), device-resident
             wrun = Runner(torch, model, clip_model, CLIPS * world, FRAMES, rank, world, args.micro_batch, args.precision)
             wrun.comm = comm
