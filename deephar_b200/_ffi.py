@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libdeephar_b200.so')
+# DEEPHAR_B200_LIB: another build of the same library (tools/: the timing-ablation build `make ABLATE=1`)
+LIB_PATH = os.environ.get('DEEPHAR_B200_LIB') or os.path.join(_HERE, 'libdeephar_b200.so')
 
 
 class DeepharB200Error(RuntimeError):

@@ -36,7 +36,7 @@ struct SepParams {
     int patch_stride;       // bytes between the two patch buffers (>= patch_bytes, 1024-aligned)
     int patch_bytes;
     int ry, fn;             // tile rows per frame, frames per tile
-    int dbg;                // ablation bits (tools/ only): 1 no depthwise math, 2 no patch TMA, 8 no DSMEM push, 16 no weight TMA
+    int dbg;                // ablation bits (tools/ only): 1 no depthwise math, 2 no patch TMA, 8 no DSMEM push, 16 no weight TMA, 64 no MMA issue (32: epilogue without global traffic, tc_common.cuh)
 };
 
 template <int KS, int TW, bool SHARE, bool BNPRO>
@@ -303,9 +303,10 @@ sep_tma_kernel(const __grid_constant__ SepParams SP, const __grid_constant__ CUt
                     int kb, nf, y0;
                     coords(j, kb, nf, y0);
                     const int w = j & 1;
-                    if ((DBG & 1024) && j + 2 < n_own) {         // pull the patch after next into L2
+                    const int pfd = (DBG & 1024) ? 2 : (DBG & 4096) ? 4 : (DBG & 8192) ? 9 : 0;   // L2 prefetch distance (K-blocks)
+                    if (pfd && j + pfd < n_own) {
                         int kb2, nf2, y2;
-                        coords(j + 2, kb2, nf2, y2);
+                        coords(j + pfd, kb2, nf2, y2);
                         tma_prefetch_4d(&map_x, kb2 * SBK, -PAD, y2 - PAD, nf2);
                     }
                     mbar_wait_relaxed(bar_pempty0 + 8 * w, (uint32_t)(((j >> 1) & 1) ^ 1), (DBG & 2048) ? 64u : 0u);
@@ -359,6 +360,7 @@ sep_tma_kernel(const __grid_constant__ SepParams SP, const __grid_constant__ CUt
                                 const uint64_t db = dbase_b + (uint64_t)((uint32_t)sb * stb16 + (uint32_t)sub * sub16);
 #pragma unroll
                                 for (int k = 0; k < SBK / 16; ++k) {
+                                    if (DBG & 64) continue;
                                     const uint32_t acc0 = (kb > 0 || k > 0) ? 1u : 0u;
                                     umma_bf16(dsub[sub], da + 2 * k, db + 2 * k, P.idesc, acc0);
                                     if (want_lo) {
@@ -450,10 +452,11 @@ int dh_launch_sep_tma(dh_ctx* ctx, const ConvParams& p, const dh_packed_w* packe
     SP.patch_stride = (SP.patch_bytes + 1023) / 1024 * 1024;
 #ifdef DH_ABLATE
     SP.dbg = ctx->dbg;
+    P.dbg = ctx->dbg;
 #else
     SP.dbg = 0;
-#endif
     P.dbg = 0;
+#endif
     const size_t smem = (size_t)NA * 2 * A_BYTES + (size_t)2 * 2 * P.bn_cta * 64 + 2 * (size_t)SP.patch_stride +
                         EPI_STAGE_BYTES + 512;
     if (smem > 227 * 1024) {

@@ -60,7 +60,7 @@ struct TcParams {
     int k_pad;
     int n_mtiles;           // ceil(M / 128); CTA (x, y) loops over tiles x, x + gridDim.x, ...
     int nslots, slot_stride; // TMEM accumulator slots (see run_epilogue): nslots x slot_stride columns
-    int dbg;                // unused (the timing-ablation switches of round 1 were compiled out of the ABI)
+    int dbg;                // `make ABLATE=1` builds only: 32 = epilogue drains TMEM but touches no global memory
 };
 
 // ---------------------------------------------------------------------------
@@ -335,7 +335,12 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& P, uint32_t tile_s
     const float* post_scale = c.post_scale;
     const float* post_shift = c.post_shift;
     const bool has_post = c.post_scale != nullptr, relu = c.post_relu != 0;
-    const bool pipe0 = vec_ok && c.res0 != nullptr, pipe1 = RES1 && vec_ok && c.res1 != nullptr;
+#ifdef DH_ABLATE
+    const bool abl_mem = (P.dbg & 32) != 0;
+#else
+    constexpr bool abl_mem = false;
+#endif
+    const bool pipe0 = vec_ok && c.res0 != nullptr && !abl_mem, pipe1 = RES1 && vec_ok && c.res1 != nullptr && !abl_mem;
 
     // This warp's chunks: flat index f = sub * nch + ck with f % EPQ == half, i.e. in sub-tile `sub` the chunks
     // ck = first(sub), first(sub) + EPQ, ...   The residual rows of a chunk are loaded one own-chunk ahead.
@@ -395,7 +400,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& P, uint32_t tile_s
                 // lane = (row r = lane/8 + 4*i, 4 columns c4 = 4*(lane%8)): 4 rows x 128 B per instruction.
                 // As each residual row is consumed its register is refilled with that row of the NEXT own chunk,
                 // so one 8 x float4 buffer per residual gives a full chunk period of load latency.
-                if (cok) {
+                if (cok && !abl_mem) {
                     float* op = out_row + co;
                     const float2 sc01 = make_float2(sc.x, sc.y), sc23 = make_float2(sc.z, sc.w);
                     const float2 sh01 = make_float2(sh.x, sh.y), sh23 = make_float2(sh.z, sh.w);
@@ -505,7 +510,11 @@ __device__ __forceinline__ void run_epilogue(const TcParams& P, uint8_t* epi_sta
         const int mbase = t * BM + q * 32;
         // pull the residual rows of the NEXT tile into L2 while this one is drained (the loads of this tile
         // were prefetched one tile ago; the first tile relies on the chunk-ahead register pipeline)
+#ifdef DH_ABLATE
+        if ((c.res0 || c.res1) && half == 0 && !(P.dbg & 32)) {
+#else
         if ((c.res0 || c.res1) && half == 0) {
+#endif
             const int tn = (t == (int)blockIdx.x) ? t : t + (int)gridDim.x;
             for (int tt = tn; tt <= t + (int)gridDim.x && tt < P.n_mtiles; tt += gridDim.x) {
                 const int m = tt * BM + q * 32 + lane;
