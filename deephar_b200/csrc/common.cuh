@@ -15,6 +15,7 @@ struct dh_ctx {
     int share_a;          // 1 = cluster pairs share the separable A tile (default), 0 = independent CTAs
     int sep_tma;          // 1 = TMA-staged separable kernel (conv_sep.cu) where it applies (default)
     int pw_smallk;        // 1 = CUDA-core kernel for wide 1x1 convs with Cin <= 64 (conv_simt.cu) (default)
+    int nsub3;        // 1 = 288-wide accumulators are 3 x 96 columns (5 TMEM slots) instead of 2 x 144 (3 slots) (default)
     int sam3d_stream;     // 1 = cluster-split streaming kernel for the volumetric head (softargmax_stream.cu) (default)
     int dense_patch;      // 1 = TMA-staged patch kernel for stride-1 Conv2D (conv_patch.cu) where it applies (default)
     void* comm;           // ncclComm_t of the output all-gather (comm.cu), NULL until dh_comm_init

@@ -418,6 +418,10 @@ int dh_launch_patch(dh_ctx* ctx, const ConvParams& p, const dh_packed_w* packed,
     P.n_kblocks = PP.ncb * PP.ntaps;
     int gy;
     tile_n(p.Cout, &P.bn_cta, &gy, &P.nsub, &P.nw);
+    if (ctx->nsub3 && P.nsub == 2 && (P.bn_cta % 48) == 0) {     // 288 = 3 x 96: five TMEM slots instead of three
+        P.nsub = 3;
+        P.nw = P.bn_cta / 3;
+    }
     P.precision = (precision == 1) ? 1 : 3;
     P.ks = 0;
     plan_tmem(P);

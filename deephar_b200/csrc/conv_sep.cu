@@ -437,6 +437,12 @@ int dh_launch_sep_tma(dh_ctx* ctx, const ConvParams& p, const dh_packed_w* packe
     P.n_kblocks = p.Cin / SBK;
     int gy;
     tile_n(p.Cout, &P.bn_cta, &gy, &P.nsub, &P.nw);
+    // 288 = 3 x 96 columns: five TMEM slots instead of three, so that the MMAs of the next tile wait for a third (not a
+    // half) of this tile's accumulator to be drained (measured: -1.5 % with one residual, -7 % with two; bit-identical)
+    if (ctx->nsub3 && P.nsub == 2 && (P.bn_cta % 48) == 0) {
+        P.nsub = 3;
+        P.nw = P.bn_cta / 3;
+    }
     P.precision = (precision == 1) ? 1 : 3;
     P.ks = p.kh;
     plan_tmem(P);

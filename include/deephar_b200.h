@@ -88,6 +88,8 @@ int         dh_set_workspace(dh_ctx* ctx, void* ptr, int64_t bytes);
  * "sep_tma" (default 1) = use the TMA-staged separable kernel where it applies;
  * "pw_smallk" (default 1) = CUDA-core kernel for wide 1x1 convs with Cin <= 64;
  * "dense_patch" (default 1) = TMA-staged patch kernel (conv_patch.cu) for stride-1 Conv2D where it applies;
+ * "sam3d_stream" (default 1) = cluster-split streaming kernel for the volumetric soft-argmax;
+ * "nsub3" (default 1) = 288-column accumulators as 3 x 96 TMEM sub-tiles (5 slots) instead of 2 x 144 (3 slots);
  * (the round-1 "dbg" timing-ablation switch only exists in tools/ builds: make ABLATE=1) */
 int         dh_set_option(dh_ctx* ctx, const char* name, int value);
 

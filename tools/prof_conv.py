@@ -23,6 +23,8 @@ if os.environ.get('DH_PATCH'):
     dev.lib.dh_set_option(dev.ctx.handle, b'dense_patch', int(os.environ['DH_PATCH']))
 if os.environ.get('DH_PWSMALLK'):
     dev.lib.dh_set_option(dev.ctx.handle, b'pw_smallk', int(os.environ['DH_PWSMALLK']))
+if os.environ.get('DH_NSUB3'):
+    _ffi.check(dev.lib.dh_set_option(dev.ctx.handle, b'nsub3', int(os.environ['DH_NSUB3'])), 'nsub3')
 if os.environ.get('DH_SHARE'):
     dev.lib.dh_set_option(dev.ctx.handle, b'share_a', int(os.environ['DH_SHARE']))
 rng = np.random.default_rng(0)
@@ -69,6 +71,8 @@ e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / reps
 mac = n * h * w * (cin * cout + (k * k * cin if kind == 'sep' else (k * k - 1) * cin * cout))
+if os.environ.get('DH_SAVE'):
+    np.save(os.environ['DH_SAVE'], out.cpu().numpy())
 print('%s n%d %dx%dx%d->%d k%d prec%d: %.1f us/launch  %.1f TFLOP/s (algorithmic)  path=%d' % (
     kind, n, h, w, cin, cout, k, precision, ms * 1000, 2 * mac / ms / 1e9,
     dev.lib.dh_last_conv_path(dev.ctx.handle)))
