@@ -7,5 +7,5 @@ timeout 170 $NCU -k regex:patch_dense -s 3 -o $out/r2_patch_stem3x3  python tool
 DH_NORES=1 timeout 170 $NCU -k regex:patch_dense -s 3 -o $out/r2_patch_regmap python tools/prof_conv.py conv 128 32 32 576 48 1 3 2 > $out/regmap.log 2>&1
 DH_RES2=1 timeout 170 $NCU -k regex:pw_smallk -s 3 -o $out/r2_pw_smallk_fremap python tools/prof_conv.py conv 128 32 32 48 576 1 3 2 > $out/fremap.log 2>&1
 timeout 170 $NCU -k regex:sam_stream  -s 3 -o $out/r2_softargmax2d_stream python tools/prof_sam.py 1024 2 2d > $out/sam2d.log 2>&1
-timeout 170 $NCU -k regex:softargmax3d -s 3 -o $out/r2_softargmax3d python tools/prof_sam.py 256 2 3d > $out/sam3d.log 2>&1
+timeout 170 $NCU -k regex:sam3d_stream -s 3 -o $out/r2_softargmax3d_stream python tools/prof_sam.py 256 2 3d > $out/sam3d.log 2>&1
 ls -la $out
