@@ -342,21 +342,20 @@ sep_tma_kernel(const __grid_constant__ SepParams SP, const __grid_constant__ CUt
                     const uint32_t it = (uint32_t)(g / NA);
                     if (!(DBG & 128)) mbar_wait(bar_full0 + 8 * s, it & 1);
                     mbar_wait(bar_fullb0 + 8 * sb, (uint32_t)(g >> 1) & 1);
-                    if (kb == 0) {                               // the epilogue must have drained the slots
-#pragma unroll
-                        for (int sub = 0; sub < MAX_NSUB; ++sub)
-                            if (sub < P.nsub) {
-                                const uint32_t uu = u + (uint32_t)sub;
-                                mbar_wait(bar_tempty0 + 8 * (uu % (uint32_t)P.nslots),
-                                          ((uu / (uint32_t)P.nslots) & 1) ^ 1);
-                            }
-                    }
                     tc_fence_after();
-                    if (leader) {
-                        const uint64_t da = dbase + (uint64_t)((uint32_t)s * sta16);
+                    const uint64_t da = dbase + (uint64_t)((uint32_t)s * sta16);
 #pragma unroll
-                        for (int sub = 0; sub < MAX_NSUB; ++sub) {
-                            if (sub < P.nsub) {
+                    for (int sub = 0; sub < MAX_NSUB; ++sub) {
+                        if (sub < P.nsub) {
+                            if (kb == 0) {
+                                // the epilogue must have drained this sub-tile's slot: waited for sub-tile by sub-tile, so
+                                // that the MMAs into the slots that are already free are issued before the wait for the one
+                                // the previous tile still occupies
+                                const uint32_t uu = u + (uint32_t)sub;
+                                mbar_wait(bar_tempty0 + 8 * (uu % (uint32_t)P.nslots), ((uu / (uint32_t)P.nslots) & 1) ^ 1);
+                                tc_fence_after();
+                            }
+                            if (leader) {
                                 const uint64_t db = dbase_b + (uint64_t)((uint32_t)sb * stb16 + (uint32_t)sub * sub16);
 #pragma unroll
                                 for (int k = 0; k < SBK / 16; ++k) {
@@ -370,6 +369,8 @@ sep_tma_kernel(const __grid_constant__ SepParams SP, const __grid_constant__ CUt
                                 }
                             }
                         }
+                    }
+                    if (leader) {
                         if (SHARE) umma_commit_pair(bar_empty0 + 16 * s + 8 * (it & 1));
                         else umma_commit(bar_empty0 + 16 * s + 8 * (it & 1));
                         umma_commit(bar_emptyb0 + 8 * sb);

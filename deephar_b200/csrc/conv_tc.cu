@@ -103,7 +103,8 @@ __device__ __forceinline__ void dense_load(const TcParams& P, const DenseRows& R
 __device__ __forceinline__ void dense_load_scalar(const TcParams& P, const DenseRows& R, int kb, int tid, DenseRegs& D) {
     const ConvParams& c = P.c;
     const int k0 = kb * BK + (tid & 15) * 4;
-    int ci[4], ky[4], kx[4];
+    // per k: tap offsets (ky, kx) and the element offset of (ky, kx, ci) relative to the row's window origin
+    int ky[4], kx[4], off[4];
     bool kv[4];
     float ps[4] = {1.f, 1.f, 1.f, 1.f}, pb[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -111,12 +112,13 @@ __device__ __forceinline__ void dense_load_scalar(const TcParams& P, const Dense
         const int k = k0 + e;
         kv[e] = k < c.K;
         const int tap = kv[e] ? k / c.Cin : 0;
-        ci[e] = kv[e] ? k - tap * c.Cin : 0;
+        const int ci = kv[e] ? k - tap * c.Cin : 0;
         ky[e] = tap / c.kw;
         kx[e] = tap - ky[e] * c.kw;
+        off[e] = (ky[e] * c.W + kx[e]) * c.ldx + ci;
         if (kv[e] && c.pre_scale) {
-            ps[e] = __ldg(c.pre_scale + ci[e]);
-            pb[e] = __ldg(c.pre_shift + ci[e]);
+            ps[e] = __ldg(c.pre_scale + ci);
+            pb[e] = __ldg(c.pre_shift + ci);
         }
     }
     D.ps = make_float4(ps[0], ps[1], ps[2], ps[3]);
@@ -124,15 +126,18 @@ __device__ __forceinline__ void dense_load_scalar(const TcParams& P, const Dense
     D.ok = 0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
+        // window origin of this output pixel (may lie outside the image: only dereferenced where valid)
+        const int iy0 = R.yx[i] >> 16, ix0 = (int)(short)(R.yx[i] & 0xffff);
+        const bool rok = R.base[i] >= 0;
+        const float* p0 = c.x + ((long long)R.base[i] + (long long)iy0 * c.W + ix0) * (long long)c.ldx;
         float v[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            const int iy = (R.yx[i] >> 16) + ky[e], ix = (int)(short)(R.yx[i] & 0xffff) + kx[e];
-            const bool ok = kv[e] && R.base[i] >= 0 && iy >= 0 && iy < c.H && ix >= 0 && ix < c.W;
+            const bool ok = rok && kv[e] && (unsigned)(iy0 + ky[e]) < (unsigned)c.H && (unsigned)(ix0 + kx[e]) < (unsigned)c.W;
             v[e] = 0.f;
             if (ok) {
                 D.ok |= 1u << (4 * i + e);
-                v[e] = __ldg(c.x + (size_t)(R.base[i] + iy * c.W + ix) * c.ldx + ci[e]);
+                v[e] = __ldg(p0 + off[e]);
             }
         }
         D.v[i] = make_float4(v[0], v[1], v[2], v[3]);
