@@ -26,6 +26,16 @@ from .layers import (act_channel_softmax, channel_slice, channel_softmax_2d, dep
 from .model import Model as _Model
 
 
+# Keras numbers auto-named layers (conv2d_7, batch_normalization_12) with ONE counter per class for the whole
+# session, across sub-models: every graph started here shares this table until clear_session().
+_SESSION_COUNTERS = {}
+
+
+def clear_session():
+    """keras.backend.clear_session(): restart the auto-name counters (call between two independent models)."""
+    _SESSION_COUNTERS.clear()
+
+
 def Input(shape=None, batch_shape=None, name=None, graph=None, frames_per_clip=None):
     """keras.layers.Input.  shape (H, W, C) -> per-frame tensor; shape (T, H, W, C) -> a clip input whose frames are
     folded into the batch axis (what TimeDistributed does in the reference, deephar/models/spnet.py:283-296).  A new
@@ -35,7 +45,11 @@ def Input(shape=None, batch_shape=None, name=None, graph=None, frames_per_clip=N
     if shape is None:
         raise ValueError('Input: shape is required')
     shape = tuple(int(s) for s in shape)
-    g = graph if graph is not None else Graph(name or 'model')
+    if graph is not None:
+        g = graph
+    else:
+        g = Graph(name or 'model')
+        g._counters = _SESSION_COUNTERS
     if len(shape) == 4:
         g.frames_per_clip = int(shape[0])
         shape = shape[1:]
@@ -167,12 +181,13 @@ class ZeroPadding2D(Layer):
 
 
 class TimeDistributed(Layer):
-    """keras.layers.TimeDistributed: frames already sit on the batch axis, so the wrapper only hands its name down."""
+    """keras.layers.TimeDistributed: frames already sit on the batch axis, so the wrapper only hands its name down
+    (a wrapped nested Model keeps its own name: its weights live under that scope)."""
 
     def __init__(self, layer, name=None, **kwargs):
         Layer.__init__(self, name, **kwargs)
         self.layer = layer
-        if name is not None:
+        if name is not None and isinstance(layer, Layer):
             layer.name = name
 
     def call(self, x):
@@ -214,20 +229,96 @@ def multiply(inputs, name=None):
     return Multiply(name=name)(inputs)
 
 
-def Model(inputs=None, outputs=None, name=None):
-    """keras.models.Model(inputs, outputs): compile the recorded graph for B200.  Layers that do not reach an output
-    are dropped, as Keras drops them (their weights become optional when loading a checkpoint)."""
-    inputs = list(inputs) if isinstance(inputs, (list, tuple)) else [inputs]
-    outputs = list(outputs) if isinstance(outputs, (list, tuple)) else [outputs]
-    if len(inputs) != 1:
-        raise NotImplementedError('Model: exactly one Input (the frame / clip tensor) is supported')
-    g = inputs[0].g
-    for t in outputs:
-        if t.g is not g:
-            raise ValueError('Model: an output does not descend from the given Input')
-    if g.inputs != inputs:
-        raise ValueError('Model: `inputs` must be the Input the graph was started from')
-    g.outputs = outputs
-    if name:
-        g.name = name
-    return _Model(g, name=name)
+def _weight_names(attrs, known):
+    """(path in attrs, weight name) for every attribute value that names a weight of the recorded graph."""
+    for key, val in attrs.items():
+        if isinstance(val, str) and val in known:
+            yield (key, None), val
+        elif isinstance(val, dict):
+            for k2, v2 in val.items():
+                if isinstance(v2, str) and v2 in known:
+                    yield (key, k2), v2
+
+
+class Model(object):
+    """keras.models.Model(inputs, outputs, name).
+
+    * used as a MODEL (`predict`, `load_weights`, `outputs`, `weight_specs`, ...): the recorded graph is compiled for
+      B200 on first use (layers that reach no output are dropped, as Keras drops them) and every attribute of
+      deephar_b200.model.Model is available on this object;
+    * used as a LAYER -- `Stem = Model(inp, x, name='Stem'); y = Stem(frames)`, the way the reference wraps its blocks
+      (deephar/models/reception.py:96-98, 128-131) -- its layers are re-recorded into the caller's graph under the
+      scope `name`, which is how Keras names the weights of a nested model in a checkpoint ("Stem/conv2d_1/kernel").
+      A nested model can be applied once (no weight sharing on the reference's forward path).
+    """
+
+    def __init__(self, inputs=None, outputs=None, name=None):
+        self._inputs = list(inputs) if isinstance(inputs, (list, tuple)) else [inputs]
+        self._outputs = list(outputs) if isinstance(outputs, (list, tuple)) else [outputs]
+        self._single = not isinstance(outputs, (list, tuple))
+        if len(self._inputs) != 1:
+            raise NotImplementedError('Model: exactly one Input (the frame / clip tensor) is supported')
+        g = self._inputs[0].g
+        for t in self._outputs:
+            if t.g is not g:
+                raise ValueError('Model: an output does not descend from the given Input')
+        if g.inputs != self._inputs:
+            raise ValueError('Model: `inputs` must be the Input the graph was started from')
+        self._graph = g
+        self._name = name or g.auto_name('model')
+        self._impl = None
+        self._applied = False
+
+    # ---- as a model ---------------------------------------------------------------------------------------------
+    def _compiled(self):
+        if self._impl is None:
+            if self._applied:
+                raise NotImplementedError('Model %r was applied as a layer of another model; compile that one' % self._name)
+            self._graph.outputs = self._outputs
+            self._graph.name = self._name
+            self._impl = _Model(self._graph, name=self._name)
+        return self._impl
+
+    def __getattr__(self, attr):
+        if attr.startswith('_'):
+            raise AttributeError(attr)
+        return getattr(self._compiled(), attr)
+
+    # ---- as a layer ---------------------------------------------------------------------------------------------
+    def __call__(self, x):
+        if self._impl is not None or self._applied:
+            raise NotImplementedError('Model %r: a nested model can be applied once, before it is used as a model'
+                                      % self._name)
+        sub, tgt = self._graph, x.g
+        if tgt is sub:
+            raise ValueError('Model %r applied to a tensor of its own graph' % self._name)
+        src_in = self._inputs[0]
+        if tuple(x.shape) != tuple(src_in.shape):
+            raise ValueError('Model %r expects input shape %s, got %s' % (self._name, src_in.shape, x.shape))
+        self._applied = True
+        known = dict(sub.weight_specs)
+        prefix = tgt.qualify(self._name)
+        for wname, shape in sub.weight_specs:                        # creation order is kept
+            layer, leaf = wname.rsplit('/', 1)
+            tgt.add_weight(prefix + '/' + layer, leaf, shape)
+        new = {src_in.id: x}
+        for nd in sub.nodes:
+            if nd.op == 'input':
+                continue
+            attrs = {}
+            for k, v in nd.attrs.items():
+                attrs[k] = dict(v) if isinstance(v, dict) else v
+            if isinstance(attrs.get('name'), str) and nd.attrs.get('name') is not None and any(True for _ in _weight_names(nd.attrs, known)):
+                attrs['name'] = prefix + '/' + attrs['name']
+            for (k1, k2), w in _weight_names(nd.attrs, known):
+                if k2 is None:
+                    attrs[k1] = prefix + '/' + w
+                else:
+                    attrs[k1][k2] = prefix + '/' + w
+            outs = tgt.op(nd.op, [new[t.id] for t in nd.inputs], [o.shape for o in nd.outs], attrs,
+                          kind=nd.outs[0].kind if nd.outs[0].kind != src_in.kind else x.kind)
+            outs = outs if isinstance(outs, tuple) else (outs,)
+            for o_src, o_new in zip(nd.outs, outs):
+                new[o_src.id] = o_new
+        res = [new[t.id] for t in self._outputs]
+        return res[0] if self._single else res

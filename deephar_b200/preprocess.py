@@ -87,6 +87,19 @@ def affine_map(box, crop_resolution, hflip):
     return apply(scale(1 / rw, 1 / rh), a)
 
 
+def mpii_windows(objpos, scale, dconf=None):
+    """deephar/data/mpii.py:99-105: the crop window of an MPII single-person sample from its annotation --
+    `scale` enlarged by 1.25, the centre moved 12 * scale down (+ scale * (transx, transy)), a square window of
+    200 * dconf['scale'] * scale pixels.  objpos (N, 2), scale (N,); dconf = `dataconf.get_fixed_config()`.
+    -> (objpos (N, 2), winsize (N,)) as FramePipeline takes them."""
+    dconf = dconf or {'scale': 1, 'transx': 0, 'transy': 0}
+    scale = 1.25 * np.asarray(scale, np.float64).reshape(-1)
+    pos = np.array(objpos, dtype=np.float64).reshape(-1, 2)
+    pos[:, 1] += 12 * scale
+    pos += scale[:, None] * np.array([dconf['transx'], dconf['transy']], np.float64)
+    return pos, 200 * dconf['scale'] * scale
+
+
 class FramePipeline(object):
     """Batched evaluation input pipeline bound to one device.
 

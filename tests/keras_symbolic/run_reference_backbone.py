@@ -1,0 +1,67 @@
+"""Executes the reference's own backbone builders on the recording `keras` of this directory and prints the recorded
+model's weight list and kernel plan as JSON (driven by tests/test_keras_compat.py in a subprocess)."""
+import json
+import os
+import sys
+import warnings
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path[:0] = [HERE, os.path.join(HERE, '..', 'golden', 'keras_shim'), os.environ.get('DEEPHAR_REFERENCE', '/root/reference'), ROOT]
+warnings.filterwarnings('ignore')
+_stderr, sys.stderr = sys.stderr, open(os.devnull, 'w')       # the reference prints a banner on import
+import deephar  # noqa: E402,F401
+from deephar.models import reception as R  # noqa: E402
+sys.stderr = _stderr
+
+from keras.layers import Input, add  # noqa: E402   (= deephar_b200.keras_compat)
+from keras.models import Model  # noqa: E402
+from deephar_b200 import keras_compat  # noqa: E402
+
+
+def spnet_case():
+    """spnet.py:317-352 entry_flow + common.py:25-108 residual / downscaling / upscaling units (the conv skeleton of a
+    pyramid level), driven by the reference's own ModelConfig."""
+    from deephar.config import ModelConfig
+    from deephar.models import spnet as S
+    from deephar.models.common import downscaling_unit, residual_unit, upscaling_unit
+    from deephar.utils.pose import pa16j2d
+    cfg = ModelConfig((256, 256, 3), pa16j2d, num_pyramids=2, num_levels=4, num_pose_features=160, num_visual_features=160)
+    keras_compat.clear_session()
+    inp = Input(shape=(256, 256, 3))
+    x = S.entry_flow(inp, cfg)
+    d = downscaling_unit(x, cfg, out_size=x.shape[-1] + cfg.growth, name='dn1')
+    d = residual_unit(d, cfg.kernel_size, name='mid1')
+    u = upscaling_unit(d, cfg, out_size=x.shape[-1], name='up1')
+    y = add([x, u])
+    m = Model(inputs=inp, outputs=[y, d], name='spnet_skeleton')
+    print(json.dumps({'weight_specs': [[n, list(s)] for n, s in m.weight_specs],
+                      'plan': [[k.kind, [list(t.shape) for t in k.outs]] for k in m.plan.kops],
+                      'output_shape': [list(s) for s in m.output_shape]}))
+
+
+def main():
+    if sys.argv[1] == 'spnet':
+        return spnet_case()
+    blocks, ksize, heatmaps = int(sys.argv[1]), (5, 5), 48
+    keras_compat.clear_session()
+    inp = Input(shape=(256, 256, 3))
+    x = R._stem(inp)
+    width = x.shape[-1]
+    outs = []
+    for b in range(1, blocks + 1):
+        x = R.build_reception_block(x, name='rBlock%d' % b, ksize=ksize)
+        ident = x
+        x = R.build_sconv_block(x, name='SepConv%d' % b, ksize=ksize)
+        h = R.build_regmap_block(x, heatmaps, name='RegMap%d' % b)
+        outs.append(h)
+        if b < blocks:
+            x = add([ident, x, R.build_fremap_block(h, width, name='fReMap%d' % b)])
+    m = Model(inputs=inp, outputs=outs, name='backbone')
+    print(json.dumps({'weight_specs': [[n, list(s)] for n, s in m.weight_specs],
+                      'plan': [[k.kind, [list(t.shape) for t in k.outs]] for k in m.plan.kops],
+                      'output_shape': [list(s) for s in m.output_shape]}))
+
+
+if __name__ == '__main__':
+    main()

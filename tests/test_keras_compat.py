@@ -1,6 +1,11 @@
 """keras_compat: model code written in the Keras functional style (the style of deephar/models/*.py) records the same
 graph, weight list and kernel plan as the function-style mirror of deephar/layers.py; unsupported Keras features are
 rejected when the model is built."""
+import json
+import os
+import subprocess
+import sys
+
 import numpy as np
 import pytest
 
@@ -117,3 +122,82 @@ def _oracle_forward(w, x):
     pose = o.to_numpy(o.softargmax2d(hm)).reshape(-1, 8, 2)
     vis = o.to_numpy(o.keypoint_confidence(hm)).reshape(-1, 8, 1)
     return [pose, vis, o.to_numpy(o.concat([t, h]))]
+
+
+def _function_style_backbone(blocks, ksize=(5, 5), heatmaps=48):
+    from deephar_b200 import reception as R
+    g = Graph('backbone')
+    x = R._stem(g.input((256, 256, 3)))
+    width, outs = x.channels, []
+    for b in range(1, blocks + 1):
+        x = R.build_reception_block(x, name='rBlock%d' % b, ksize=ksize)
+        ident = x
+        x = R.build_sconv_block(x, name='SepConv%d' % b, ksize=ksize)
+        h = R.build_regmap_block(x, heatmaps, name='RegMap%d' % b)
+        outs.append(h)
+        if b < blocks:
+            x = L.add([ident, x, R.build_fremap_block(h, width, name='fReMap%d' % b)])
+    g.outputs = outs
+    return Model(g)
+
+
+def test_nested_models_and_session_counters():
+    """`Model(xi, x, name=...)(inp)` re-records the block under its scope; auto-names count per session."""
+    K.clear_session()
+    xi = K.Input(shape=(16, 16, 8))
+    y = K.BatchNormalization()(K.Conv2D(8, (3, 3), padding='same', use_bias=False)(xi))
+    blk = K.Model(inputs=xi, outputs=y, name='Blk')
+    inp = K.Input(shape=(16, 16, 8))
+    z = K.Conv2D(4, (1, 1), use_bias=False)(K.Activation('relu')(blk(inp)))
+    m = K.Model(inputs=inp, outputs=z)
+    assert [n for n, _ in m.weight_specs] == [
+        'Blk/conv2d_1/kernel', 'Blk/batch_normalization_1/gamma', 'Blk/batch_normalization_1/beta',
+        'Blk/batch_normalization_1/moving_mean', 'Blk/batch_normalization_1/moving_variance', 'conv2d_2/kernel']
+    assert m.optional_weights == [] and [k.kind for k in m.plan.kops] == ['conv', 'conv']
+    with pytest.raises(NotImplementedError):
+        blk(inp)                                               # a nested model is applied once
+    with pytest.raises(NotImplementedError):
+        blk.predict(np.zeros((1, 16, 16, 8), np.float32))      # ... and then belongs to the outer model
+
+
+@pytest.mark.skipif(not os.path.isdir(os.environ.get('DEEPHAR_REFERENCE', '/root/reference')),
+                    reason='needs the reference tree (development container only)')
+def test_reference_backbone_builders_record_the_same_model():
+    """The REFERENCE'S OWN code -- deephar/layers.py and models/reception.py::_stem / build_reception_block /
+    build_sconv_block / build_regmap_block / build_fremap_block, unmodified -- imported on a `keras` that is
+    keras_compat (tests/keras_symbolic) records the weight list, auto-names and kernel plan of deephar_b200's builders."""
+    here = os.path.dirname(os.path.abspath(__file__))
+    out = subprocess.run([sys.executable, os.path.join(here, 'keras_symbolic', 'run_reference_backbone.py'), '3'],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    got = json.loads([l for l in out.stdout.splitlines() if l.startswith('{')][-1])
+    want = _function_style_backbone(3)
+    assert [(n, tuple(s)) for n, s in got['weight_specs']] == want.weight_specs
+    assert len(want.weight_specs) > 200
+    assert got['plan'] == [[k.kind, [list(t.shape) for t in k.outs]] for k in want.plan.kops]
+    assert [tuple(s) for s in got['output_shape']] == [tuple(s) for s in want.output_shape]
+
+
+@pytest.mark.skipif(not os.path.isdir(os.environ.get('DEEPHAR_REFERENCE', '/root/reference')),
+                    reason='needs the reference tree (development container only)')
+def test_reference_spnet_skeleton_records_the_same_model():
+    """Same for deephar/models/spnet.py::entry_flow and models/common.py::residual_unit / downscaling_unit /
+    upscaling_unit (the reference's code and its own ModelConfig / pose layout, on the recording keras)."""
+    from deephar_b200 import common, spnet
+    from deephar_b200.config import ModelConfig, pa16j2d
+    here = os.path.dirname(os.path.abspath(__file__))
+    out = subprocess.run([sys.executable, os.path.join(here, 'keras_symbolic', 'run_reference_backbone.py'), 'spnet'],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    got = json.loads([l for l in out.stdout.splitlines() if l.startswith('{')][-1])
+    cfg = ModelConfig((256, 256, 3), pa16j2d, num_pyramids=2, num_levels=4, num_pose_features=160, num_visual_features=160)
+    g = Graph('spnet_skeleton')
+    x = spnet.entry_flow(g.input((256, 256, 3)), cfg)
+    d = common.downscaling_unit(x, cfg, out_size=x.channels + cfg.growth, name='dn1')
+    d = common.residual_unit(d, cfg.kernel_size, name='mid1')
+    u = common.upscaling_unit(d, cfg, out_size=x.channels, name='up1')
+    g.outputs = [L.add([x, u]), d]
+    want = Model(g)
+    assert [(n, tuple(s)) for n, s in got['weight_specs']] == want.weight_specs and len(want.weight_specs) > 60
+    assert got['plan'] == [[k.kind, [list(t.shape) for t in k.outs]] for k in want.plan.kops]
+    assert [tuple(s) for s in got['output_shape']] == [tuple(s) for s in want.output_shape]

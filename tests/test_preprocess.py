@@ -76,6 +76,25 @@ def test_plan_shares_tables_and_rejects_bad_input():
         pipe([np.zeros((8, 8, 3), np.float32)], [[4, 4]], 4.0)
 
 
+def test_mpii_window_and_fixed_dataconf():
+    """data/mpii.py:99-105 with config.py:42-50's fixed configuration."""
+    from deephar_b200.config import DataConfig, mpii_sp_dataconf, pennaction_dataconf
+    d = mpii_sp_dataconf.get_fixed_config()
+    assert d == {'angle': 0, 'scale': 1, 'transx': 0, 'transy': 0, 'hflip': 0, 'chpower': 1, 'geoocclusion': None, 'subspl': 1}
+    assert mpii_sp_dataconf.input_shape == (256, 256, 3) and pennaction_dataconf.get_fixed_config()['subspl'] == 6
+    pos, win = preprocess.mpii_windows([[594.0, 257.0], [300.0, 100.0]], [3.021, 1.5], d)
+    s = 1.25 * np.array([3.021, 1.5])
+    assert np.allclose(pos, [[594.0, 257.0 + 12 * s[0]], [300.0, 100.0 + 12 * s[1]]], atol=1e-12)
+    assert np.allclose(win, 200 * s, atol=1e-12)
+    d2 = DataConfig(crop_resolution=(128, 128), scales=[0.7, 1.3], fixed_scale=1.3, fixed_trans_x=5).get_fixed_config()
+    pos2, win2 = preprocess.mpii_windows([[10.0, 20.0]], [1.0], d2)
+    assert np.allclose(pos2, [[10.0 + 1.25 * 5, 20.0 + 15.0]]) and np.allclose(win2, [200 * 1.3 * 1.25])
+    with pytest.raises(NotImplementedError):
+        mpii_sp_dataconf.random_data_generator()
+    with pytest.raises(TypeError):
+        DataConfig(resolution=(1, 1))
+
+
 @pytest.mark.gpu
 def test_gpu_pipeline_matches_reference_golden(cuda):
     for name in CASES:
