@@ -146,3 +146,24 @@ def test_gpu_pipeline_feeds_the_network_input_size(cuda):
     for i in (0, 13, 31):
         want = opre.eval_frame(imgs[i], preprocess.crop_box(objpos[i], wins[i]), (256, 256))
         assert np.array_equal(out[i].cpu().numpy(), want)
+
+
+def test_tables_randomised_against_oracle_and_pillow():
+    """Random (in, out) size pairs: product tables == oracle tables; oracle resize == Pillow where importable; every
+    weight row sums to 2^22 within the rounding of its taps (Pillow's normalisation)."""
+    rng = np.random.default_rng(2024)
+    pairs = [(int(a), int(b)) for a, b in zip(rng.integers(1, 700, 40), rng.integers(1, 400, 40))]
+    for a, b in pairs:
+        pb, pc = preprocess.resample_tables(a, b)
+        ob, oc = opre.resample_coefficients(a, b)
+        assert np.array_equal(pb, ob) and np.array_equal(pc, oc), (a, b)
+        assert np.all(pb[:, 0] >= 0) and np.all(pb[:, 0] + pb[:, 1] <= a) and np.all(pb[:, 1] >= 1)
+        assert np.all(np.abs(pc.sum(axis=1) - (1 << 22)) <= pc.shape[1])
+    try:
+        from PIL import Image
+    except ImportError:
+        return
+    for (h, w), (ow, oh) in [((int(a), int(b)), (int(c), int(d))) for a, b, c, d in rng.integers(1, 90, (12, 4))]:
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        want = np.asarray(Image.fromarray(img).resize((ow, oh), Image.BILINEAR))
+        assert np.array_equal(opre.resize_bilinear(img, (ow, oh)), want), ((h, w), (ow, oh))
