@@ -52,6 +52,34 @@ def test_param_count_and_plan():
     assert kinds.count('pose_regression_2d_context') == 8
     flops = m.conv_flops_per_frame()
     assert abs(flops - 19.67e9) / 19.67e9 < 0.005
+    # hourglass glue fused into the neighbouring conv kernels (reception.py:108-110, 122-127):
+    # 2 x 8 `add([a, UpSampling2D(b)])` as the last (half-resolution) residual of the sepconv producing a,
+    # 7 MaxPooling2D of the block-end add as the second output of the fReMap kernel that computes it
+    up = [k for k in m.plan.kops if k.attrs.get('res_up2x')]
+    assert len(up) == 16 and all(k.kind == 'sepconv' and k.ins[-1].shape[0] * 2 == k.outs[0].shape[0] for k in up)
+    assert sorted(set(k.outs[0].shape[1] for k in up)) == [16, 32]
+    pooled = [k for k in m.plan.kops if k.attrs.get('pool_out')]
+    assert len(pooled) == 7 and all(k.kind == 'conv' and k.attrs['size'] == (1, 1) and len(k.outs) == 2 and
+                                    k.outs[1].shape == (16, 16, 576) for k in pooled)
+    assert 'upsample_add' not in kinds and kinds.count('maxpool') == 11 and len(kinds) == 127
+
+
+def test_fusions_are_refused_where_the_kernels_cannot_take_them():
+    from deephar_b200 import layers as L
+    from deephar_b200.graph import Graph
+    from deephar_b200.model import Model
+    # pooled second output needs the wide pointwise kernel (Cin <= 64): a 272-channel fReMap (3-D model) keeps its max-pool
+    m3 = reception.build((256, 256, 3), 17, 3, num_blocks=2, ksize=(5, 5))
+    k3 = [k.kind for k in m3.plan.kops]
+    assert not any(k.attrs.get('pool_out') for k in m3.plan.kops) and k3.count('maxpool') >= 4
+    # upsampled residual: 8-pixel-wide maps and stride-2 / dense producers stay separate `upsample_add` kernels
+    g = Graph('t')
+    x = g.input((8, 8, 32))
+    a = L.BatchNormalization(L.sepconv2d(L.relu(x), 32, (3, 3), name='s'), name='b')
+    low = L.conv2d(L.maxpooling2d(x), 32, (1, 1), name='c')
+    g.outputs = [L.add([a, L.UpSampling2D(low)])]
+    kk = [k.kind for k in Model(g).plan.kops]
+    assert 'upsample_add' in kk
 
 
 def test_flops_3d():
