@@ -49,3 +49,26 @@ def test_no_gpu_fails_loudly():
 
 def lib_rc(h):
     return _ffi.lib().dh_ctx_create(ctypes.byref(h), 0)
+
+
+def test_header_is_plain_c_and_struct_layouts_match_ctypes():
+    """The boundary is a C ABI: the header must compile as C99 (no C++, no torch types), and the ctypes mirrors in
+    _ffi.py must have the compiler's struct sizes."""
+    import shutil
+    import subprocess
+    import tempfile
+    import pytest
+    gcc = shutil.which('gcc')
+    if gcc is None:
+        pytest.skip('no gcc')
+    hdr = os.path.join(ROOT, 'include', 'deephar_b200.h')
+    subprocess.check_call([gcc, '-fsyntax-only', '-x', 'c', '-std=c99', '-Wall', '-Werror', hdr])
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, 's.c')
+        open(src, 'w').write('#include <stdio.h>\n#include "deephar_b200.h"\nint main(void) { printf("%zu %zu %zu %zu\\n", '
+                             'sizeof(dh_view), sizeof(dh_conv_desc), sizeof(dh_packed_w), sizeof(dh_frame_src)); return 0; }\n')
+        exe = os.path.join(d, 's')
+        subprocess.check_call([gcc, '-std=c99', '-I', os.path.join(ROOT, 'include'), src, '-o', exe])
+        sizes = [int(v) for v in subprocess.check_output([exe]).split()]
+    assert sizes == [ctypes.sizeof(_ffi.dh_view), ctypes.sizeof(_ffi.dh_conv_desc), ctypes.sizeof(_ffi.dh_packed_w),
+                     ctypes.sizeof(_ffi.dh_frame_src)]
