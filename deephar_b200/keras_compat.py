@@ -180,6 +180,48 @@ class ZeroPadding2D(Layer):
         return L.ZeroPadding2D(x, self.padding)
 
 
+class _SliceProbe(object):
+    """What a Lambda body sees instead of a tensor: it may take a slice of the channel axis, nothing else."""
+
+    def __init__(self, t):
+        self._t = t
+
+    def __getitem__(self, idx):
+        idx = idx if isinstance(idx, tuple) else (idx,)
+        full = slice(None, None, None)
+        if len(idx) != len(self._t.shape) + 1 or any(i != full for i in idx[:-1]) or not isinstance(idx[-1], slice) \
+                or idx[-1].step not in (None, 1):
+            raise NotImplementedError('Lambda: only channel slices x[..., a:b] can be recorded')
+        c = self._t.channels
+        a, b, _ = idx[-1].indices(c)
+        return L.channel_slice(self._t, a, b)
+
+    def __getattr__(self, name):
+        raise NotImplementedError('Lambda: only channel slices x[..., a:b] can be recorded (the body used .%s)' % name)
+
+
+class Lambda(Layer):
+    """keras.layers.Lambda, for the one body the reference's forward path needs outside its parameter-free head models:
+    a slice of the channel axis (`Lambda(lambda x: x[:,:,:,:num_joints])`, reception.py:171-172).  Any other body is
+    arbitrary backend arithmetic and is rejected."""
+
+    def __init__(self, function, name=None, **kwargs):
+        Layer.__init__(self, name, **{k: v for k, v in kwargs.items() if k not in ('output_shape', 'arguments', 'mask')})
+        self.function = function
+
+    def call(self, x):
+        from .graph import Tensor
+        try:
+            out = self.function(_SliceProbe(x))
+        except NotImplementedError:
+            raise
+        except Exception as e:                                  # K.* on the probe, arithmetic, ...
+            raise NotImplementedError('Lambda: only channel slices x[..., a:b] can be recorded (%s)' % e)
+        if not isinstance(out, Tensor):
+            raise NotImplementedError('Lambda: only channel slices x[..., a:b] can be recorded')
+        return out
+
+
 class TimeDistributed(Layer):
     """keras.layers.TimeDistributed: frames already sit on the batch axis, so the wrapper only hands its name down
     (a wrapped nested Model keeps its own name: its weights live under that scope)."""
@@ -229,6 +271,141 @@ def multiply(inputs, name=None):
     return Multiply(name=name)(inputs)
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# The reference's parameter-free head models (deephar/models/blocks.py:217-343).  In Keras they are small sub-models of
+# Lambda / pooling / frozen Dense and SeparableConv2D layers; here each is ONE recordable object, and the combination the
+# builders make of them (reception.py:167-190) is rewritten into the single fused graph op the kernels implement.
+# ---------------------------------------------------------------------------------------------------------------------
+class _Head(object):
+    def __init__(self, kind, name=None, **attrs):
+        self.kind, self.name, self.attrs = kind, name, attrs
+        self.trainable = False
+
+    def __call__(self, x):
+        xs = list(x) if isinstance(x, (list, tuple)) else [x]
+        g = xs[0].g
+        if self.kind in ('sam2d', 'jprob'):
+            h, w, c = xs[0].shape
+            shape = (1, c, 2 if self.kind == 'sam2d' else 1)
+        elif self.kind == 'agg':
+            shape = (1, self.attrs['num_joints'], 2)
+        else:
+            raise NotImplementedError('head model %r is not recordable yet' % self.kind)
+        return g.op('head_' + self.kind, xs, shape, dict(self.attrs, name=self.name))
+
+
+def build_softargmax_2d(input_shape, rho=0., name=None):
+    """blocks.py:306-325: channel softmax + the two linear interpolations = soft-argmax of every map -> (C, 2)."""
+    _no(rho > 0, 'kl_divergence_regularizer (rho > 0)')
+    return _Head('sam2d', name)
+
+
+def build_joints_probability(input_shape, name=None, verbose=0):
+    """blocks.py:328-343: 4 * AveragePooling2D((2,2), strides 1) -> GlobalMaxPooling2D on the raw maps -> (C, 1)."""
+    return _Head('jprob', name)
+
+
+def build_context_aggregation(num_joints, num_context, alpha, num_frames=1, name=None):
+    """blocks.py:217-285: pose = alpha * ys + (1 - alpha) * sum(pc * yc) / sum(pc) over each joint's context maps."""
+    _no(num_frames != 1, 'build_context_aggregation(num_frames > 1)')
+    return _Head('agg', name, num_joints=int(num_joints), num_context=int(num_context), alpha=float(alpha))
+
+
+def build_softargmax_1d(input_shape, name=None):
+    """blocks.py:288-303 (zSAM of the 3-D head).  Built by reception.build for every model, only CALLED for dim = 3."""
+    return _Head('sam1d', name)
+
+
+def _fuse_heads(g, outputs):
+    """Replay the recorded graph into a new one, replacing the head-model calls by the fused ops of the layer graph:
+       agg([sam2d(h[..., :nj]), sam2d(h[..., nj:]), jprob(h[..., nj:])]) + jprob(h[..., :nj])  ->  pose_regression_2d_context(h)
+       sam2d(h) + jprob(h)                                                                  ->  pose_regression_2d(h)
+    Returns (new graph, new outputs); a head call left over after the rewrite is an error."""
+    if not any(nd.op.startswith('head_') for nd in g.nodes):
+        return g, outputs
+
+    def sliced(t):
+        nd = t.node
+        if nd is not None and nd.op == 'slice':
+            return nd.inputs[0], nd.attrs['c0'], nd.attrs['c1']
+        return t, 0, t.channels
+
+    plans = {}          # node id -> ('ctx' | 'plain', ...) for the node at whose position the fused op is emitted
+    alias = {}          # head node id -> (anchor node id, output index of the fused op)
+    jprobs = [nd for nd in g.nodes if nd.op == 'head_jprob']
+    used = set()
+    for nd in g.nodes:
+        if nd.op != 'head_agg':
+            continue
+        ys, yc, pc = nd.inputs
+        if not (ys.node.op == 'head_sam2d' and yc.node.op == 'head_sam2d' and pc.node.op == 'head_jprob'):
+            raise NotImplementedError('context aggregation of tensors that are not soft-argmax / probability heads')
+        h, a0, a1 = sliced(ys.node.inputs[0])
+        h2, b0, b1 = sliced(yc.node.inputs[0])
+        h3, c0, c1 = sliced(pc.node.inputs[0])
+        nj, nc = nd.attrs['num_joints'], nd.attrs['num_context']
+        if not (h is h2 is h3 and (a0, a1) == (0, nj) and (b0, b1) == (c0, c1) == (nj, h.channels)
+                and h.channels == nj * (nc + 1)):
+            raise NotImplementedError('context aggregation over an unexpected split of the heat-maps')
+        vis = [j for j in jprobs if j.id not in used and sliced(j.inputs[0])[0] is h and sliced(j.inputs[0])[1:] == (0, nj)]
+        if len(vis) != 1:
+            raise NotImplementedError('context head without its joint-probability on the specialised maps')
+        for n_ in (ys.node, yc.node, pc.node, vis[0]):
+            used.add(n_.id)
+        plans[nd.id] = ('ctx', h, nd.attrs)
+        alias[vis[0].id] = (nd.id, 1)
+    for nd in g.nodes:
+        if nd.op == 'head_sam2d' and nd.id not in used:
+            t = nd.inputs[0]
+            vis = [j for j in jprobs if j.id not in used and j.inputs[0] is t]
+            if len(vis) != 1:
+                raise NotImplementedError('soft-argmax head without its joint-probability model')
+            used.update((nd.id, vis[0].id))
+            plans[nd.id] = ('plain', t, nd.attrs)
+            alias[vis[0].id] = (nd.id, 1)
+    left = [nd for nd in g.nodes if nd.op.startswith('head_') and nd.id not in used and nd.id not in plans]
+    if left:
+        raise NotImplementedError('head model call(s) outside a recordable pattern: %s' % left)
+
+    new = Graph(g.name)
+    new.frames_per_clip = g.frames_per_clip
+    new.weight_specs = list(g.weight_specs)
+    new._weight_names = set(g._weight_names)
+    new._counters = g._counters
+    tmap, fused = {}, {}
+    for nd in g.nodes:
+        if nd.op == 'input':
+            tmap[nd.outs[0].id] = new.input(nd.outs[0].shape, nd.outs[0].kind)
+            continue
+        if nd.id in plans:
+            kind, h, attrs = plans[nd.id]
+            if kind == 'ctx':
+                outs = new.op('pose_regression_2d_context', [tmap[h.id]],
+                              [(1, attrs['num_joints'], 2), (1, attrs['num_joints'], 1)],
+                              {'num_joints': attrs['num_joints'], 'num_context': attrs['num_context'],
+                               'alpha': attrs['alpha']})
+            else:
+                c = h.channels
+                outs = new.op('pose_regression_2d', [tmap[h.id]], [(1, c, 2), (1, c, 1)], {})
+            fused[nd.id] = outs
+            tmap[nd.outs[0].id] = outs[0]
+            continue
+        if nd.id in alias:
+            anchor, idx = alias[nd.id]
+            if anchor not in fused:
+                raise NotImplementedError('joint-probability head recorded before the soft-argmax head it belongs to')
+            tmap[nd.outs[0].id] = fused[anchor][idx]
+            continue
+        if nd.op.startswith('head_'):
+            continue                                    # absorbed operands (ps, pc, vc)
+        attrs = {k: (dict(v) if isinstance(v, dict) else v) for k, v in nd.attrs.items()}
+        outs = new.op(nd.op, [tmap[t.id] for t in nd.inputs], [o.shape for o in nd.outs], attrs, kind=nd.outs[0].kind)
+        outs = outs if isinstance(outs, tuple) else (outs,)
+        for o_src, o_new in zip(nd.outs, outs):
+            tmap[o_src.id] = o_new
+    return new, [tmap[t.id] for t in outputs]
+
+
 def _weight_names(attrs, known):
     """(path in attrs, weight name) for every attribute value that names a weight of the recorded graph."""
     for key, val in attrs.items():
@@ -274,9 +451,10 @@ class Model(object):
         if self._impl is None:
             if self._applied:
                 raise NotImplementedError('Model %r was applied as a layer of another model; compile that one' % self._name)
-            self._graph.outputs = self._outputs
-            self._graph.name = self._name
-            self._impl = _Model(self._graph, name=self._name)
+            g, outs = _fuse_heads(self._graph, self._outputs)
+            g.outputs = outs
+            g.name = self._name
+            self._impl = _Model(g, name=self._name)
         return self._impl
 
     def __getattr__(self, attr):

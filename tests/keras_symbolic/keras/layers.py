@@ -1,7 +1,7 @@
 """keras.layers -> deephar_b200.keras_compat; every other layer class the reference merely imports is a stub that
 fails when it is constructed."""
 from deephar_b200.keras_compat import (Activation, Add, BatchNormalization, Concatenate, Conv2D, Input,  # noqa: F401
-                                       MaxPooling2D, Multiply, SeparableConv2D, TimeDistributed, UpSampling2D,
+                                       Lambda, MaxPooling2D, Multiply, SeparableConv2D, TimeDistributed, UpSampling2D,
                                        ZeroPadding2D, add, concatenate, multiply)
 
 

@@ -10,6 +10,8 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path[:0] = [HERE, os.path.join(HERE, '..', 'golden', 'keras_shim'), os.environ.get('DEEPHAR_REFERENCE', '/root/reference'), ROOT]
 warnings.filterwarnings('ignore')
 _stderr, sys.stderr = sys.stderr, open(os.devnull, 'w')       # the reference prints a banner on import
+import recording_blocks  # noqa: E402
+sys.modules['deephar.models.blocks'] = recording_blocks     # the four parameter-free head builders, recordable
 import deephar  # noqa: E402,F401
 from deephar.models import reception as R  # noqa: E402
 sys.stderr = _stderr
@@ -40,9 +42,24 @@ def spnet_case():
                       'output_shape': [list(s) for s in m.output_shape]}))
 
 
+def _dump(m):
+    print(json.dumps({'weight_specs': [[n, list(s)] for n, s in m.weight_specs],
+                      'plan': [[k.kind, [list(t.shape) for t in k.outs]] for k in m.plan.kops],
+                      'output_shape': [list(s) for s in m.output_shape]}))
+
+
+def full_model_case(concat):
+    """The reference's COMPLETE reception.build() (reception.py:225-321), heads included: BASELINE configs[0]/[1]."""
+    keras_compat.clear_session()
+    _dump(R.build((256, 256, 3), 16, dim=2, num_context_per_joint=2, num_blocks=8, ksize=(5, 5),
+                  concat_pose_confidence=bool(concat), export_heatmaps=bool(concat)))
+
+
 def main():
     if sys.argv[1] == 'spnet':
         return spnet_case()
+    if sys.argv[1] == 'full2d':
+        return full_model_case(int(sys.argv[2]))
     blocks, ksize, heatmaps = int(sys.argv[1]), (5, 5), 48
     keras_compat.clear_session()
     inp = Input(shape=(256, 256, 3))

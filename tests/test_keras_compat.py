@@ -201,3 +201,48 @@ def test_reference_spnet_skeleton_records_the_same_model():
     assert [(n, tuple(s)) for n, s in got['weight_specs']] == want.weight_specs and len(want.weight_specs) > 60
     assert got['plan'] == [[k.kind, [list(t.shape) for t in k.outs]] for k in want.plan.kops]
     assert [tuple(s) for s in got['output_shape']] == [tuple(s) for s in want.output_shape]
+
+
+@pytest.mark.skipif(not os.path.isdir(os.environ.get('DEEPHAR_REFERENCE', '/root/reference')),
+                    reason='needs the reference tree (development container only)')
+@pytest.mark.parametrize('concat', [0, 1])
+def test_reference_full_reception_build_records_the_headline_model(concat):
+    """The reference's COMPLETE `reception.build()` (reception.py:225-321) -- unmodified file, Lambda channel slices
+    and head-model calls included -- on the recording keras, with `deephar.models.blocks`' four parameter-free head
+    builders taken from keras_compat: the recorded model IS deephar_b200.reception.build's (BASELINE configs[0]/[1]:
+    weight list, auto-names, kernel plan, output order and shapes)."""
+    from deephar_b200 import reception
+    here = os.path.dirname(os.path.abspath(__file__))
+    out = subprocess.run([sys.executable, os.path.join(here, 'keras_symbolic', 'run_reference_backbone.py'), 'full2d',
+                          str(concat)], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    got = json.loads([l for l in out.stdout.splitlines() if l.startswith('{')][-1])
+    want = reception.build((256, 256, 3), 16, dim=2, num_context_per_joint=2, num_blocks=8, ksize=(5, 5),
+                           concat_pose_confidence=bool(concat), export_heatmaps=bool(concat))
+    assert [(n, tuple(s)) for n, s in got['weight_specs']] == want.weight_specs
+    assert got['plan'] == [[k.kind, [list(t.shape) for t in k.outs]] for k in want.plan.kops]
+    assert [tuple(s) for s in got['output_shape']] == [tuple(s) for s in want.output_shape]
+    assert len(got['output_shape']) == 16        # 8 x (pose, visible), or 8 x (pose|visible, heat-maps)
+
+
+def test_head_models_and_lambda_slices():
+    K.clear_session()
+    inp = K.Input(shape=(32, 32, 8))
+    h = K.Conv2D(48, (1, 1), use_bias=False, name='RegMap')(inp)
+    hs = K.Lambda(lambda x: x[:, :, :, :16])(h)
+    hc = K.Lambda(lambda x: x[:, :, :, 16:])(h)
+    pose = K.build_context_aggregation(16, 2, 0.8, name='Agg')(
+        [K.build_softargmax_2d((32, 32, 16), name='sSAM')(hs), K.build_softargmax_2d((32, 32, 32), name='cSAM')(hc),
+         K.build_joints_probability((32, 32, 32), name='cjProb')(hc)])
+    vis = K.build_joints_probability((32, 32, 16), name='sjProb')(hs)
+    m = K.Model(inputs=inp, outputs=[pose, vis, hs])
+    assert [k.kind for k in m.plan.kops] == ['conv', 'pose_regression_2d_context']
+    assert m.output_shape == [(None, 16, 2), (None, 16, 1), (None, 32, 32, 16)]
+    # a Lambda that is not a channel slice, and a head call outside the recordable patterns, fail at build time
+    with pytest.raises(NotImplementedError):
+        K.Lambda(lambda x: 4 * x)(h)
+    with pytest.raises(NotImplementedError):
+        K.Lambda(lambda x: x[:, 1:, :, :])(h)
+    lone = K.Model(inputs=inp, outputs=[K.build_softargmax_2d((32, 32, 48))(h)])
+    with pytest.raises(NotImplementedError):
+        lone.plan
