@@ -458,7 +458,8 @@ class Model(object):
         return self._impl
 
     def __getattr__(self, attr):
-        if attr.startswith('_'):
+        # only reached for names this wrapper does not define: everything else is the compiled model's
+        if attr.startswith('__') or attr in ('_impl', '_applied', '_graph', '_inputs', '_outputs', '_single', '_name'):
             raise AttributeError(attr)
         return getattr(self._compiled(), attr)
 
