@@ -2,7 +2,9 @@
 reference's evaluators: poses back to image coordinates with the inverse crop affine, then PCKh / mean distance
 (exp/common/mpii_tools.py:93-129, deephar/utils/transform.py:136-209, deephar/measures.py:5-93).  Same function
 names and argument meaning as the reference; arrays may be numpy (copied to the device) or CUDA tensors, results
-come back as numpy / python floats.  One kernel (dh_pose_eval_f32); no CPU path.
+come back as numpy / python floats.  One kernel (dh_pose_eval_f32); no CPU path for the pose arithmetic.
+The action evaluators' arithmetic after the forward (penn_tools.py:13-36, 85-150: a product of a few KB of
+probabilities per video and an arg-max) is host code here as it is there: `multiclip_action_scores`.
 """
 import ctypes as C
 
@@ -101,3 +103,35 @@ def eval_singleperson_pckh(model, fval, pval, afmat_val, headsize_val, batch_siz
             valid[b] = v if valid[b] is None else valid[b] + v
     used = torch.tensor(PCKH_USED_JOINTS, device='cuda')
     return [float(hits[b][used].sum().item()) / float(valid[b][used].sum().item()) for b in range(num_blocks)]
+
+
+def multiclip_action_scores(probs, video_of_item, truth, n_videos=None):
+    """exp/common/penn_tools.py:85-150 / ntu_tools.py after the predictions: every video is scored by the product, over
+    its clips x {no flip, h-flip}, of each prediction block's action probabilities; arg-max against the label; accuracy
+    in percent per block.  probs: (num_blocks, N_items, n_act) or a list of per-block (N_items, n_act) arrays (what
+    `model.predict` returns for a batch of all clips); video_of_item (N_items,); truth (n_videos,) class indices or
+    (n_videos, n_act) one-hot.  A few KB of arithmetic: done on the host in float64 like the reference (the forward
+    that produces `probs` is where the time goes -- run it batched, not clip by clip as the reference does)."""
+    probs = np.stack([np.asarray(p) for p in probs]) if isinstance(probs, (list, tuple)) else np.asarray(probs)
+    if probs.ndim != 3:
+        raise ValueError('multiclip_action_scores: probs must be (num_blocks, N_items, n_act), got %s' % (probs.shape,))
+    video_of_item = np.asarray(video_of_item, np.int64).reshape(-1)
+    truth = np.asarray(truth)
+    if truth.ndim == 2:
+        truth = truth.argmax(axis=-1)
+    nb, n_items, n_act = probs.shape
+    if len(video_of_item) != n_items:
+        raise ValueError('multiclip_action_scores: %d items but %d video indices' % (n_items, len(video_of_item)))
+    n_videos = int(n_videos if n_videos is not None else len(truth))
+    a_pred = np.ones((nb, n_videos, n_act), np.float64)
+    for b in range(nb):
+        np.multiply.at(a_pred[b], video_of_item, probs[b].astype(np.float64))     # unbuffered: items in order
+    correct = a_pred.argmax(axis=-1) == truth[None, :]
+    return 100.0 * correct.sum(axis=-1) / n_videos
+
+
+def singleclip_action_scores(preds, action_true):
+    """exp/common/penn_tools.py:13-36 after the predict: fraction of clips whose arg-max class is the label's, per block."""
+    action_true = np.asarray(action_true)
+    label = action_true.argmax(axis=-1) if action_true.ndim == 2 else action_true
+    return [float(np.mean(np.asarray(p).argmax(axis=-1) == label)) for p in preds]

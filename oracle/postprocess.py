@@ -41,3 +41,18 @@ def mean_distance_error(y_true, y_pred):
     valid = _valid(y_true)
     dist = np.sqrt(np.sum((y_true - y_pred) ** 2, axis=-1))
     return float((dist * valid).sum() / valid.sum())
+
+
+def multiclip_action_scores(probs, video_of_item, truth, n_videos=None):
+    """exp/common/penn_tools.py:85-150 (eval_multiclip_dataset) after the predictions: per video the PRODUCT over its
+    clips x {no flip, h-flip} of every block's action probabilities (float64 accumulator starting at 1), arg-max against
+    the label, accuracy in percent per block.  probs (num_blocks, N_items, n_act); plain loops as in the reference."""
+    probs = np.asarray(probs)
+    nb, n_items, n_act = probs.shape
+    n_videos = int(n_videos if n_videos is not None else np.max(video_of_item) + 1)
+    a_pred = np.ones((nb, n_videos, n_act))
+    for k in range(n_items):
+        for b in range(nb):
+            a_pred[b, video_of_item[k], :] *= probs[b][k]
+    correct = np.argmax(a_pred, axis=-1) == np.asarray(truth)[None, :]
+    return 100 * np.sum(correct, axis=-1) / n_videos

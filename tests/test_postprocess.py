@@ -53,3 +53,26 @@ def test_eval_singleperson_pckh_end_to_end(cuda):
     for b in range(2):
         y_pred = oracle_pp.transform_pose_sequence(A, outs[2 * b], inverse=True)
         assert scores[b] == pytest.approx(oracle_pp.pckh(y_true, y_pred, head, 0.5), abs=1e-9)
+
+
+def test_multiclip_action_scores_match_the_reference_evaluator():
+    """tests/golden/ref_action_eval.npz: scores printed by the reference's own eval_multiclip_dataset
+    (exp/common/penn_tools.py:85-150) on seeded probabilities (make_action_eval_golden.py)."""
+    from deephar_b200 import postprocess as pp
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'ref_action_eval.npz'))
+    want = G['scores']
+    assert want.shape == (4,) and want[-1] > want[0]
+    got_o = oracle_pp.multiclip_action_scores(G['probs'], G['video_of_item'], G['truth'])
+    got_p = pp.multiclip_action_scores(G['probs'], G['video_of_item'], G['truth'])
+    assert np.array_equal(got_o, want) and np.array_equal(got_p, want)
+    # list-of-blocks input, one-hot labels, items in another order (a product does not care), bad shapes
+    perm = np.random.default_rng(0).permutation(len(G['video_of_item']))
+    onehot = np.eye(15)[G['truth']]
+    got2 = pp.multiclip_action_scores([p[perm] for p in G['probs']], G['video_of_item'][perm], onehot)
+    assert np.array_equal(got2, want)
+    with pytest.raises(ValueError):
+        pp.multiclip_action_scores(G['probs'][0], G['video_of_item'], G['truth'])
+    with pytest.raises(ValueError):
+        pp.multiclip_action_scores(G['probs'], G['video_of_item'][:-1], G['truth'])
+    single = pp.singleclip_action_scores(list(G['probs']), G['truth'][G['video_of_item']])
+    assert len(single) == 4 and all(0.0 <= v <= 1.0 for v in single) and single[-1] > single[0]
