@@ -135,3 +135,47 @@ def singleclip_action_scores(preds, action_true):
     action_true = np.asarray(action_true)
     label = action_true.argmax(axis=-1) if action_true.ndim == 2 else action_true
     return [float(np.mean(np.asarray(p).argmax(axis=-1) == label)) for p in preds]
+
+
+def human36m_mpjpe(preds, afmat, rootz, scam, pose_w, resol_z=2000., map_to_pa17j=None):
+    """exp/common/h36m_tools.py:12-99 after the predict (the H36M evaluator's score): per prediction block, (x, y) of
+    the normalised predictions back to image pixels with the inverse crop affine, z = resol_z * (z - 0.5) + rootz,
+    camera inverse projection (deephar/utils/camera.py:52-71, distortion coefficients included) with each sample's
+    serialised camera [R(9) t(3) f(2) c(2) p(2) k(3)], predicted and true poses root-centred, mean per-joint distance
+    in mm.  preds: list of (N, nj, >= 3) arrays (what `model.predict` returns); -> list of errors, one per block.
+    Vectorised over samples on the host in float64: N x 17 x 3 numbers (the reference loops per sample)."""
+    afmat = np.asarray(afmat, np.float64)
+    scam = np.asarray(scam, np.float64)
+    rootz = np.asarray(rootz, np.float64).reshape(-1, 1)
+    y_true = np.array(pose_w, np.float64)
+    if map_to_pa17j is not None:
+        y_true = y_true[:, map_to_pa17j, :]
+    y_true = y_true - y_true[:, 0:1, :]
+    n = len(y_true)
+    R = scam[:, 0:9].reshape(n, 3, 3)
+    t, f, c, p = scam[:, None, 9:12], scam[:, None, 12:14], scam[:, None, 14:16], scam[:, None, 16:18]
+    k = scam[:, 18:21] if scam.shape[1] > 18 else None
+    Rinv = np.linalg.inv(R)
+    Ainv = np.linalg.inv(afmat)
+    valid = np.all(y_true > -1e6, axis=-1)
+    out = []
+    for pred in preds:
+        y = np.array(pred, np.float64)[:, :, 0:3]
+        if y.shape[0] != n:
+            raise ValueError('human36m_mpjpe: %d predictions for %d samples' % (y.shape[0], n))
+        xy = np.einsum('nij,nkj->nki', Ainv[:, :2, :2], y[:, :, 0:2]) + Ainv[:, None, :2, 2]
+        z = resol_z * (y[:, :, 2] - 0.5) + rootz
+        if map_to_pa17j is not None:
+            xy, z = xy[:, map_to_pa17j], z[:, map_to_pa17j]
+        x = (xy - c) / f
+        if k is not None:
+            r2 = x[..., 0] ** 2 + x[..., 1] ** 2
+            radial = 1. + r2 * k[:, None, 0] + r2 ** 2 * k[:, None, 1] + r2 ** 3 * k[:, None, 2]
+            tan = np.sum(x * p, axis=-1)
+            x = (x - r2[..., None] * p) / (radial + tan)[..., None]
+        cam = np.concatenate([x * z[..., None], z[..., None]], axis=-1)
+        w = np.einsum('nij,nkj->nki', Rinv, cam) + t
+        w = w - w[:, 0:1, :]
+        dist = np.sqrt(np.sum((y_true - w) ** 2, axis=-1))
+        out.append(float((dist * valid).sum() / valid.sum()))
+    return out

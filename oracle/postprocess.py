@@ -56,3 +56,44 @@ def multiclip_action_scores(probs, video_of_item, truth, n_videos=None):
             a_pred[b, video_of_item[k], :] *= probs[b][k]
     correct = np.argmax(a_pred, axis=-1) == np.asarray(truth)[None, :]
     return 100 * np.sum(correct, axis=-1) / n_videos
+
+
+def camera_inverse_project(scam, uvd):
+    """deephar/utils/camera.py:52-71 + camera_deserialize (:97-110) for ONE serialised camera
+    [R(9) t(3) f(2) c(2) p(2) k(3, optional)]: (u, v pixels, depth mm) -> world mm.  Like the reference, the working
+    copy keeps the dtype of `uvd` (float32 predictions stay float32 through the in-place steps)."""
+    scam = np.asarray(scam, np.float64)
+    R, t = scam[0:9].reshape(3, 3), scam[9:12].reshape(3, 1)
+    f, c, p = scam[12:14].reshape(1, 2), scam[14:16].reshape(1, 2), scam[16:18].reshape(1, 2)
+    k = scam[18:21] if len(scam) > 18 else None
+    x = uvd.copy()
+    x[:, 0:2] = (x[:, 0:2] - c) / f
+    if k is not None:
+        r2 = np.power(x[:, 0], 2) + np.power(x[:, 1], 2)
+        radial = 1. + r2 * k[0] + np.power(r2, 2) * k[1] + np.power(r2, 3) * k[2]
+        tan = np.sum(x[:, 0:2] * p, axis=-1)
+        x[:, 0:2] -= np.dot(np.expand_dims(r2, axis=-1), p)
+        x[:, 0:2] /= np.expand_dims(radial + tan, axis=-1)
+    x[:, 0:2] *= x[:, 2:3]
+    return (np.matmul(np.linalg.inv(R), x.T) + t).T
+
+
+def human36m_mpjpe(preds, afmat, rootz, scam, pose_w, resol_z=2000.):
+    """exp/common/h36m_tools.py:12-99 after the predict: per block, (x, y) back through the inverse crop affine,
+    z = resol_z * (z - 0.5) + rootz, camera inverse projection per sample, both poses root-centred, mean joint
+    distance in mm.  preds: list of (N, nj, >= 3); per-sample loop and in-place (dtype-preserving) updates as in the
+    reference, so float32 predictions are rounded to float32 after every step exactly as there."""
+    y_true = np.array(pose_w, np.float64)
+    y_true -= y_true[:, 0:1, :]
+    rootz = np.asarray(rootz, np.float64).reshape(-1, 1)
+    out = []
+    for p in preds:
+        y = np.array(p)[:, :, 0:3]
+        y[:, :, 0:2] = transform_pose_sequence(np.array(afmat, np.float64), y[:, :, 0:2], inverse=True)
+        y[:, :, 2] = (resol_z * (y[:, :, 2] - 0.5)) + rootz
+        w = np.zeros(y_true.shape)
+        for j in range(len(y)):
+            w[j] = camera_inverse_project(scam[j], y[j])
+        w -= w[:, 0:1, :]
+        out.append(mean_distance_error(y_true, w))
+    return out

@@ -76,3 +76,27 @@ def test_multiclip_action_scores_match_the_reference_evaluator():
         pp.multiclip_action_scores(G['probs'], G['video_of_item'][:-1], G['truth'])
     single = pp.singleclip_action_scores(list(G['probs']), G['truth'][G['video_of_item']])
     assert len(single) == 4 and all(0.0 <= v <= 1.0 for v in single) and single[-1] > single[0]
+
+
+def test_human36m_mpjpe_matches_the_reference_evaluator():
+    """tests/golden/ref_h36m_eval.npz: errors returned by the reference's own eval_human36m_sc_error
+    (exp/common/h36m_tools.py:12-136, deephar/utils/camera.py) on seeded predictions and cameras with distortion."""
+    from deephar_b200 import postprocess as pp
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'ref_h36m_eval.npz'))
+    want = G['scores']
+    assert want.shape == (3,) and want[0] > want[2] > 1.0
+    args = (list(G['preds']), G['afmat'], G['rootz'], G['scam'], G['pose_w'])
+    got_o = oracle_pp.human36m_mpjpe(*args, resol_z=float(G['resol_z']))
+    got_p = pp.human36m_mpjpe(*args, resol_z=float(G['resol_z']))
+    assert np.allclose(got_o, want, rtol=1e-12, atol=1e-9)          # same dtype-preserving in-place steps as the reference
+    # the product computes in float64 throughout; the reference rounds its float32 predictions after every step
+    assert np.allclose(got_p, want, rtol=1e-6)
+    assert np.allclose(got_p, oracle_pp.human36m_mpjpe([q.astype(np.float64) for q in args[0]], *args[1:],
+                                                       resol_z=float(G['resol_z'])), rtol=1e-12)
+    # cameras without distortion coefficients, a joint re-mapping, and a length mismatch
+    ident = list(range(17))
+    assert np.allclose(pp.human36m_mpjpe(*args, resol_z=float(G['resol_z']), map_to_pa17j=ident), got_p, rtol=1e-12)
+    nod = pp.human36m_mpjpe(args[0], args[1], args[2], G['scam'][:, :18], args[4])
+    assert all(abs(a - b) < 5.0 for a, b in zip(nod, want)) and not np.allclose(nod, want, rtol=1e-5)
+    with pytest.raises(ValueError):
+        pp.human36m_mpjpe([G['preds'][0][:-1]], args[1], args[2], args[3], args[4])
