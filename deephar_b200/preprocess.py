@@ -100,6 +100,43 @@ def mpii_windows(objpos, scale, dconf=None):
     return pos, 200 * dconf['scale'] * scale
 
 
+def clip_frame_index(sequence_size, subsample, num_frames):
+    """deephar/data/datasets.py:6-38 with random_clip=False: the frame indices of the evaluation clip of a video --
+    `num_frames` frames `subsample` apart, centred; the step shrinks for short videos and videos shorter than the clip
+    repeat frames (the index grid is stretched by 1.5 until it fits)."""
+    if not (isinstance(subsample, (int, np.integer)) and subsample > 0):
+        raise ValueError('clip_frame_index: subsample must be a positive integer')
+    stretch, size = 1.0, float(sequence_size)
+    while stretch * sequence_size < num_frames:
+        stretch *= 1.5
+    size = sequence_size * stretch
+    subsample = min(int(subsample), int(size / num_frames))
+    span = subsample * (num_frames - 1) + 1
+    start = int((size - span) / 2)
+    frames = list(range(start, start + span, subsample))
+    return [int(f / stretch) for f in frames] if stretch > 1 else frames
+
+
+def clip_window(image_size, dconf=None, bbox=None):
+    """deephar/data/pennaction.py:118-134 (the same lines in data/ntu.py): the ONE crop window shared by all frames of an
+    evaluation clip -- centre and size of `bbox` [x0, y0, x1, y1] (ground-truth or predicted), or, without one, a square
+    of dconf['scale'] * max(w, h) around the image centre; windows thinner than 32 pixels become 32 x 32; the centre
+    moves by scale * (transx, transy).  -> (objpos (2,), winsize (2,)) as FramePipeline takes them (repeat per frame)."""
+    dconf = dconf or {'scale': 1, 'transx': 0, 'transy': 0}
+    w, h = image_size
+    if bbox is None:
+        side = dconf['scale'] * max(w, h)
+        objpos, winsize = np.array([w / 2, h / 2], np.float64), (side, side)
+    else:
+        bbox = np.asarray(bbox, np.float64)
+        objpos = np.array([(bbox[0] + bbox[2]) / 2, (bbox[1] + bbox[3]) / 2])
+        winsize = (bbox[2] - bbox[0], bbox[3] - bbox[1])
+    if min(winsize) < 32:
+        winsize = (32, 32)
+    objpos = objpos + dconf['scale'] * np.array([dconf['transx'], dconf['transy']], np.float64)
+    return objpos, np.array(winsize, np.float64)
+
+
 class FramePipeline(object):
     """Batched evaluation input pipeline bound to one device.
 

@@ -167,3 +167,20 @@ def test_tables_randomised_against_oracle_and_pillow():
         img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
         want = np.asarray(Image.fromarray(img).resize((ow, oh), Image.BILINEAR))
         assert np.array_equal(opre.resize_bilinear(img, (ow, oh)), want), ((h, w), (ow, oh))
+
+
+def test_clip_sampling_and_windows_match_the_reference_helpers():
+    """tests/golden/ref_clip_windows.npz: outputs of the reference's own get_clip_frame_index (random_clip=False) and
+    bbox_to_objposwin / objposwin_to_bbox combined as data/pennaction.py:118-134 does (make_clipwindow_golden.py)."""
+    G = np.load(os.path.join(HERE, 'golden', 'ref_clip_windows.npz'))
+    for (size, sub, nf), want in zip(G['cases'], G['frames']):
+        got = preprocess.clip_frame_index(int(size), int(sub), int(nf))
+        assert got == [int(v) for v in want[:nf]], (size, sub, nf)
+        assert len(got) == nf and all(0 <= f < size for f in got)
+    for row in G['windows']:
+        w, h, scale, tx, ty = row[:5]
+        bbox = None if np.isnan(row[5]) else row[5:9]
+        objpos, win = preprocess.clip_window((w, h), {'scale': scale, 'transx': tx, 'transy': ty}, bbox)
+        assert np.allclose(objpos, row[9:11], rtol=0, atol=1e-12) and np.allclose(win, row[11:13], rtol=0, atol=1e-12)
+    with pytest.raises(ValueError):
+        preprocess.clip_frame_index(100, 0, 16)
