@@ -10,6 +10,11 @@ folds T into the batch, layers.py:66-104) or 'clip' (B clips; the action head tr
 """
 
 
+def _trace():
+    from . import keras_trace
+    return keras_trace
+
+
 class Tensor(object):
     __slots__ = ('g', 'id', 'shape', 'kind', 'node', 'out_index')
 
@@ -28,6 +33,28 @@ class Tensor(object):
 
     def __repr__(self):
         return 'T%d%s<%s>' % (self.id, self.shape, self.node.op if self.node else 'input')
+
+    # Arithmetic and indexing exist for the bodies of `Lambda` layers in Keras-style model code: each records a
+    # backend-op node (keras_trace.py) that the front end rewrites into a fused layer op, or rejects, at build time.
+    def __mul__(self, o):
+        return _trace().arith('mul', self, o)
+
+    def __rmul__(self, o):
+        return _trace().arith('mul', self, o)
+
+    def __sub__(self, o):
+        return _trace().arith('sub', self, o)
+
+    def __truediv__(self, o):
+        return _trace().arith('div', self, o)
+
+    def __neg__(self):
+        return _trace().neg(self)
+
+    def __getitem__(self, idx):
+        return _trace().getitem(self, idx)
+
+    __hash__ = object.__hash__
 
 
 class Node(object):
@@ -108,6 +135,35 @@ class Graph(object):
         for i, s in enumerate(out_shapes):
             node.outs.append(Tensor(self, s, kind, node, i))
         return node.outs[0] if len(node.outs) == 1 else tuple(node.outs)
+
+    def signatures(self, tensors=None):
+        """One digest per tensor (default: the outputs) of the expression that computes it: op, attributes (weight and
+        layer names included), operand digests, shapes.  Two graphs whose outputs have equal digests are the same
+        function of the same weights, whatever order their nodes were recorded in."""
+        import hashlib
+        memo = {}
+
+        def canon(v):
+            if isinstance(v, dict):
+                return tuple(sorted((k, canon(x)) for k, x in v.items()))
+            if isinstance(v, (list, tuple)):
+                return tuple(canon(x) for x in v)
+            return v
+
+        def sig(t):
+            if t.id not in memo:
+                nd = t.node
+                body = repr((nd.op, canon(nd.attrs), [sig(i) for i in nd.inputs], t.out_index, t.shape, t.kind))
+                memo[t.id] = hashlib.sha1(body.encode()).hexdigest()
+            return memo[t.id]
+
+        import sys
+        limit = sys.getrecursionlimit()
+        sys.setrecursionlimit(max(limit, 20000))
+        try:
+            return [sig(t) for t in (self.outputs if tensors is None else tensors)]
+        finally:
+            sys.setrecursionlimit(limit)
 
     def num_params(self):
         n = 0

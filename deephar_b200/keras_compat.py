@@ -19,8 +19,9 @@ in deephar_b200.layers and re-exported here (`channel_softmax_2d`, `softargmax2d
 `TimeDistributed(layer, name=...)` is the identity on the folded B*T frame axis and passes its name to the wrapped
 layer, which is how Keras names the weights of a wrapped layer in a checkpoint.
 """
+from . import keras_trace as backend          # `from deephar_b200.keras_compat import backend as K`
 from . import layers as L
-from .graph import Graph
+from .graph import Graph, Tensor
 from .layers import (act_channel_softmax, channel_slice, channel_softmax_2d, depth_expectation,  # noqa: F401
                      global_max_min_pooling, keypoint_confidence, kronecker_prod, max_min_pooling, softargmax2d)
 from .model import Model as _Model
@@ -75,9 +76,25 @@ class Layer(object):
             raise NotImplementedError('%s %r: calling a weighted layer twice (weight sharing) is not used by the '
                                       'reference models' % (type(self).__name__, self.name))
         self._built = True
+        if self._spatial and isinstance(x, Tensor):
+            x = _as_image(x)
         return self.call(x)
 
     _has_weights = False
+    _spatial = False            # works on the (rows, cols, channels) axes of its input
+
+
+_TD_DEPTH = [0]                 # > 0 while a TimeDistributed wrapper applies its layer
+
+
+def _as_image(x):
+    """What a spatial layer sees.  Backend-op results and per-joint tensors are 4-D (None, T, joints, c) for Keras: a
+    plain Conv2D / MaxPooling2D treats (T, joints) as the image (spnet.py:113-132) -- here a clip-axis tensor."""
+    if backend.is_raw(x):
+        return backend.as_map(x, per_frame=_TD_DEPTH[0] > 0)
+    if _TD_DEPTH[0] == 0 and x.kind == 'frame' and x.g.frames_per_clip > 1 and x.shape[0] == 1 and backend._is_dense(x):
+        return L.frames_to_clip(x)
+    return x
 
 
 def _no(cond, what):
@@ -87,6 +104,7 @@ def _no(cond, what):
 
 class Conv2D(Layer):
     _has_weights = True
+    _spatial = True
 
     def __init__(self, filters, kernel_size, strides=(1, 1), padding='valid', data_format=None, dilation_rate=(1, 1),
                  activation=None, use_bias=True, name=None, **kwargs):
@@ -104,6 +122,7 @@ class Conv2D(Layer):
 
 class SeparableConv2D(Layer):
     _has_weights = True
+    _spatial = True
 
     def __init__(self, filters, kernel_size, strides=(1, 1), padding='valid', data_format=None, depth_multiplier=1,
                  activation=None, use_bias=True, name=None, **kwargs):
@@ -116,11 +135,25 @@ class SeparableConv2D(Layer):
         self.filters, self.kernel_size, self.strides, self.padding = int(filters), kernel_size, strides, padding
 
     def call(self, x):
-        return L.sepconv2d(x, self.filters, self.kernel_size, self.strides, self.padding, name=self.name)
+        out = L.sepconv2d(x, self.filters, self.kernel_size, self.strides, self.padding, name=self.name)
+        self._node = out.node
+        return out
+
+    # The reference freezes a SeparableConv2D into a constant operator (the soft-argmax grid, layers.py:184-194):
+    # get_weights() -> edit -> set_weights(); trainable = False.  The kernels then are constants of the graph.
+    def get_weights(self):
+        import numpy as np
+        g = self._node.outs[0].g
+        shapes = dict(g.weight_specs)
+        return [np.zeros(shapes[self._node.attrs[k]], np.float32) for k in ('depthwise', 'pointwise')]
+
+    def set_weights(self, weights):
+        backend.freeze_separable(self._node, weights)
 
 
 class BatchNormalization(Layer):
     _has_weights = True
+    _spatial = True
 
     def __init__(self, axis=-1, momentum=0.99, epsilon=1e-3, center=True, scale=True, name=None, **kwargs):
         Layer.__init__(self, name, **{k: v for k, v in kwargs.items() if not k.endswith(('_initializer', '_regularizer',
@@ -136,20 +169,36 @@ class BatchNormalization(Layer):
 
 
 class Activation(Layer):
+    """Activation('relu' | 'sigmoid' | 'softmax'), or Activation(function): the function is run on the symbolic tensor
+    (`Activation(channel_softmax_2d(alpha=...))`, deephar/activations.py:3-16) and must come out as a known op."""
+
     def __init__(self, activation, name=None, **kwargs):
         Layer.__init__(self, name, **kwargs)
-        if activation not in ('relu', 'sigmoid', 'softmax'):
+        if not callable(activation) and activation not in ('relu', 'sigmoid', 'softmax'):
             raise NotImplementedError('Activation(%r): the reference models use relu / sigmoid / softmax and the '
                                       'helpers channel_softmax_2d(...)' % (activation,))
         self.activation = activation
 
     def call(self, x):
+        if callable(self.activation):
+            out = self.activation(x)
+            if not isinstance(out, Tensor):
+                raise NotImplementedError('Activation(function): the function did not return a tensor')
+            if backend.is_raw(out):
+                out.node.attrs['name'] = self.name
+            return out
+        if backend.is_raw(x):
+            if self.activation != 'relu':
+                return backend.activation(x, self.activation, name=self.name)
+            x = _as_image(x)                    # relu of e.g. a max+min pooling: a map again
         if self.activation == 'softmax' and x.kind != 'frame':
             return L.softmax_lastaxis(x, name=self.name)
         return L.Activation(x, self.activation, name=self.name)
 
 
 class MaxPooling2D(Layer):
+    _spatial = True
+
     def __init__(self, pool_size=(2, 2), strides=None, padding='valid', data_format=None, name=None, **kwargs):
         Layer.__init__(self, name, **kwargs)
         self.pool_size, self.strides, self.padding = pool_size, strides, padding
@@ -159,6 +208,8 @@ class MaxPooling2D(Layer):
 
 
 class UpSampling2D(Layer):
+    _spatial = True
+
     def __init__(self, size=(2, 2), data_format=None, name=None, **kwargs):
         Layer.__init__(self, name, **kwargs)
         self.size = size
@@ -168,6 +219,8 @@ class UpSampling2D(Layer):
 
 
 class ZeroPadding2D(Layer):
+    _spatial = True
+
     def __init__(self, padding=(1, 1), data_format=None, name=None, **kwargs):
         Layer.__init__(self, name, **kwargs)
         if isinstance(padding, int):
@@ -180,45 +233,57 @@ class ZeroPadding2D(Layer):
         return L.ZeroPadding2D(x, self.padding)
 
 
-class _SliceProbe(object):
-    """What a Lambda body sees instead of a tensor: it may take a slice of the channel axis, nothing else."""
+class AveragePooling2D(Layer):
+    """Only inside the joint-confidence construction (layers.py:111-115): recorded as a backend op."""
 
-    def __init__(self, t):
-        self._t = t
+    def __init__(self, pool_size=(2, 2), strides=None, padding='valid', data_format=None, name=None, **kwargs):
+        Layer.__init__(self, name, **kwargs)
+        self.pool_size = L._pair(pool_size)
+        self.strides = self.pool_size if strides is None else L._pair(strides)
+        self.padding = padding
 
-    def __getitem__(self, idx):
-        idx = idx if isinstance(idx, tuple) else (idx,)
-        full = slice(None, None, None)
-        if len(idx) != len(self._t.shape) + 1 or any(i != full for i in idx[:-1]) or not isinstance(idx[-1], slice) \
-                or idx[-1].step not in (None, 1):
-            raise NotImplementedError('Lambda: only channel slices x[..., a:b] can be recorded')
-        c = self._t.channels
-        a, b, _ = idx[-1].indices(c)
-        return L.channel_slice(self._t, a, b)
+    def call(self, x):
+        return backend.average_pooling_2d(x, self.pool_size, self.strides, self.padding)
 
-    def __getattr__(self, name):
-        raise NotImplementedError('Lambda: only channel slices x[..., a:b] can be recorded (the body used .%s)' % name)
+
+class GlobalMaxPooling2D(Layer):
+    def __init__(self, data_format=None, name=None, **kwargs):
+        Layer.__init__(self, name, **kwargs)
+
+    def call(self, x):
+        return backend.global_max_pooling_2d(x)
+
+
+class GlobalMaxPooling1D(Layer):
+    def __init__(self, name=None, **kwargs):
+        Layer.__init__(self, name, **kwargs)
+
+    def call(self, x):
+        return backend.global_max_pooling_1d(x)
 
 
 class Lambda(Layer):
-    """keras.layers.Lambda, for the one body the reference's forward path needs outside its parameter-free head models:
-    a slice of the channel axis (`Lambda(lambda x: x[:,:,:,:num_joints])`, reception.py:171-172).  Any other body is
-    arbitrary backend arithmetic and is rejected."""
+    """keras.layers.Lambda.  The body runs on the symbolic tensor(s): a slice of the channel axis
+    (`Lambda(lambda x: x[:,:,:,:num_joints])`, reception.py:171-172) is a view; arithmetic and `keras.backend` calls
+    (`K.tile`, `K.sum`, `4 * AveragePooling2D(...)(x)`, ...) record backend-op nodes (keras_trace.py) which must add up
+    to one of the reference's parameter-free constructions when the model is built -- any other body is rejected then,
+    naming the ops.  Indexing other than a channel slice is rejected here."""
 
     def __init__(self, function, name=None, **kwargs):
         Layer.__init__(self, name, **{k: v for k, v in kwargs.items() if k not in ('output_shape', 'arguments', 'mask')})
         self.function = function
 
     def call(self, x):
-        from .graph import Tensor
         try:
-            out = self.function(_SliceProbe(x))
+            out = self.function(list(x) if isinstance(x, (list, tuple)) else x)
         except NotImplementedError:
             raise
-        except Exception as e:                                  # K.* on the probe, arithmetic, ...
-            raise NotImplementedError('Lambda: only channel slices x[..., a:b] can be recorded (%s)' % e)
+        except (TypeError, AttributeError, IndexError) as e:            # Python / numpy arithmetic on a symbolic tensor
+            raise NotImplementedError('Lambda: the body cannot be recorded (%s: %s)' % (type(e).__name__, e))
         if not isinstance(out, Tensor):
-            raise NotImplementedError('Lambda: only channel slices x[..., a:b] can be recorded')
+            raise NotImplementedError('Lambda: the body did not return a tensor')
+        if backend.is_raw(out) and self.name is not None:
+            out.node.attrs['name'] = self.name
         return out
 
 
@@ -233,22 +298,34 @@ class TimeDistributed(Layer):
             layer.name = name
 
     def call(self, x):
-        return self.layer(x)
+        _TD_DEPTH[0] += 1
+        try:
+            return self.layer(x)
+        finally:
+            _TD_DEPTH[0] -= 1
 
 
 class _Merge(Layer):
     fn = None
+    raw = None
 
     def call(self, ts):
-        return type(self).fn(list(ts), name=self.name)
+        ts = list(ts)
+        if any(backend.is_raw(t) for t in ts):
+            if self.raw is None:
+                raise NotImplementedError('%s of a backend-op result' % type(self).__name__)
+            return backend.merge(self.raw, ts, name=self.name)
+        return type(self).fn(ts, name=self.name)
 
 
 class Add(_Merge):
     fn = staticmethod(L.add)
+    raw = 'add'
 
 
 class Concatenate(_Merge):
     fn = staticmethod(L.concatenate)
+    raw = 'concat'
 
     def __init__(self, axis=-1, name=None, **kwargs):
         _Merge.__init__(self, name, **kwargs)
@@ -257,6 +334,7 @@ class Concatenate(_Merge):
 
 class Multiply(_Merge):
     fn = staticmethod(L.multiply)
+    raw = 'multiply'
 
 
 def add(inputs, name=None):
@@ -283,15 +361,16 @@ class _Head(object):
 
     def __call__(self, x):
         xs = list(x) if isinstance(x, (list, tuple)) else [x]
-        g = xs[0].g
-        if self.kind in ('sam2d', 'jprob'):
-            h, w, c = xs[0].shape
-            shape = (1, c, 2 if self.kind == 'sam2d' else 1)
-        elif self.kind == 'agg':
-            shape = (1, self.attrs['num_joints'], 2)
+        ks = backend.kshape(xs[0])
+        if self.kind == 'sam2d':
+            shape = ks[:-3] + (ks[-1], 2)
+        elif self.kind == 'jprob':
+            shape = ks[:-3] + (ks[-1], 1)
+        elif self.kind == 'sam1d':
+            shape = ks[:-2] + (ks[-1], 1)
         else:
-            raise NotImplementedError('head model %r is not recordable yet' % self.kind)
-        return g.op('head_' + self.kind, xs, shape, dict(self.attrs, name=self.name))
+            shape = ks[:-2] + (self.attrs['num_joints'], 2)
+        return xs[0].g.op('head_' + self.kind, xs, [shape], dict(self.attrs, name=self.name), kind='raw')
 
 
 def build_softargmax_2d(input_shape, rho=0., name=None):
@@ -314,96 +393,6 @@ def build_context_aggregation(num_joints, num_context, alpha, num_frames=1, name
 def build_softargmax_1d(input_shape, name=None):
     """blocks.py:288-303 (zSAM of the 3-D head).  Built by reception.build for every model, only CALLED for dim = 3."""
     return _Head('sam1d', name)
-
-
-def _fuse_heads(g, outputs):
-    """Replay the recorded graph into a new one, replacing the head-model calls by the fused ops of the layer graph:
-       agg([sam2d(h[..., :nj]), sam2d(h[..., nj:]), jprob(h[..., nj:])]) + jprob(h[..., :nj])  ->  pose_regression_2d_context(h)
-       sam2d(h) + jprob(h)                                                                  ->  pose_regression_2d(h)
-    Returns (new graph, new outputs); a head call left over after the rewrite is an error."""
-    if not any(nd.op.startswith('head_') for nd in g.nodes):
-        return g, outputs
-
-    def sliced(t):
-        nd = t.node
-        if nd is not None and nd.op == 'slice':
-            return nd.inputs[0], nd.attrs['c0'], nd.attrs['c1']
-        return t, 0, t.channels
-
-    plans = {}          # node id -> ('ctx' | 'plain', ...) for the node at whose position the fused op is emitted
-    alias = {}          # head node id -> (anchor node id, output index of the fused op)
-    jprobs = [nd for nd in g.nodes if nd.op == 'head_jprob']
-    used = set()
-    for nd in g.nodes:
-        if nd.op != 'head_agg':
-            continue
-        ys, yc, pc = nd.inputs
-        if not (ys.node.op == 'head_sam2d' and yc.node.op == 'head_sam2d' and pc.node.op == 'head_jprob'):
-            raise NotImplementedError('context aggregation of tensors that are not soft-argmax / probability heads')
-        h, a0, a1 = sliced(ys.node.inputs[0])
-        h2, b0, b1 = sliced(yc.node.inputs[0])
-        h3, c0, c1 = sliced(pc.node.inputs[0])
-        nj, nc = nd.attrs['num_joints'], nd.attrs['num_context']
-        if not (h is h2 is h3 and (a0, a1) == (0, nj) and (b0, b1) == (c0, c1) == (nj, h.channels)
-                and h.channels == nj * (nc + 1)):
-            raise NotImplementedError('context aggregation over an unexpected split of the heat-maps')
-        vis = [j for j in jprobs if j.id not in used and sliced(j.inputs[0])[0] is h and sliced(j.inputs[0])[1:] == (0, nj)]
-        if len(vis) != 1:
-            raise NotImplementedError('context head without its joint-probability on the specialised maps')
-        for n_ in (ys.node, yc.node, pc.node, vis[0]):
-            used.add(n_.id)
-        plans[nd.id] = ('ctx', h, nd.attrs)
-        alias[vis[0].id] = (nd.id, 1)
-    for nd in g.nodes:
-        if nd.op == 'head_sam2d' and nd.id not in used:
-            t = nd.inputs[0]
-            vis = [j for j in jprobs if j.id not in used and j.inputs[0] is t]
-            if len(vis) != 1:
-                raise NotImplementedError('soft-argmax head without its joint-probability model')
-            used.update((nd.id, vis[0].id))
-            plans[nd.id] = ('plain', t, nd.attrs)
-            alias[vis[0].id] = (nd.id, 1)
-    left = [nd for nd in g.nodes if nd.op.startswith('head_') and nd.id not in used and nd.id not in plans]
-    if left:
-        raise NotImplementedError('head model call(s) outside a recordable pattern: %s' % left)
-
-    new = Graph(g.name)
-    new.frames_per_clip = g.frames_per_clip
-    new.weight_specs = list(g.weight_specs)
-    new._weight_names = set(g._weight_names)
-    new._counters = g._counters
-    tmap, fused = {}, {}
-    for nd in g.nodes:
-        if nd.op == 'input':
-            tmap[nd.outs[0].id] = new.input(nd.outs[0].shape, nd.outs[0].kind)
-            continue
-        if nd.id in plans:
-            kind, h, attrs = plans[nd.id]
-            if kind == 'ctx':
-                outs = new.op('pose_regression_2d_context', [tmap[h.id]],
-                              [(1, attrs['num_joints'], 2), (1, attrs['num_joints'], 1)],
-                              {'num_joints': attrs['num_joints'], 'num_context': attrs['num_context'],
-                               'alpha': attrs['alpha']})
-            else:
-                c = h.channels
-                outs = new.op('pose_regression_2d', [tmap[h.id]], [(1, c, 2), (1, c, 1)], {})
-            fused[nd.id] = outs
-            tmap[nd.outs[0].id] = outs[0]
-            continue
-        if nd.id in alias:
-            anchor, idx = alias[nd.id]
-            if anchor not in fused:
-                raise NotImplementedError('joint-probability head recorded before the soft-argmax head it belongs to')
-            tmap[nd.outs[0].id] = fused[anchor][idx]
-            continue
-        if nd.op.startswith('head_'):
-            continue                                    # absorbed operands (ps, pc, vc)
-        attrs = {k: (dict(v) if isinstance(v, dict) else v) for k, v in nd.attrs.items()}
-        outs = new.op(nd.op, [tmap[t.id] for t in nd.inputs], [o.shape for o in nd.outs], attrs, kind=nd.outs[0].kind)
-        outs = outs if isinstance(outs, tuple) else (outs,)
-        for o_src, o_new in zip(nd.outs, outs):
-            tmap[o_src.id] = o_new
-    return new, [tmap[t.id] for t in outputs]
 
 
 def _weight_names(attrs, known):
@@ -451,7 +440,7 @@ class Model(object):
         if self._impl is None:
             if self._applied:
                 raise NotImplementedError('Model %r was applied as a layer of another model; compile that one' % self._name)
-            g, outs = _fuse_heads(self._graph, self._outputs)
+            g, outs = backend.rewrite(self._graph, self._outputs)
             g.outputs = outs
             g.name = self._name
             self._impl = _Model(g, name=self._name)

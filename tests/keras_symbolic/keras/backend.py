@@ -1,20 +1,7 @@
-"""keras.backend: the few functions the reference's graph-building code calls on symbolic tensors."""
-
-
-def image_data_format():
-    return 'channels_last'
-
-
-def set_image_data_format(fmt):
-    assert fmt == 'channels_last'
-
-
-def int_shape(x):
-    return (None,) + tuple(x.shape)
-
-
-def ndim(x):
-    return len(x.shape) + 1          # + the batch axis (clip inputs are already folded into frames)
+"""keras.backend: the functions the reference's graph-building code and Lambda bodies call on symbolic tensors
+(deephar_b200.keras_trace records them); anything else fails when it is called."""
+from deephar_b200.keras_trace import (clip, epsilon, exp, expand_dims, image_data_format, int_shape, max, mean,  # noqa: F401,A004
+                                      ndim, reshape, set_image_data_format, squeeze, stop_gradient, sum, tile)
 
 
 def __getattr__(name):
@@ -22,5 +9,5 @@ def __getattr__(name):
         raise AttributeError(name)
 
     def stub(*args, **kwargs):
-        raise NotImplementedError('keras.backend.%s: tensor arithmetic is not part of the recording API' % name)
+        raise NotImplementedError('keras.backend.%s is not part of the recording API (deephar_b200.keras_trace)' % name)
     return stub

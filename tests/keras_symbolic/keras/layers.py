@@ -1,8 +1,9 @@
 """keras.layers -> deephar_b200.keras_compat; every other layer class the reference merely imports is a stub that
 fails when it is constructed."""
-from deephar_b200.keras_compat import (Activation, Add, BatchNormalization, Concatenate, Conv2D, Input,  # noqa: F401
-                                       Lambda, MaxPooling2D, Multiply, SeparableConv2D, TimeDistributed, UpSampling2D,
-                                       ZeroPadding2D, add, concatenate, multiply)
+from deephar_b200.keras_compat import (Activation, Add, AveragePooling2D, BatchNormalization, Concatenate,  # noqa: F401
+                                       Conv2D, GlobalMaxPooling1D, GlobalMaxPooling2D, Input, Lambda, MaxPooling2D,
+                                       Multiply, SeparableConv2D, TimeDistributed, UpSampling2D, ZeroPadding2D, add,
+                                       concatenate, multiply)
 
 
 def __getattr__(name):

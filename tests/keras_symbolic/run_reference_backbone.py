@@ -45,7 +45,9 @@ def spnet_case():
 def _dump(m):
     print(json.dumps({'weight_specs': [[n, list(s)] for n, s in m.weight_specs],
                       'plan': [[k.kind, [list(t.shape) for t in k.outs]] for k in m.plan.kops],
-                      'output_shape': [list(s) for s in m.output_shape]}))
+                      'output_shape': [list(s) for s in m.output_shape],
+                      'optional_weights': list(m.optional_weights),
+                      'signatures': m.graph.signatures()}))
 
 
 def full_model_case(concat):
@@ -55,9 +57,36 @@ def full_model_case(concat):
                   concat_pose_confidence=bool(concat), export_heatmaps=bool(concat)))
 
 
+def full_3d_case():
+    """reception.build(dim=3) with its Lambda / keras.backend 3-D head (reception.py:193-222): BASELINE configs[2]."""
+    keras_compat.clear_session()
+    _dump(R.build((256, 256, 3), 17, dim=3, num_blocks=8, ksize=(5, 5), concat_pose_confidence=False))
+
+
+def full_spnet_case(which):
+    """The reference's COMPLETE spnet.build(cfg) (spnet.py:355-410) on its own layers.py / activations.py / common.py /
+    config.py: prediction blocks with the frozen-SeparableConv2D soft-argmax, Lambda confidence, kronecker product,
+    depth expectation and the whole action head.  BASELINE configs[3] (PennAction) and configs[4] (NTU, 3-D)."""
+    from deephar.config import ModelConfig
+    from deephar.models import spnet as S
+    from deephar.utils.pose import pa16j2d, pa17j3d
+    keras_compat.clear_session()
+    if which == 'penn':
+        cfg = ModelConfig((16, 256, 256, 3), pa16j2d, num_actions=[15], num_pyramids=6, action_pyramids=[5, 6],
+                          num_levels=4, pose_replica=True, num_pose_features=160, num_visual_features=160)
+    else:
+        cfg = ModelConfig((16, 256, 256, 3), pa17j3d, num_actions=[60], num_pyramids=2, action_pyramids=[1, 2],
+                          num_levels=4, pose_replica=False, num_pose_features=192, num_visual_features=192)
+    _dump(S.build(cfg))
+
+
 def main():
     if sys.argv[1] == 'spnet':
         return spnet_case()
+    if sys.argv[1] == 'full3d':
+        return full_3d_case()
+    if sys.argv[1] == 'spnet_full':
+        return full_spnet_case(sys.argv[2])
     if sys.argv[1] == 'full2d':
         return full_model_case(int(sys.argv[2]))
     blocks, ksize, heatmaps = int(sys.argv[1]), (5, 5), 48

@@ -225,6 +225,66 @@ def test_reference_full_reception_build_records_the_headline_model(concat):
     assert len(got['output_shape']) == 16        # 8 x (pose, visible), or 8 x (pose|visible, heat-maps)
 
 
+def _run_reference(*args):
+    here = os.path.dirname(os.path.abspath(__file__))
+    out = subprocess.run([sys.executable, os.path.join(here, 'keras_symbolic', 'run_reference_backbone.py')] + list(args),
+                         capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-2000:]
+    return json.loads([l for l in out.stdout.splitlines() if l.startswith('{')][-1])
+
+
+def _same_model(got, want, same_launch_order=True):
+    plan = [[k.kind, [list(t.shape) for t in k.outs]] for k in want.plan.kops]
+    assert [(n, tuple(s)) for n, s in got['weight_specs']] == want.weight_specs
+    assert got['optional_weights'] == list(want.optional_weights)
+    assert [tuple(s) for s in got['output_shape']] == [tuple(s) for s in want.output_shape]
+    # every output is the same expression of the same weights (op, attributes, names, operands -- recursively) ...
+    assert got['signatures'] == want.graph.signatures()
+    # ... compiled into the same kernel launches
+    assert sorted(map(str, got['plan'])) == sorted(map(str, plan))
+    if same_launch_order:
+        assert got['plan'] == plan
+
+
+@pytest.mark.skipif(not os.path.isdir(os.environ.get('DEEPHAR_REFERENCE', '/root/reference')),
+                    reason='needs the reference tree (development container only)')
+def test_reference_reception_3d_build_records_the_c3_model():
+    """reception.build(dim=3) of the reference, unmodified: the 3-D head is Lambda / keras.backend arithmetic there
+    (reshape to (H, W, D, joints), two means, global max poolings, sigmoid -- reception.py:193-222); recorded as backend
+    ops and rewritten into the fused pose_regression_3d op, the model is deephar_b200.reception.build's (BASELINE
+    configs[2]), launch for launch."""
+    from deephar_b200 import reception
+    got = _run_reference('full3d')
+    want = reception.build((256, 256, 3), 17, dim=3, num_blocks=8, ksize=(5, 5), concat_pose_confidence=False)
+    _same_model(got, want)
+    assert len(got['plan']) == 134 and len(got['output_shape']) == 16
+
+
+@pytest.mark.skipif(not os.path.isdir(os.environ.get('DEEPHAR_REFERENCE', '/root/reference')),
+                    reason='needs the reference tree (development container only)')
+@pytest.mark.parametrize('which', ['penn', 'ntu'])
+def test_reference_full_spnet_build_records_the_c4_c5_models(which):
+    """The reference's COMPLETE `spnet.build(cfg)` -- spnet.py, common.py, layers.py, activations.py, config.py, all
+    unmodified -- on the recording keras: the channel soft-max body, the frozen SeparableConv2D soft-argmax (its grid
+    values are checked), the Lambda joint confidence, kronecker product, confidence mask, depth expectation and
+    max+min poolings are traced as backend ops and rewritten into deephar_b200's fused ops.  The result is the SAME
+    function of the SAME weights as deephar_b200.spnet.build(cfg) (BASELINE configs[3] / configs[4]) and compiles to the
+    same 345 / 237 launches; only the position of the per-block pose-output copies in the launch sequence differs
+    (the reference concatenates (pose, confidence) after the re-injection add, spnet.py:239-240)."""
+    from deephar_b200 import spnet
+    from deephar_b200.config import ModelConfig, pa16j2d, pa17j3d
+    if which == 'penn':
+        cfg = ModelConfig((16, 256, 256, 3), pa16j2d, num_actions=[15], num_pyramids=6, action_pyramids=[5, 6],
+                          num_levels=4, pose_replica=True, num_pose_features=160, num_visual_features=160)
+    else:
+        cfg = ModelConfig((16, 256, 256, 3), pa17j3d, num_actions=[60], num_pyramids=2, action_pyramids=[1, 2],
+                          num_levels=4, pose_replica=False, num_pose_features=192, num_visual_features=192)
+    got = _run_reference('spnet_full', which)
+    _same_model(got, spnet.build(cfg), same_launch_order=False)
+    assert len(got['plan']) == {'penn': 345, 'ntu': 237}[which]
+    assert len(got['output_shape']) == {'penn': 24, 'ntu': 12}[which]
+
+
 def test_head_models_and_lambda_slices():
     K.clear_session()
     inp = K.Input(shape=(32, 32, 8))
@@ -238,11 +298,15 @@ def test_head_models_and_lambda_slices():
     m = K.Model(inputs=inp, outputs=[pose, vis, hs])
     assert [k.kind for k in m.plan.kops] == ['conv', 'pose_regression_2d_context']
     assert m.output_shape == [(None, 16, 2), (None, 16, 1), (None, 32, 32, 16)]
-    # a Lambda that is not a channel slice, and a head call outside the recordable patterns, fail at build time
-    with pytest.raises(NotImplementedError):
-        K.Lambda(lambda x: 4 * x)(h)
+    # indexing other than a channel slice fails in the Lambda; backend arithmetic that is not one of the reference's
+    # constructions, and a head call outside the recordable patterns, fail when the model is built -- naming the ops
     with pytest.raises(NotImplementedError):
         K.Lambda(lambda x: x[:, 1:, :, :])(h)
+    with pytest.raises(NotImplementedError):
+        K.Lambda(lambda x: x + 1)(h)
+    odd = K.Model(inputs=inp, outputs=[K.Lambda(lambda x: 4 * x)(h)])
+    with pytest.raises(NotImplementedError, match='k_scale'):
+        odd.plan
     lone = K.Model(inputs=inp, outputs=[K.build_softargmax_2d((32, 32, 48))(h)])
     with pytest.raises(NotImplementedError):
         lone.plan
