@@ -310,3 +310,139 @@ def test_head_models_and_lambda_slices():
     lone = K.Model(inputs=inp, outputs=[K.build_softargmax_2d((32, 32, 48))(h)])
     with pytest.raises(NotImplementedError):
         lone.plan
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# backend-op tracing (keras_trace.py), without the reference tree: a small multitask clip model written the way one
+# writes it for Keras -- soft-max / soft-argmax / confidence / feature pooling as backend arithmetic -- against the
+# same model written with the fused helpers of deephar_b200.layers
+# ---------------------------------------------------------------------------------------------------------------------
+def _grid_expectation(prob, along, name, values=None):
+    """E[coordinate] of every map as a frozen depthwise convolution over the whole map with a coordinate-grid kernel."""
+    KB = K.backend
+    _, _, rows, cols, ch = KB.int_shape(prob)
+    conv = K.SeparableConv2D(ch, (rows, cols), use_bias=False, name=name)
+    out = K.TimeDistributed(conv, name=name)(prob)
+    w = conv.get_weights()
+    w[0][:] = 0
+    w[1][:] = 0
+    ramp = np.linspace(0., 1., cols if along == 'x' else rows) if values is None else values
+    for c in range(ch):
+        w[0][:, :, c, 0] = ramp[None, :] if along == 'x' else ramp[:, None]
+        w[1][0, 0, c, c] = 1
+    conv.set_weights(w)
+    conv.trainable = False
+    out = K.Lambda(lambda t: KB.squeeze(t, axis=-2))(out)
+    out = K.Lambda(lambda t: KB.squeeze(t, axis=-2))(out)
+    return K.Lambda(lambda t: KB.expand_dims(t, axis=-1))(out)
+
+
+def _keras_style_multitask(inp, n_maps=6, n_act=5, sharpness=2.0, bad_grid=False):
+    KB = K.backend
+
+    def spatial_softmax(t):
+        t = sharpness * t
+        e = KB.exp(t - KB.max(t, axis=(-3, -2), keepdims=True))
+        return e / KB.clip(KB.sum(e, axis=(-3, -2), keepdims=True), KB.epsilon(), None)
+
+    def confidence(t):
+        return KB.expand_dims(K.GlobalMaxPooling2D()(4 * K.AveragePooling2D((2, 2), strides=(1, 1))(t)), axis=-1)
+
+    def pooled_features(ts):
+        hm, f = ts
+        hm = KB.tile(KB.expand_dims(hm, axis=-1), [1, 1, 1, 1, 1, KB.int_shape(f)[-1]])
+        f = KB.tile(KB.expand_dims(f, axis=-2), [1, 1, 1, 1, KB.int_shape(hm)[-2], 1])
+        return KB.sum(hm * f, axis=(2, 3))
+
+    def max_plus_min(t):
+        return K.MaxPooling2D((2, 2), padding='same')(t) - K.MaxPooling2D((2, 2), padding='same')(-t)
+
+    def global_max_plus_min(t):
+        return K.GlobalMaxPooling2D()(t) - K.GlobalMaxPooling2D()(-t)
+
+    feat = K.TimeDistributed(K.Conv2D(16, (3, 3), strides=(2, 2), padding='same', use_bias=False), name='feat')(inp)
+    feat = K.TimeDistributed(K.Activation('relu'))(feat)
+    maps = K.TimeDistributed(K.Conv2D(n_maps, (1, 1), use_bias=False), name='maps')(feat)
+    depth = K.TimeDistributed(K.Conv2D(n_maps, (1, 1), use_bias=False), name='depth')(feat)
+    prob = K.TimeDistributed(K.Activation(spatial_softmax), name='prob')(maps)
+    xy = K.concatenate([_grid_expectation(prob, 'x', 'xy_x', np.linspace(0., 2., 16) if bad_grid else None),
+                        _grid_expectation(prob, 'y', 'xy_y')], name='xy')
+    vis = K.TimeDistributed(K.Lambda(confidence), name='vis')(prob)
+    z = K.multiply([K.Activation('sigmoid')(depth), prob])
+    z = K.Lambda(lambda t: KB.expand_dims(KB.sum(t, axis=(-2, -3)), axis=-1))(z)
+    xyz = K.concatenate([xy, z], name='xyz')
+    pose = K.concatenate([xyz, vis], name='pose')
+
+    masked = K.Lambda(lambda ts: ts[0] * ts[1])([xyz, K.Lambda(lambda t: KB.tile(t, (1, 1, 1, 3)))(vis)])
+    a = K.Conv2D(8, (3, 3), padding='same', use_bias=False, name='pose_conv')(masked)
+    b = K.Conv2D(8, (1, 1), padding='same', use_bias=False, name='vis_conv')(K.Lambda(pooled_features, name='kron')([prob, feat]))
+    x = K.concatenate([a, b])
+    x = K.Lambda(max_plus_min)(K.Conv2D(12, (3, 3), padding='same', use_bias=False, name='mix')(x))
+    x = K.Activation('relu')(K.BatchNormalization(name='bn')(x))
+    logits = K.Conv2D(n_act, (3, 3), padding='same', use_bias=False, name='cls')(x)
+    act = K.Activation('softmax', name='action')(K.Lambda(global_max_plus_min)(logits))
+    return [pose, act]
+
+
+def _function_style_multitask(inp, n_maps=6, n_act=5, sharpness=2.0):
+    feat = L.relu(L.conv2d(inp, 16, (3, 3), strides=(2, 2), name='feat'))
+    maps = L.conv2d(feat, n_maps, (1, 1), padding='valid', name='maps')
+    depth = L.conv2d(feat, n_maps, (1, 1), padding='valid', name='depth')
+    prob = L.channel_softmax_2d(maps, alpha=sharpness, name='prob')
+    xy = L.softargmax2d(prob, name='xy')
+    vis = L.keypoint_confidence(prob, name='vis')
+    xyz = L.concatenate([xy, L.depth_expectation(depth, prob)], name='xyz')
+    pose = L.concatenate([xyz, vis], name='pose')
+    masked = L.mask_multiply(L.frames_to_clip(xyz), L.frames_to_clip(vis))
+    a = L.conv2d(masked, 8, (3, 3), name='pose_conv')
+    b = L.conv2d(L.frames_to_clip(L.kronecker_prod(prob, feat, name='kron')), 8, (1, 1), name='vis_conv')
+    x = L.max_min_pooling(L.conv2d(L.concatenate([a, b]), 12, (3, 3), name='mix'), (2, 2))
+    x = L.relu(L.BatchNormalization(x, name='bn'))
+    logits = L.conv2d(x, n_act, (3, 3), name='cls')
+    return [pose, L.softmax_lastaxis(L.global_max_min_pooling(logits), name='action')]
+
+
+def test_backend_arithmetic_is_rewritten_into_the_fused_ops():
+    K.clear_session()
+    inp = K.Input(shape=(4, 32, 32, 3))
+    mk = K.Model(inputs=inp, outputs=_keras_style_multitask(inp), name='toy_multitask')
+    g = Graph('toy_multitask')
+    g.frames_per_clip = 4
+    g.outputs = _function_style_multitask(g.input((32, 32, 3)))
+    mf = Model(g)
+    assert mk.weight_specs == mf.weight_specs                      # the frozen grid kernels are not weights
+    assert [n for n, _ in mk.weight_specs if n.startswith('xy')] == []
+    assert mk.graph.signatures() == mf.graph.signatures()
+    assert [(k.kind, [t.shape for t in k.outs]) for k in mk.plan.kops] == \
+           [(k.kind, [t.shape for t in k.outs]) for k in mf.plan.kops]
+    assert 'sam2d' in [k.kind for k in mk.plan.kops] and mk.output_shape == [(None, 4, 6, 4), (None, 5)]
+
+
+def test_backend_arithmetic_that_is_not_a_known_construction_is_rejected():
+    KB = K.backend
+    # a frozen grid that is not the reference's [0, 1] ramp
+    K.clear_session()
+    inp = K.Input(shape=(4, 32, 32, 3))
+    m = K.Model(inputs=inp, outputs=_keras_style_multitask(inp, bad_grid=True))
+    with pytest.raises(NotImplementedError, match='soft-argmax grid'):
+        m.plan
+    # heat-map x feature pooling without the time axis: the reference's axis=(2, 3) would sum columns and joints
+    K.clear_session()
+    inp = K.Input(shape=(32, 32, 3))
+    f = K.Conv2D(8, (3, 3), padding='same', use_bias=False)(inp)
+    h = K.Conv2D(4, (1, 1), use_bias=False)(f)
+
+    def pooled(ts):
+        hm = KB.tile(KB.expand_dims(ts[0], axis=-1), [1, 1, 1, 1, 8])
+        ft = KB.tile(KB.expand_dims(ts[1], axis=-2), [1, 1, 1, 4, 1])
+        return KB.sum(hm * ft, axis=(2, 3))
+    m = K.Model(inputs=inp, outputs=[K.Lambda(pooled)([h, f])])
+    with pytest.raises(NotImplementedError, match='clip tensors'):
+        m.plan
+    # shape rules of the backend functions themselves
+    assert KB.int_shape(h) == (None, 32, 32, 4) and KB.ndim(h) == 4
+    assert KB.int_shape(KB.mean(KB.reshape(KB.expand_dims(h), (-1, 32, 32, 2, 2)), axis=3)) == (None, 32, 32, 2)
+    with pytest.raises(NotImplementedError):
+        KB.sum(h, axis=0)                                          # the batch axis
+    with pytest.raises(ValueError):
+        KB.squeeze(h, axis=-1)
