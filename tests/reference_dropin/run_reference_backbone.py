@@ -1,5 +1,6 @@
-"""Executes the reference's own backbone builders on the recording `keras` of this directory and prints the recorded
-model's weight list and kernel plan as JSON (driven by tests/test_keras_compat.py in a subprocess)."""
+"""Executes the reference's own model builders after deephar_b200.dropin.install() and prints the recorded model's
+weight list, kernel plan, output shapes and expression digests as JSON (driven by tests/test_keras_compat.py in a
+subprocess, only where the reference tree exists)."""
 import json
 import os
 import sys
@@ -7,11 +8,11 @@ import warnings
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-sys.path[:0] = [HERE, os.path.join(HERE, '..', 'golden', 'keras_shim'), os.environ.get('DEEPHAR_REFERENCE', '/root/reference'), ROOT]
+sys.path[:0] = [os.environ.get('DEEPHAR_REFERENCE', '/root/reference'), ROOT]
 warnings.filterwarnings('ignore')
+import deephar_b200.dropin  # noqa: E402
+deephar_b200.dropin.install()                                 # `keras` / `tensorflow` -> the recording front end
 _stderr, sys.stderr = sys.stderr, open(os.devnull, 'w')       # the reference prints a banner on import
-import recording_blocks  # noqa: E402
-sys.modules['deephar.models.blocks'] = recording_blocks     # the four parameter-free head builders, recordable
 import deephar  # noqa: E402,F401
 from deephar.models import reception as R  # noqa: E402
 sys.stderr = _stderr

@@ -165,9 +165,9 @@ def test_nested_models_and_session_counters():
 def test_reference_backbone_builders_record_the_same_model():
     """The REFERENCE'S OWN code -- deephar/layers.py and models/reception.py::_stem / build_reception_block /
     build_sconv_block / build_regmap_block / build_fremap_block, unmodified -- imported on a `keras` that is
-    keras_compat (tests/keras_symbolic) records the weight list, auto-names and kernel plan of deephar_b200's builders."""
+    keras_compat (tests/reference_dropin) records the weight list, auto-names and kernel plan of deephar_b200's builders."""
     here = os.path.dirname(os.path.abspath(__file__))
-    out = subprocess.run([sys.executable, os.path.join(here, 'keras_symbolic', 'run_reference_backbone.py'), '3'],
+    out = subprocess.run([sys.executable, os.path.join(here, 'reference_dropin', 'run_reference_backbone.py'), '3'],
                          capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     got = json.loads([l for l in out.stdout.splitlines() if l.startswith('{')][-1])
@@ -186,7 +186,7 @@ def test_reference_spnet_skeleton_records_the_same_model():
     from deephar_b200 import common, spnet
     from deephar_b200.config import ModelConfig, pa16j2d
     here = os.path.dirname(os.path.abspath(__file__))
-    out = subprocess.run([sys.executable, os.path.join(here, 'keras_symbolic', 'run_reference_backbone.py'), 'spnet'],
+    out = subprocess.run([sys.executable, os.path.join(here, 'reference_dropin', 'run_reference_backbone.py'), 'spnet'],
                          capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     got = json.loads([l for l in out.stdout.splitlines() if l.startswith('{')][-1])
@@ -213,7 +213,7 @@ def test_reference_full_reception_build_records_the_headline_model(concat):
     weight list, auto-names, kernel plan, output order and shapes)."""
     from deephar_b200 import reception
     here = os.path.dirname(os.path.abspath(__file__))
-    out = subprocess.run([sys.executable, os.path.join(here, 'keras_symbolic', 'run_reference_backbone.py'), 'full2d',
+    out = subprocess.run([sys.executable, os.path.join(here, 'reference_dropin', 'run_reference_backbone.py'), 'full2d',
                           str(concat)], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     got = json.loads([l for l in out.stdout.splitlines() if l.startswith('{')][-1])
@@ -227,7 +227,7 @@ def test_reference_full_reception_build_records_the_headline_model(concat):
 
 def _run_reference(*args):
     here = os.path.dirname(os.path.abspath(__file__))
-    out = subprocess.run([sys.executable, os.path.join(here, 'keras_symbolic', 'run_reference_backbone.py')] + list(args),
+    out = subprocess.run([sys.executable, os.path.join(here, 'reference_dropin', 'run_reference_backbone.py')] + list(args),
                          capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stderr[-2000:]
     return json.loads([l for l in out.stdout.splitlines() if l.startswith('{')][-1])
@@ -446,3 +446,45 @@ def test_backend_arithmetic_that_is_not_a_known_construction_is_rejected():
         KB.sum(h, axis=0)                                          # the batch axis
     with pytest.raises(ValueError):
         KB.squeeze(h, axis=-1)
+
+
+def test_dropin_registers_a_recording_keras():
+    """deephar_b200.dropin.install(): `import keras` / `import tensorflow` resolve to the recording front end; what the
+    forward path never calls exists but fails, by name, when it is called."""
+    code = r'''
+import sys
+import deephar_b200.dropin as d
+k = d.install()
+assert d.install() is k
+import keras, tensorflow as tf
+import keras.backend as K
+from keras.layers import Input, Conv2D, Dense, LSTM, Lambda, TimeDistributed
+from keras.models import Model
+from keras.optimizers import SGD, RMSprop
+from keras.callbacks import Callback, LearningRateScheduler
+from keras.utils import Sequence
+from keras.utils.data_utils import get_file
+from keras.regularizers import l1
+from deephar_b200 import keras_compat
+assert keras.__version__ == '2.1.4' and Model is keras_compat.Model and K.epsilon() == 1e-7
+SGD(lr=0.1); LearningRateScheduler(lambda e: 0.1)
+class Loader(Sequence):
+    pass
+for bad in (lambda: Dense(10), lambda: LSTM(4), lambda: tf.divide(1, 2), lambda: K.sqrt(1), lambda: get_file('x', 'http://x')):
+    try:
+        bad()
+    except NotImplementedError as e:
+        continue
+    raise AssertionError('stub did not fail')
+inp = Input(shape=(16, 16, 3))
+m = Model(inputs=inp, outputs=Conv2D(4, (3, 3), padding='same', use_bias=False, name='c')(inp), name='tiny')
+assert m.weight_specs == [('c/kernel', (3, 3, 3, 4))] and [k_.kind for k_ in m.plan.kops] == ['conv']
+B = sys.modules['deephar.models.blocks']   # what `from .blocks import *` in the reference's model files will find
+assert B.build_softargmax_2d is keras_compat.build_softargmax_2d
+d.uninstall()
+assert 'keras' not in sys.modules and 'deephar.models.blocks' not in sys.modules
+print('ok')
+'''
+    out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=300,
+                         cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert out.returncode == 0 and out.stdout.strip().endswith('ok'), out.stderr[-2000:]
