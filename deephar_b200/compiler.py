@@ -527,3 +527,56 @@ def compile_graph(g_full):
         'floats_per_item_clip': sum(f for (kd, f) in plan.phys if kd == 'clip'),
     }
     return plan
+
+
+def verify_plan(plan, g):
+    """Independent replay of a plan's buffer assignment (the planner above is liveness + greedy slot reuse; this is
+    the check that it is memory-safe, used by the tests on every BASELINE model): walking the launches in order,
+      * every channel range a launch reads was written before, by launches of the SAME logical buffer, and no other
+        buffer has taken over the physical slot in between;
+      * no launch writes a slot it is reading through another buffer, or a channel range of its own input;
+      * every model output is intact after the last launch.
+    Returns the number of (launch, operand) pairs checked; raises AssertionError naming the launch otherwise."""
+    owner, written, checked = {}, {}, 0
+
+    def covered(spans, lo, hi):
+        pos = lo
+        for a, b in sorted(spans):
+            if a > pos:
+                break
+            pos = max(pos, b)
+        return pos >= hi
+
+    def span(t):
+        s = plan.storage[t.id]
+        return s.buf, s.c_off, s.c_off + t.channels
+
+    for t in g.inputs:
+        b, lo, hi = span(t)
+        owner[b.phys] = b.id
+        written[b.id] = [(lo, hi)]
+    for i, k in enumerate(plan.kops):
+        reads = [span(t) for t in k.ins]
+        for t, (b, lo, hi) in zip(k.ins, reads):
+            assert owner.get(b.phys) == b.id, \
+                'launch %d (%s) reads %r but its slot %d holds buffer %r' % (i, k.kind, t, b.phys, owner.get(b.phys))
+            assert covered(written[b.id], lo, hi), \
+                'launch %d (%s) reads channels [%d, %d) of %r that no earlier launch wrote' % (i, k.kind, lo, hi, t)
+            checked += 1
+        for t in k.outs:
+            b, lo, hi = span(t)
+            for u, (bu, ulo, uhi) in zip(k.ins, reads):
+                if bu.phys != b.phys:
+                    continue
+                assert bu is b, 'launch %d (%s) writes %r into the slot of its own operand %r' % (i, k.kind, t, u)
+                assert hi <= ulo or uhi <= lo, \
+                    'launch %d (%s) overwrites channels of its own operand %r' % (i, k.kind, u)
+            if owner.get(b.phys) != b.id:
+                owner[b.phys] = b.id
+                written[b.id] = []
+            written[b.id].append((lo, hi))
+            checked += 1
+    for t in g.outputs:
+        b, lo, hi = span(t)
+        assert owner.get(b.phys) == b.id and covered(written[b.id], lo, hi), 'model output %r is not intact' % (t,)
+    return checked

@@ -20,6 +20,7 @@ sys.stderr = _stderr
 from keras.layers import Input, add  # noqa: E402   (= deephar_b200.keras_compat)
 from keras.models import Model  # noqa: E402
 from deephar_b200 import keras_compat  # noqa: E402
+from deephar_b200.compiler import verify_plan  # noqa: E402
 
 
 def spnet_case():
@@ -48,7 +49,8 @@ def _dump(m):
                       'plan': [[k.kind, [list(t.shape) for t in k.outs]] for k in m.plan.kops],
                       'output_shape': [list(s) for s in m.output_shape],
                       'optional_weights': list(m.optional_weights),
-                      'signatures': m.graph.signatures()}))
+                      'signatures': m.graph.signatures(),
+                      'plan_checked': verify_plan(m.plan, m.graph)}))       # memory-safe in ITS launch order
 
 
 def full_model_case(concat):

@@ -2,6 +2,7 @@
 (names, Keras layouts, creation order) that the oracle's independent restatement consumes;
 synthetic weight generators agree; fusion plan sanity; FLOP counts of SURVEY.md 8(d)."""
 import numpy as np
+import pytest
 
 from deephar_b200 import reception
 from deephar_b200.weights import load_calibration, split_bf16, synthetic_weight
@@ -109,3 +110,68 @@ def test_split_bf16_reconstructs():
     hi, lo = split_bf16(w)
     rec = (hi.astype(np.uint32) << 16).view(np.float32) + (lo.astype(np.uint32) << 16).view(np.float32)
     assert np.abs(rec - w).max() <= np.abs(w).max() * 2.0 ** -16
+
+
+def _baseline_models():
+    from deephar_b200 import action, reception, spnet
+    from deephar_b200.config import ModelConfig, pa16j2d, pa17j3d
+    yield 'c1', reception.build((256, 256, 3), 16, dim=2, num_blocks=8, num_context_per_joint=2, ksize=(5, 5),
+                                concat_pose_confidence=False)
+    yield 'c1_heatmaps', reception.build((256, 256, 3), 16, dim=2, num_blocks=8, num_context_per_joint=2, ksize=(5, 5),
+                                         export_heatmaps=True)
+    yield 'c3', reception.build((256, 256, 3), 17, dim=3, num_blocks=8, ksize=(5, 5), concat_pose_confidence=False)
+    yield 'c4', spnet.build(ModelConfig((16, 256, 256, 3), pa16j2d, num_actions=[15], num_pyramids=6,
+                                        action_pyramids=[5, 6], num_levels=4, pose_replica=True,
+                                        num_pose_features=160, num_visual_features=160))
+    yield 'c5', spnet.build(ModelConfig((16, 256, 256, 3), pa17j3d, num_actions=[60], num_pyramids=2,
+                                        action_pyramids=[1, 2], num_levels=4, pose_replica=False,
+                                        num_pose_features=192, num_visual_features=192))
+    pe = reception.build((256, 256, 3), 16, dim=2, num_blocks=4, num_context_per_joint=2, ksize=(5, 5))
+    yield 'merge2d', action.build_merge_model(pe, 15, (256, 256, 3), 16, 16, 4, pose_dim=2)
+    pe = reception.build((256, 256, 3), 20, dim=3, num_blocks=4, depth_maps=8, ksize=(5, 5))
+    yield 'merge3d', action.build_merge_model(pe, 60, (256, 256, 3), 16, 20, 4, pose_dim=3, depth_maps=8,
+                                              output_poses=True)
+
+
+def test_buffer_plans_of_every_baseline_model_are_memory_safe():
+    """compiler.verify_plan replays the launches over the physical slots: every read sees what its producer wrote, no
+    launch writes over an operand, outputs survive.  (The planner reuses a slot as soon as its buffer is dead; the
+    headline model runs in 35 slots instead of 140 buffers.)"""
+    from deephar_b200.compiler import verify_plan
+    seen = {}
+    for name, m in _baseline_models():
+        n = verify_plan(m.plan, m.graph)
+        assert n > 2 * len(m.plan.kops)
+        seen[name] = (len(m.plan.kops), m.plan.stats['phys_slots'], m.plan.stats['buffers'])
+    assert seen['c1'][0] == 127 and seen['c3'][0] == 134 and seen['c4'][0] == 345 and seen['c5'][0] == 237
+    assert all(slots < bufs for _, slots, bufs in seen.values())
+
+
+def test_verify_plan_catches_a_clobbered_buffer():
+    from deephar_b200 import reception
+    from deephar_b200.compiler import verify_plan
+    m = reception.build((64, 64, 3), 16, dim=2, num_blocks=2, num_context_per_joint=2, ksize=(5, 5))
+    plan = m.plan
+    verify_plan(plan, m.graph)
+    # put a long-lived buffer (a block's identity branch) on the slot of a buffer that is written while it is live
+    bufs = sorted((b for b in plan.buffers if not b.is_input and not b.is_output), key=lambda b: b.first - b.last)
+    victim = bufs[0]
+    other = next(b for b in plan.buffers if victim.first < b.first < victim.last and b.phys != victim.phys
+                 and not b.is_input and not b.is_output)
+    keep = other.phys
+    other.phys = victim.phys
+    try:
+        with pytest.raises(AssertionError, match='launch'):
+            verify_plan(plan, m.graph)
+    finally:
+        other.phys = keep
+    # a launch that no longer has its operand written
+    k = next(k for k in plan.kops if k.kind in ('conv', 'sepconv') and len(k.ins) > 1)
+    dropped = plan.kops.index(next(p for p in plan.kops if k.ins[1] in p.outs))
+    removed = plan.kops.pop(dropped)
+    try:
+        with pytest.raises(AssertionError):
+            verify_plan(plan, m.graph)
+    finally:
+        plan.kops.insert(dropped, removed)
+    verify_plan(plan, m.graph)

@@ -244,6 +244,8 @@ def _same_model(got, want, same_launch_order=True):
     assert sorted(map(str, got['plan'])) == sorted(map(str, plan))
     if same_launch_order:
         assert got['plan'] == plan
+    # ... whose buffer plan was replayed by compiler.verify_plan in the recorded launch order
+    assert got['plan_checked'] > 2 * len(plan)
 
 
 @pytest.mark.skipif(not os.path.isdir(os.environ.get('DEEPHAR_REFERENCE', '/root/reference')),
