@@ -12,7 +12,8 @@
 keras_compat's and whose backend is keras_trace's: the reference's builders (deephar/models/reception.py, spnet.py,
 common.py on its own layers.py / activations.py / config.py) then RECORD deephar_b200's layer graph instead of building a
 TensorFlow graph, and the `Model(...)` they return is the compiled B200 model with the `keras.Model` protocol the
-evaluators use.  The four parameter-free head-model builders of deephar/models/blocks.py:217-343 (soft-argmax 2-D / 1-D,
+evaluators use; `spnet.split_model` and `action.build_merge_model(model_pe, ...)` (get_layer / TimeDistributed re-wiring
+of the pose network, action.py:112-400) work on those models the same way.  The four parameter-free head-model builders of deephar/models/blocks.py:217-343 (soft-argmax 2-D / 1-D,
 joint probability, context aggregation -- frozen Dense / SeparableConv2D / tf.divide sub-models in the reference) are
 provided here as recordable objects under the module name `deephar.models.blocks`.
 

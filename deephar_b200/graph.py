@@ -89,6 +89,7 @@ class Graph(object):
         self._counters = {}
         self._scope = []
         self.frames_per_clip = 1    # T (TimeDistributed fold); 1 for single-frame models
+        self.layers = {}            # name -> sub-model / head model applied in this graph (keras `get_layer`)
 
     # --- naming (Keras auto names: one global counter per class prefix) --------
     def auto_name(self, prefix):
@@ -136,6 +137,30 @@ class Graph(object):
             node.outs.append(Tensor(self, s, kind, node, i))
         return node.outs[0] if len(node.outs) == 1 else tuple(node.outs)
 
+    def absorb(self, other):
+        """Move every node, tensor, input and weight of `other` into this graph (Keras Inputs are independent; a model
+        with several of them becomes one graph the first time an op combines their tensors).  `other` is left empty."""
+        if other is self:
+            return
+        for nd in other.nodes:
+            nd.id = len(self.nodes)
+            self.nodes.append(nd)
+        for t in other.tensors:
+            t.id = len(self.tensors)
+            t.g = self
+            self.tensors.append(t)
+        self.inputs.extend(other.inputs)
+        for name, shape in other.weight_specs:
+            if name in self._weight_names:
+                raise ValueError('duplicate weight name %s' % name)
+            self._weight_names.add(name)
+            self.weight_specs.append((name, shape))
+        for k, v in getattr(other, 'layers', {}).items():
+            self.layers.setdefault(k, v)
+        other.nodes, other.tensors, other.inputs, other.weight_specs = [], [], [], []
+        other._weight_names = set()
+        other.merged_into = self
+
     def signatures(self, tensors=None):
         """One digest per tensor (default: the outputs) of the expression that computes it: op, attributes (weight and
         layer names included), operand digests, shapes.  Two graphs whose outputs have equal digests are the same
@@ -153,7 +178,10 @@ class Graph(object):
         def sig(t):
             if t.id not in memo:
                 nd = t.node
-                body = repr((nd.op, canon(nd.attrs), [sig(i) for i in nd.inputs], t.out_index, t.shape, t.kind))
+                attrs = nd.attrs
+                if nd.op in ('conv', 'sepconv') and tuple(attrs['size']) == (1, 1) and tuple(attrs['strides']) == (1, 1):
+                    attrs = dict(attrs, padding='same')         # a 1x1 / stride-1 window needs no padding either way
+                body = repr((nd.op, canon(attrs), [sig(i) for i in nd.inputs], t.out_index, t.shape, t.kind))
                 memo[t.id] = hashlib.sha1(body.encode()).hexdigest()
             return memo[t.id]
 

@@ -148,7 +148,21 @@ class SeparableConv2D(Layer):
         return [np.zeros(shapes[self._node.attrs[k]], np.float32) for k in ('depthwise', 'pointwise')]
 
     def set_weights(self, weights):
-        backend.freeze_separable(self._node, weights)
+        self._assigned = weights
+        if not self._trainable:
+            backend.freeze_separable(self._node, weights)
+
+    @property
+    def trainable(self):
+        return self._trainable
+
+    @trainable.setter
+    def trainable(self, value):
+        self._trainable = bool(value)
+        if not value and self._assigned is not None and self._node.op == 'sepconv':
+            backend.freeze_separable(self._node, self._assigned)
+
+    _trainable, _assigned = True, None
 
 
 class BatchNormalization(Layer):
@@ -311,6 +325,7 @@ class _Merge(Layer):
 
     def call(self, ts):
         ts = list(ts)
+        backend.unify(ts)
         if any(backend.is_raw(t) for t in ts):
             if self.raw is None:
                 raise NotImplementedError('%s of a backend-op result' % type(self).__name__)
@@ -361,6 +376,9 @@ class _Head(object):
 
     def __call__(self, x):
         xs = list(x) if isinstance(x, (list, tuple)) else [x]
+        backend.unify(xs)
+        if self.name is not None:
+            xs[0].g.layers.setdefault(self.name, self)
         ks = backend.kshape(xs[0])
         if self.kind == 'sam2d':
             shape = ks[:-3] + (ks[-1], 2)
@@ -386,7 +404,6 @@ def build_joints_probability(input_shape, name=None, verbose=0):
 
 def build_context_aggregation(num_joints, num_context, alpha, num_frames=1, name=None):
     """blocks.py:217-285: pose = alpha * ys + (1 - alpha) * sum(pc * yc) / sum(pc) over each joint's context maps."""
-    _no(num_frames != 1, 'build_context_aggregation(num_frames > 1)')
     return _Head('agg', name, num_joints=int(num_joints), num_context=int(num_context), alpha=float(alpha))
 
 
@@ -409,37 +426,60 @@ def _weight_names(attrs, known):
 class Model(object):
     """keras.models.Model(inputs, outputs, name).
 
-    * used as a MODEL (`predict`, `load_weights`, `outputs`, `weight_specs`, ...): the recorded graph is compiled for
-      B200 on first use (layers that reach no output are dropped, as Keras drops them) and every attribute of
-      deephar_b200.model.Model is available on this object;
+    * used as a MODEL (`predict`, `load_weights`, `weight_specs`, `output_shape`, ...): the recorded graph is compiled
+      for B200 on first use (layers that reach no output are dropped, as Keras drops them) and every attribute of
+      deephar_b200.model.Model is available on this object.  `model.input` / `model.outputs` are the symbolic tensors, so
+      `Model(full.input, full.outputs[:n])` (deephar/models/spnet.py:443-446) makes a model of a subset of the outputs;
     * used as a LAYER -- `Stem = Model(inp, x, name='Stem'); y = Stem(frames)`, the way the reference wraps its blocks
       (deephar/models/reception.py:96-98, 128-131) -- its layers are re-recorded into the caller's graph under the
-      scope `name`, which is how Keras names the weights of a nested model in a checkpoint ("Stem/conv2d_1/kernel").
-      A nested model can be applied once (no weight sharing on the reference's forward path).
+      scope `name`, which is how Keras names the weights of a nested model in a checkpoint ("Stem/conv2d_1/kernel");
+      layers that already carry the scope of an inner sub-model keep it (one scope per weight: Keras layer names are
+      unique per session).  A nested model is applied once per graph (no weight sharing inside one model); applying it
+      again in ANOTHER model -- `TimeDistributed(model_pe.get_layer('Stem'))(clips)`, action.py:117-125 -- records the
+      same layers, with the same weight names, there.  Models with several Inputs can be nested (`model_pose([y, p])`,
+      action.py:354) but not compiled on their own.
     """
+
+    _OWN = ('_impl', '_applied_to', '_graph', '_inputs', '_outputs', '_single', '_name', 'trainable')
 
     def __init__(self, inputs=None, outputs=None, name=None):
         self._inputs = list(inputs) if isinstance(inputs, (list, tuple)) else [inputs]
         self._outputs = list(outputs) if isinstance(outputs, (list, tuple)) else [outputs]
         self._single = not isinstance(outputs, (list, tuple))
-        if len(self._inputs) != 1:
-            raise NotImplementedError('Model: exactly one Input (the frame / clip tensor) is supported')
-        g = self._inputs[0].g
-        for t in self._outputs:
-            if t.g is not g:
-                raise ValueError('Model: an output does not descend from the given Input')
-        if g.inputs != self._inputs:
-            raise ValueError('Model: `inputs` must be the Input the graph was started from')
+        g = backend.unify(self._inputs + self._outputs)
+        if any(t not in g.inputs for t in self._inputs):
+            raise ValueError('Model: `inputs` must be Input tensors')
+        if len(set(id(t) for t in self._inputs)) != len(g.inputs):
+            raise ValueError('Model: the outputs depend on an Input that is not listed in `inputs`')
         self._graph = g
         self._name = name or g.auto_name('model')
         self._impl = None
-        self._applied = False
+        self._applied_to = []
+        self.trainable = True
+
+    name = property(lambda self: self._name)
+    input = property(lambda self: self._inputs[0] if len(self._inputs) == 1 else list(self._inputs))
+    inputs = property(lambda self: list(self._inputs))
+    output = property(lambda self: self._outputs[0] if len(self._outputs) == 1 else list(self._outputs))
+    outputs = property(lambda self: list(self._outputs))
+
+    def get_layer(self, name=None, index=None):
+        """The nested sub-model / parameter-free head model applied in this model under `name`."""
+        if name is None or name not in self._graph.layers:
+            raise ValueError('No such layer: %s' % (name,))
+        return self._graph.layers[name]
+
+    def summary(self, *args, **kwargs):
+        pass
 
     # ---- as a model ---------------------------------------------------------------------------------------------
     def _compiled(self):
         if self._impl is None:
-            if self._applied:
+            if self._applied_to:
                 raise NotImplementedError('Model %r was applied as a layer of another model; compile that one' % self._name)
+            if len(self._inputs) != 1:
+                raise NotImplementedError('Model %r: a model with several Inputs can only be used inside another model'
+                                          % self._name)
             g, outs = backend.rewrite(self._graph, self._outputs)
             g.outputs = outs
             g.name = self._name
@@ -448,43 +488,58 @@ class Model(object):
 
     def __getattr__(self, attr):
         # only reached for names this wrapper does not define: everything else is the compiled model's
-        if attr.startswith('__') or attr in ('_impl', '_applied', '_graph', '_inputs', '_outputs', '_single', '_name'):
+        if attr.startswith('__') or attr in Model._OWN:
             raise AttributeError(attr)
         return getattr(self._compiled(), attr)
 
     # ---- as a layer ---------------------------------------------------------------------------------------------
     def __call__(self, x):
-        if self._impl is not None or self._applied:
-            raise NotImplementedError('Model %r: a nested model can be applied once, before it is used as a model'
-                                      % self._name)
-        sub, tgt = self._graph, x.g
+        xs = list(x) if isinstance(x, (list, tuple)) else [x]
+        if self._impl is not None:
+            raise NotImplementedError('Model %r was already compiled as a model of its own' % self._name)
+        if len(xs) != len(self._inputs):
+            raise ValueError('Model %r expects %d input(s), got %d' % (self._name, len(self._inputs), len(xs)))
+        sub, tgt = self._graph, backend.unify(xs)
         if tgt is sub:
             raise ValueError('Model %r applied to a tensor of its own graph' % self._name)
-        src_in = self._inputs[0]
-        if tuple(x.shape) != tuple(src_in.shape):
-            raise ValueError('Model %r expects input shape %s, got %s' % (self._name, src_in.shape, x.shape))
-        self._applied = True
-        known = dict(sub.weight_specs)
+        if any(g is tgt for g in self._applied_to):
+            raise NotImplementedError('Model %r: a nested model is applied once per model (no weight sharing on the '
+                                      "reference's forward path)" % self._name)
+        per_frame = _TD_DEPTH[0] > 0
+        if any(nd.outs[0].kind == 'raw' for nd in sub.nodes) and per_frame and tgt.frames_per_clip != sub.frames_per_clip:
+            raise NotImplementedError('Model %r holds backend arithmetic and is applied under TimeDistributed' % self._name)
+        new = {}
+        for x, src_in in zip(xs, self._inputs):
+            x = _as_image(x)            # per-joint tensors (None, T, joints, c): (T, joints) is the image of the sub-model
+            if tuple(x.shape) != tuple(src_in.shape):
+                raise ValueError('Model %r expects input shape %s, got %s' % (self._name, src_in.shape, x.shape))
+            new[src_in.id] = x
+        kind = new[self._inputs[0].id].kind
+        self._applied_to.append(tgt)
+        tgt.layers.setdefault(self._name, self)
+
         prefix = tgt.qualify(self._name)
+        scoped = lambda n, parts: n if n.count('/') >= parts else prefix + '/' + n      # noqa: E731
+        known = {}
         for wname, shape in sub.weight_specs:                        # creation order is kept
             layer, leaf = wname.rsplit('/', 1)
-            tgt.add_weight(prefix + '/' + layer, leaf, shape)
-        new = {src_in.id: x}
+            known[wname] = tgt.add_weight(scoped(layer, 1), leaf, shape)
         for nd in sub.nodes:
             if nd.op == 'input':
                 continue
             attrs = {}
             for k, v in nd.attrs.items():
                 attrs[k] = dict(v) if isinstance(v, dict) else v
-            if isinstance(attrs.get('name'), str) and nd.attrs.get('name') is not None and any(True for _ in _weight_names(nd.attrs, known)):
-                attrs['name'] = prefix + '/' + attrs['name']
-            for (k1, k2), w in _weight_names(nd.attrs, known):
+            touched = list(_weight_names(nd.attrs, known))
+            if touched and isinstance(attrs.get('name'), str):
+                attrs['name'] = scoped(attrs['name'], 1)
+            for (k1, k2), w in touched:
                 if k2 is None:
-                    attrs[k1] = prefix + '/' + w
+                    attrs[k1] = known[w]
                 else:
-                    attrs[k1][k2] = prefix + '/' + w
+                    attrs[k1][k2] = known[w]
             outs = tgt.op(nd.op, [new[t.id] for t in nd.inputs], [o.shape for o in nd.outs], attrs,
-                          kind=nd.outs[0].kind if nd.outs[0].kind != src_in.kind else x.kind)
+                          kind=kind if nd.outs[0].kind == 'frame' else nd.outs[0].kind)
             outs = outs if isinstance(outs, tuple) else (outs,)
             for o_src, o_new in zip(nd.outs, outs):
                 new[o_src.id] = o_new

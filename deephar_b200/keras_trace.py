@@ -81,6 +81,17 @@ def set_image_data_format(fmt):
     assert fmt == 'channels_last'
 
 
+def unify(ts):
+    """Tensors that descend from different Inputs end up in one graph the first time an op combines them."""
+    g = ts[0].g
+    for t in ts[1:]:
+        if t.g is not g:
+            if t.g.frames_per_clip != g.frames_per_clip:
+                raise ValueError('inputs of one model with different clip lengths')
+            g.absorb(t.g)
+    return g
+
+
 def _raw(op, inputs, shape, **attrs):
     return inputs[0].g.op('k_' + op, list(inputs), [tuple(int(d) for d in shape)], attrs, kind='raw')
 
@@ -181,8 +192,7 @@ def arith(op, a, b):
         if op != 'mul':
             raise NotImplementedError('tensor %s scalar' % op)
         return _raw('scale', [a], kshape(a), s=float(b))
-    if a.g is not b.g:
-        raise ValueError('arithmetic between tensors of two models')
+    unify([a, b])
     return _raw(op, [a, b], np.broadcast_shapes(kshape(a), kshape(b)))
 
 
@@ -392,8 +402,8 @@ class _Rewriter(object):
             raise _NoMatch()
         return self.got(nd.inputs[0])
 
-    def p_softmax2d(self, nd):
-        """activations.py:9-14: e = exp(a*x - max_hw(a*x)); e / clip(sum_hw(e), eps, inf)."""
+    def _softmax_parts(self, nd):
+        """activations.py:9-14: e = exp(a*x - max_hw(a*x)); e / clip(sum_hw(e), eps, inf)  ->  (x, a)."""
         if nd.op != 'k_div':
             raise _NoMatch()
         e, s = nd.inputs
@@ -412,8 +422,18 @@ class _Rewriter(object):
         alpha, x = 1.0, y
         if y.node is not None and y.node.op == 'k_scale':
             alpha, x = y.node.attrs['s'], y.node.inputs[0]
-        if is_raw(x) or sm.attrs['axes'] != self.hw_axes(x) or mx.attrs['axes'] != self.hw_axes(x):
+        if sm.attrs['axes'] != self.hw_axes(x) or mx.attrs['axes'] != self.hw_axes(x):
             raise _NoMatch()
+        return x, alpha
+
+    def p_softmax2d(self, nd):
+        x, alpha = self._softmax_parts(nd)
+        if is_raw(x):
+            # softmax of the depth-averaged volume (action.py:294-295): third output of the extended 3-D head
+            h, depth, nj, _ = self._volume_xy(x)
+            if alpha != 1.0:
+                raise _NoMatch()
+            return self._pose3d(h, depth, nj)[2]
         return L.channel_softmax_2d(self.got(x), alpha=alpha, name=nd.attrs.get('name'))
 
     def _lin_interp(self, t, dim):
@@ -576,13 +596,25 @@ class _Rewriter(object):
             return nd.inputs[0], nd.attrs['c0'], nd.attrs['c1']
         return t, 0, t.channels
 
-    def _visibility_of(self, h, c0, c1):
+    def _visibility_of(self, h, c0, c1, outs):
+        """The joint-probability head on the maps h[..., c0:c1] -- or on s * those maps (`sjProb(4 * hs)`, action.py:200:
+        max of a 2x2 mean is positively homogeneous, so that is s * the fused op's second output) -- gets `outs[1]`."""
+        def maps_of(j):
+            t, s = j.inputs[0], 1.0
+            if t.node is not None and t.node.op == 'k_scale' and t.node.attrs['s'] > 0:
+                t, s = t.node.inputs[0], t.node.attrs['s']
+            return self._sliced(t), s
+
         vis = [j for j in self.g.nodes if j.op == 'head_jprob' and j.id not in self.used_jprob
-               and self._sliced(j.inputs[0])[0] is h and self._sliced(j.inputs[0])[1:] == (c0, c1)]
+               and maps_of(j)[0][0] is h and maps_of(j)[0][1:] == (c0, c1)]
         if len(vis) != 1:
             raise NotImplementedError('soft-argmax head without its joint-probability model on the same maps')
         self.used_jprob.add(vis[0].id)
-        return vis[0]
+        scale = maps_of(vis[0])[1]
+        v = outs[1]
+        if scale != 1.0:
+            v = self.new.op('scale', [v], v.shape, {'value': float(scale)})
+        self.tmap[vis[0].outs[0].id] = v
 
     def p_head_context(self, nd):
         """agg([sam2d(h[..., :nj]), sam2d(h[..., nj:]), jprob(h[..., nj:])]) + jprob(h[..., :nj])."""
@@ -599,10 +631,9 @@ class _Rewriter(object):
                 and h.channels == nj * (nc + 1)):
             raise NotImplementedError('context aggregation over an unexpected split of the heat-maps')
         self.used_jprob.add(pc.node.id)
-        vis = self._visibility_of(h, 0, nj)
         outs = self.new.op('pose_regression_2d_context', [self.got(h)], [(1, nj, 2), (1, nj, 1)],
                            {'num_joints': nj, 'num_context': nc, 'alpha': nd.attrs['alpha']})
-        self.tmap[vis.outs[0].id] = outs[1]
+        self._visibility_of(h, 0, nj, outs)
         return outs[0]
 
     def p_head_plain(self, nd):
@@ -615,19 +646,15 @@ class _Rewriter(object):
         t = nd.inputs[0]
         if is_raw(t):
             raise _NoMatch()
-        vis = self._visibility_of(*self._sliced(t))
         c = t.channels
         outs = self.new.op('pose_regression_2d', [self.got(t)], [(1, c, 2), (1, c, 1)], {})
-        self.tmap[vis.outs[0].id] = outs[1]
+        self._visibility_of(*(self._sliced(t) + (outs,)))
         return outs[0]
 
-    def _volume(self, hxy, hz):
-        """reception.py:196-205: h (H, W, D*nj) -> reshape (H, W, D, nj); hxy = mean over D, hz = mean over (H, W)."""
+    def _volume_xy(self, hxy):
+        """reception.py:196-204: h (H, W, D*nj) -> reshape (H, W, D, nj) (depth-major channels); hxy = mean over D."""
         mxy = self.node(hxy, 'k_mean', keepdims=False)
-        mz = self.node(hz, 'k_mean', keepdims=False)
         rs = self.node(mxy.inputs[0], 'k_reshape')
-        if mz.inputs[0] is not mxy.inputs[0]:
-            raise _NoMatch()
         ex = self.node(rs.inputs[0], 'k_expand_dims')
         h = ex.inputs[0]
         if is_raw(h):
@@ -635,16 +662,63 @@ class _Rewriter(object):
         rows, cols, ch = h.shape
         vol = kshape(rs.outs[0])
         n = len(vol)
-        if vol[-4:-2] != (rows, cols) or vol[-2] * vol[-1] != ch or mxy.attrs['axes'] != (n - 2,) \
-                or mz.attrs['axes'] != (n - 4, n - 3):
+        if vol[-4:-2] != (rows, cols) or vol[-2] * vol[-1] != ch or mxy.attrs['axes'] != (n - 2,):
             raise _NoMatch()
-        return h, vol[-2], vol[-1]
+        return h, vol[-2], vol[-1], rs
+
+    def _volume(self, hxy, hz):
+        """... and hz = mean over (H, W) of the same volume (reception.py:205)."""
+        h, depth, nj, rs = self._volume_xy(hxy)
+        mz = self.node(hz, 'k_mean', keepdims=False)
+        n = len(kshape(rs.outs[0]))
+        if mz.inputs[0] is not rs.outs[0] or mz.attrs['axes'] != (n - 4, n - 3):
+            raise _NoMatch()
+        return h, depth, nj
+
+    def _visibility_3d(self, nd):
+        """sigmoid(s * expand_dims(GlobalMaxPooling2D(hxy) + GlobalMaxPooling1D(hz)))  ->  (h, D, nj, s);
+        s = 1 in reception.py:217-220, 2 in action.py:291-292."""
+        if nd.op != 'k_act' or nd.attrs['fn'] != 'sigmoid':
+            raise _NoMatch()
+        t, scale = nd.inputs[0], 1.0
+        if t.node is not None and t.node.op == 'k_scale':
+            t, scale = t.node.inputs[0], t.node.attrs['s']
+        ex = self.node(t, 'k_expand_dims')
+        ad = self.node(ex.inputs[0], 'k_add')
+        if len(ad.inputs) != 2:
+            raise _NoMatch()
+        g2 = self.node(ad.inputs[0], 'k_gmax2d')
+        g1 = self.node(ad.inputs[1], 'k_gmax1d')
+        return self._volume(g2.inputs[0], g1.inputs[0]) + (scale,)
 
     def _pose3d(self, h, depth, nj):
-        if h.id not in self.p3d:
-            self.p3d[h.id] = self.new.op('pose_regression_3d', [self.got(h)], [(1, nj, 3), (1, nj, 1)],
-                                         {'num_joints': nj, 'depth_maps': depth})
-        return self.p3d[h.id]
+        """The fused 3-D head of the heat-map volume h: (pose, visibility) -- or, when the model also takes the
+        soft-max of the depth-averaged maps or scales the visibility logit (the CVPR'18 clip model), the extended op
+        (pose, visibility, probability maps)."""
+        if h.id in self.p3d:
+            return self.p3d[h.id]
+        scale, wants_prob = 1.0, False
+        for nd in self.g.nodes:
+            try:
+                hv, _, _, sv = self._visibility_3d(nd)
+                if hv is h:
+                    scale = sv
+            except _NoMatch:
+                pass
+            try:
+                x, _ = self._softmax_parts(nd)
+                wants_prob = wants_prob or (is_raw(x) and self._volume_xy(x)[0] is h)
+            except _NoMatch:
+                pass
+        if scale == 1.0 and not wants_prob:
+            outs = self.new.op('pose_regression_3d', [self.got(h)], [(1, nj, 3), (1, nj, 1)],
+                               {'num_joints': nj, 'depth_maps': depth})
+        else:
+            rows, cols, _ = h.shape
+            outs = self.new.op('pose_regression_3d_ex', [self.got(h)], [(1, nj, 3), (1, nj, 1), (rows, cols, nj)],
+                               {'num_joints': nj, 'depth_maps': depth, 'vis_scale': float(scale)})
+        self.p3d[h.id] = outs
+        return outs
 
     def p_head_3d_pose(self, nd):
         """concatenate([sSAM(hxy), zSAM(hz)])."""
@@ -656,16 +730,7 @@ class _Rewriter(object):
         return self._pose3d(h, depth, nj)[0]
 
     def p_head_3d_visibility(self, nd):
-        """sigmoid(expand_dims(GlobalMaxPooling2D(hxy) + GlobalMaxPooling1D(hz)))."""
-        if nd.op != 'k_act' or nd.attrs['fn'] != 'sigmoid':
-            raise _NoMatch()
-        ex = self.node(nd.inputs[0], 'k_expand_dims')
-        ad = self.node(ex.inputs[0], 'k_add')
-        if len(ad.inputs) != 2:
-            raise _NoMatch()
-        g2 = self.node(ad.inputs[0], 'k_gmax2d')
-        g1 = self.node(ad.inputs[1], 'k_gmax1d')
-        h, depth, nj = self._volume(g2.inputs[0], g1.inputs[0])
+        h, depth, nj, _ = self._visibility_3d(nd)
         return self._pose3d(h, depth, nj)[1]
 
     PATTERNS = (p_identity, p_softmax2d, p_softargmax2d, p_keypoint_confidence, p_max_min_pooling,

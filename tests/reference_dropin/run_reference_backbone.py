@@ -80,10 +80,33 @@ def full_spnet_case(which):
     else:
         cfg = ModelConfig((16, 256, 256, 3), pa17j3d, num_actions=[60], num_pyramids=2, action_pyramids=[1, 2],
                           num_levels=4, pose_replica=False, num_pose_features=192, num_visual_features=192)
-    _dump(S.build(cfg))
+    full = S.build(cfg)
+    _dump(full)
+    # spnet.py:417-448 on the recorded model: Model(full.input, full.outputs[:n]) / [n:]
+    pose, act = S.split_model(full, cfg, interlaced=False, model_names=['Pose', 'Action'])
+    print(json.dumps({'split': [[pose.name, len(pose.outputs), pose.graph.signatures()],
+                                [act.name, len(act.outputs), act.graph.signatures()]]}))
+
+
+def merge_model_case(pose_dim):
+    """deephar/models/action.py::build_merge_model (the CVPR'18 clip model, action.py:319-400), unmodified: the
+    sub-models of the pose network are fetched with get_layer() and re-applied under TimeDistributed, `PoseReg` nests
+    them again, PoseAR is a two-Input model, the heads are TimeDistributed head models, sjProb(4 * hs), the soft-max of
+    the heat-maps feeds the kronecker product, 1x1 SeparableConv2D merge weights set with set_weights()."""
+    from deephar.models import action as A
+    keras_compat.clear_session()
+    if pose_dim == 2:
+        pe = R.build((256, 256, 3), 16, dim=2, num_blocks=4, num_context_per_joint=2, ksize=(5, 5))
+        m = A.build_merge_model(pe, 15, (256, 256, 3), 16, 16, 4, pose_dim=2, pose_net_version='v1', full_trainable=False)
+    else:
+        pe = R.build((256, 256, 3), 20, dim=3, num_blocks=4, depth_maps=8, ksize=(5, 5))
+        m = A.build_merge_model(pe, 60, (256, 256, 3), 16, 20, 4, pose_dim=3, depth_maps=8, output_poses=True)
+    _dump(m)
 
 
 def main():
+    if sys.argv[1] == 'merge':
+        return merge_model_case(int(sys.argv[2]))
     if sys.argv[1] == 'spnet':
         return spnet_case()
     if sys.argv[1] == 'full3d':

@@ -230,7 +230,12 @@ def _run_reference(*args):
     out = subprocess.run([sys.executable, os.path.join(here, 'reference_dropin', 'run_reference_backbone.py')] + list(args),
                          capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stderr[-2000:]
-    return json.loads([l for l in out.stdout.splitlines() if l.startswith('{')][-1])
+    lines = [json.loads(l) for l in out.stdout.splitlines() if l.startswith('{')]
+    got = next(d for d in lines if 'weight_specs' in d)
+    for d in lines:
+        if 'weight_specs' not in d:
+            got.update(d)
+    return got
 
 
 def _same_model(got, want, same_launch_order=True):
@@ -282,9 +287,36 @@ def test_reference_full_spnet_build_records_the_c4_c5_models(which):
         cfg = ModelConfig((16, 256, 256, 3), pa17j3d, num_actions=[60], num_pyramids=2, action_pyramids=[1, 2],
                           num_levels=4, pose_replica=False, num_pose_features=192, num_visual_features=192)
     got = _run_reference('spnet_full', which)
-    _same_model(got, spnet.build(cfg), same_launch_order=False)
+    want = spnet.build(cfg)
+    _same_model(got, want, same_launch_order=False)
     assert len(got['plan']) == {'penn': 345, 'ntu': 237}[which]
     assert len(got['output_shape']) == {'penn': 24, 'ntu': 12}[which]
+    # the reference's split_model (spnet.py:417-448) on the recorded model: pose outputs / action outputs
+    n_pose = spnet.get_num_predictions(cfg.num_pyramids, cfg.num_levels)
+    (pname, pn, psig), (aname, an, asig) = got['split']
+    assert (pname, pn, aname, an) == ('Pose', n_pose, 'Action', len(got['output_shape']) - n_pose)
+    assert psig == got['signatures'][:n_pose] and asig == got['signatures'][n_pose:]
+
+
+@pytest.mark.skipif(not os.path.isdir(os.environ.get('DEEPHAR_REFERENCE', '/root/reference')),
+                    reason='needs the reference tree (development container only)')
+@pytest.mark.parametrize('pose_dim', [2, 3])
+def test_reference_merge_model_build_records_the_clip_models(pose_dim):
+    """deephar/models/action.py::build_merge_model, unmodified, on the recording keras (SURVEY 8 a16 / f2): get_layer()
+    of the pose network's sub-models re-applied under TimeDistributed, the nested `PoseReg` model, the two-Input PoseAR
+    model, TimeDistributed head models, sjProb(4 * hs), soft-max -> kronecker product, the 3-D head with its doubled
+    visibility logit (action.py:291-292) and the set_weights()-initialised 1x1 merge convolutions: the recorded model is
+    deephar_b200.action.build_merge_model's -- weights, expressions, launches and their order."""
+    from deephar_b200 import action, reception
+    got = _run_reference('merge', str(pose_dim))
+    if pose_dim == 2:
+        pe = reception.build((256, 256, 3), 16, dim=2, num_blocks=4, num_context_per_joint=2, ksize=(5, 5))
+        want = action.build_merge_model(pe, 15, (256, 256, 3), 16, 16, 4, pose_dim=2)
+    else:
+        pe = reception.build((256, 256, 3), 20, dim=3, num_blocks=4, depth_maps=8, ksize=(5, 5))
+        want = action.build_merge_model(pe, 60, (256, 256, 3), 16, 20, 4, pose_dim=3, depth_maps=8, output_poses=True)
+    _same_model(got, want)
+    assert len(got['weight_specs']) == 421 and len(got['output_shape']) == (9 if pose_dim == 2 else 11)
 
 
 def test_head_models_and_lambda_slices():
@@ -490,3 +522,64 @@ print('ok')
     out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=300,
                          cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert out.returncode == 0 and out.stdout.strip().endswith('ok'), out.stderr[-2000:]
+
+
+def test_models_as_layers_of_other_models():
+    """What deephar/models/action.py does with Keras models, on small ones: a two-Input model used as a layer, sub-models
+    fetched with get_layer() and applied again in another model (same weight names there), a model nesting nested models
+    (one scope per weight), set_weights() that does NOT freeze while the layer stays trainable."""
+    KB = K.backend
+    K.clear_session()
+    # a "pose network" with two named blocks
+    inp = K.Input(shape=(16, 16, 3))
+    xi = K.Input(shape=(16, 16, 3))
+    stem = K.Model(xi, K.Conv2D(8, (3, 3), padding='same', use_bias=False)(xi), name='Stem')
+    x = stem(inp)
+    xi = K.Input(shape=KB.int_shape(x)[1:])
+    head = K.Model(xi, K.Conv2D(4, (1, 1), use_bias=False)(K.Activation('relu')(xi)), name='Head')
+    pe = K.Model(inputs=inp, outputs=head(x))
+    assert pe.get_layer('Stem') is stem and pe.get_layer('Head').name == 'Head'
+    with pytest.raises(ValueError):
+        pe.get_layer('nope')
+    assert [n for n, _ in pe.weight_specs] == ['Stem/conv2d_1/kernel', 'Head/conv2d_2/kernel']
+
+    # a clip model re-using them: Stem under TimeDistributed, Head nested once more inside 'Wrap'
+    clips = K.Input(shape=(4, 16, 16, 3))
+    f = K.TimeDistributed(pe.get_layer('Stem'), name='td_Stem')(clips)
+    wi = K.Input(shape=KB.int_shape(f)[2:])
+    wrap = K.Model(wi, pe.get_layer('Head')(wi), name='Wrap')
+    maps = K.TimeDistributed(wrap, name='td_Wrap')(f)
+    assert KB.int_shape(wrap.output) == (None, 16, 16, 4) and KB.int_shape(maps) == (None, 4, 16, 16, 4)
+
+    # a two-Input sub-model on (T, joints, c) tensors, applied to per-frame results
+    a, b = K.Input(shape=(4, 4, 2)), K.Input(shape=(4, 4, 1))
+    masked = K.Lambda(lambda ts: ts[0] * ts[1])([a, K.Lambda(lambda t: KB.tile(t, [1, 1, 1, 2]))(b)])
+    two = K.Model(inputs=[a, b], outputs=K.Conv2D(6, (3, 3), padding='same', use_bias=False)(masked), name='Two')
+    assert a.g is b.g and len(a.g.inputs) == 2                       # the two Inputs became one graph
+    with pytest.raises(NotImplementedError):
+        two.plan                                                     # several Inputs: only inside another model
+
+    def softmax(t):
+        e = KB.exp(t - KB.max(t, axis=(-3, -2), keepdims=True))
+        return e / KB.clip(KB.sum(e, axis=(-3, -2), keepdims=True), KB.epsilon(), None)
+    prob = K.TimeDistributed(K.Activation(softmax), name='prob')(maps)
+    xy = K.concatenate([_grid_expectation(prob, 'x', 'xy_x'), _grid_expectation(prob, 'y', 'xy_y')], name='xy')
+    vis = K.TimeDistributed(K.Lambda(lambda t: KB.expand_dims(K.GlobalMaxPooling2D()(
+        4 * K.AveragePooling2D((2, 2), strides=(1, 1))(t)), axis=-1)), name='vis')(prob)
+    y = two([xy, vis])
+    # merge weights initialised by hand but left trainable: they stay weights of the model
+    conv = K.SeparableConv2D(6, (1, 1), use_bias=False)
+    z = conv(y)
+    w = conv.get_weights()
+    w[0].fill(1.)
+    conv.set_weights(w)
+    m = K.Model(clips, [z, xy])
+    assert [n for n, _ in m.weight_specs] == ['Stem/conv2d_1/kernel', 'Head/conv2d_2/kernel', 'Two/conv2d_3/kernel',
+                                              'separable_conv2d_1/depthwise_kernel', 'separable_conv2d_1/pointwise_kernel']
+    kinds = [k.kind for k in m.plan.kops]
+    assert kinds.count('conv') == 3 and 'sam2d' in kinds and 'mask_mul' in kinds and kinds[-1] == 'sepconv'
+    assert m.output_shape == [(None, 4, 4, 6), (None, 4, 4, 2)]
+    with pytest.raises(NotImplementedError):
+        stem.plan                                                    # applied as a layer: compile the outer model
+    with pytest.raises(NotImplementedError):
+        pe.get_layer('Stem')(f)                                      # once per model
