@@ -1,6 +1,8 @@
 """Host-side logic (no GPU): the product's layer graph must expose exactly the weight list
 (names, Keras layouts, creation order) that the oracle's independent restatement consumes;
 synthetic weight generators agree; fusion plan sanity; FLOP counts of SURVEY.md 8(d)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -175,3 +177,20 @@ def test_verify_plan_catches_a_clobbered_buffer():
     finally:
         plan.kops.insert(dropped, removed)
     verify_plan(plan, m.graph)
+
+
+def test_roofline_accounting_matches_the_flop_counter_and_the_committed_profile():
+    """tools/roofline_by_layer.py: the per-launch algorithmic flops add up to Model.conv_flops_per_frame, the labels are
+    the ones of the committed per-op profile, and every launch moves at least its output once."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location('roofline_by_layer', os.path.join(root, 'tools', 'roofline_by_layer.py'))
+    rl = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(rl)
+    m = reception.build((256, 256, 3), 16, dim=2, num_blocks=8, num_context_per_joint=2, ksize=(5, 5),
+                        concat_pose_confidence=False)
+    work = [rl.work_of(k, 256, 1) for k in m.plan.kops]
+    assert abs(sum(f for _, f in work) / 256 - m.conv_flops_per_frame()) / m.conv_flops_per_frame() < 1e-9
+    assert all(b >= 4.0 * 256 * np.prod(k.outs[0].shape) for (b, _), k in zip(work, m.plan.kops))
+    prof = open(os.path.join(root, 'profiles', 'r2_prof_reception2d.txt')).read()
+    assert all(rl.label_of(k) in prof for k in m.plan.kops)
