@@ -31,6 +31,10 @@ MSG_DATASPACE, MSG_LINKINFO, MSG_DATATYPE, MSG_LINK, MSG_LAYOUT = 0x01, 0x02, 0x
 MSG_FILTER, MSG_ATTRIBUTE, MSG_CONTINUATION, MSG_SYMTAB, MSG_ATTRINFO = 0x0B, 0x0C, 0x10, 0x11, 0x15
 
 
+# what parsing a damaged file image raises at the lowest level (bad offsets, sizes, strings, type codes)
+CORRUPT = (IndexError, ValueError, TypeError, KeyError, AttributeError, OverflowError, UnicodeDecodeError, MemoryError)
+
+
 class Hdf5Error(IOError):
     pass
 
@@ -173,6 +177,16 @@ class File(Group):
         self._data = memoryview(self._mm)
         self.path = path
         self._objects = {}
+        try:
+            self._read_superblock(path)
+        except Hdf5Error:
+            self.close()
+            raise
+        except CORRUPT as e:            # a damaged image walks the parser off the data: report it as what it is
+            self.close()
+            raise Hdf5Error('%s: corrupt or truncated HDF5 file (%s: %s)' % (path, type(e).__name__, e))
+
+    def _read_superblock(self, path):
         sb = 0
         while True:
             if sb + 8 > len(self._data):
@@ -206,6 +220,8 @@ class File(Group):
         try:
             self._data.release()
             self._mm.close()
+        except BufferError:             # slices still referenced (e.g. by a traceback in flight): the GC unmaps later
+            pass
         finally:
             self._fh.close()
 

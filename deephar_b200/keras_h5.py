@@ -40,7 +40,18 @@ def _weights_root(f):
 
 
 def read_entries(path):
-    """-> ([(group, weight_name, ndarray)], file attrs) in the file's layer / weight order."""
+    """-> ([(group, weight_name, ndarray)], file attrs) in the file's layer / weight order.  A file that is not a
+    readable Keras weight file (truncated download, damaged bytes, a layer group that misses a listed weight) raises
+    hdf5.Hdf5Error, never a parser-internal exception."""
+    try:
+        return _read_entries(path)
+    except hdf5.Hdf5Error:
+        raise
+    except hdf5.CORRUPT as e:
+        raise hdf5.Hdf5Error('%s: corrupt or truncated Keras HDF5 weight file (%s: %s)' % (path, type(e).__name__, e))
+
+
+def _read_entries(path):
     with hdf5.File(path) as f:
         root = _weights_root(f)
         if 'layer_names' in root.attrs:

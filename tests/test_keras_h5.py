@@ -123,3 +123,35 @@ def test_shape_mismatch_is_an_error(tmp_path):
     other = reception.build((32, 32, 3), **dict(KW, num_joints=5))
     with pytest.raises(ValueError):
         other.load_weights(p, by_name=True)
+
+
+def test_damaged_files_raise_hdf5error_not_parser_internals(tmp_path):
+    """Truncated downloads and flipped bytes: the reader either still finds a consistent file or raises hdf5.Hdf5Error
+    (an IOError) -- never IndexError / struct noise, never a hang."""
+    import random
+    src = open(os.path.join(HERE, 'golden', 'tiny_keras_weights.h5'), 'rb').read()
+    rnd = random.Random(7)
+    p = str(tmp_path / 'damaged.h5')
+    outcomes = {'ok': 0, 'error': 0}
+    for it in range(240):
+        b = bytearray(src)
+        if it % 3 == 0:
+            b = b[:rnd.randrange(1, len(b))]
+        elif it % 3 == 1:
+            for _ in range(rnd.randint(1, 4)):
+                b[rnd.randrange(len(b))] = rnd.randrange(256)
+        else:
+            i = rnd.randrange(len(b) - 8)
+            b[i:i + 8] = bytes([rnd.choice([0, 255])] * 8)
+        with open(p, 'wb') as f:
+            f.write(bytes(b))
+        try:
+            keras_h5.read_entries(p)
+            outcomes['ok'] += 1
+        except hdf5.Hdf5Error:
+            outcomes['error'] += 1
+    assert outcomes['error'] >= 80 and outcomes['ok'] >= 40          # every truncation fails; most flips hit float data
+    with open(p, 'wb') as f:
+        f.write(b'')
+    with pytest.raises(hdf5.Hdf5Error):
+        keras_h5.read_entries(p)
