@@ -480,10 +480,20 @@ class Model(object):
             if len(self._inputs) != 1:
                 raise NotImplementedError('Model %r: a model with several Inputs can only be used inside another model'
                                           % self._name)
+            # a model of SOME outputs of a model that is already compiled (spnet.split_model after build + load_weights,
+            # eval_penn_multitask.py:66-81) is a view of that network: same weights, same buffers
+            for outs_full, impl in getattr(self._graph, 'compiled', []):
+                where = [next((i for i, o in enumerate(outs_full) if o is t), None) for t in self._outputs]
+                if None not in where:
+                    self._impl = impl.output_subset(where, name=self._name)
+                    return self._impl
             g, outs = backend.rewrite(self._graph, self._outputs)
             g.outputs = outs
             g.name = self._name
             self._impl = _Model(g, name=self._name)
+            if not hasattr(self._graph, 'compiled'):
+                self._graph.compiled = []
+            self._graph.compiled.append((list(self._outputs), self._impl))
         return self._impl
 
     def __getattr__(self, attr):

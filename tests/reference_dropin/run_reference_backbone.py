@@ -84,8 +84,10 @@ def full_spnet_case(which):
     _dump(full)
     # spnet.py:417-448 on the recorded model: Model(full.input, full.outputs[:n]) / [n:]
     pose, act = S.split_model(full, cfg, interlaced=False, model_names=['Pose', 'Action'])
-    print(json.dumps({'split': [[pose.name, len(pose.outputs), pose.graph.signatures()],
-                                [act.name, len(act.outputs), act.graph.signatures()]]}))
+    print(json.dumps({'split': [[pose.name, len(pose.outputs), [list(s) for s in pose.output_shape],
+                                 pose._compiled().full is full._compiled()],
+                                [act.name, len(act.outputs), [list(s) for s in act.output_shape],
+                                 act._compiled().full is full._compiled()]]}))
 
 
 def merge_model_case(pose_dim):

@@ -293,9 +293,10 @@ def test_reference_full_spnet_build_records_the_c4_c5_models(which):
     assert len(got['output_shape']) == {'penn': 24, 'ntu': 12}[which]
     # the reference's split_model (spnet.py:417-448) on the recorded model: pose outputs / action outputs
     n_pose = spnet.get_num_predictions(cfg.num_pyramids, cfg.num_levels)
-    (pname, pn, psig), (aname, an, asig) = got['split']
+    (pname, pn, pshapes, pshared), (aname, an, ashapes, ashared) = got['split']
     assert (pname, pn, aname, an) == ('Pose', n_pose, 'Action', len(got['output_shape']) - n_pose)
-    assert psig == got['signatures'][:n_pose] and asig == got['signatures'][n_pose:]
+    assert pshapes == got['output_shape'][:n_pose] and ashapes == got['output_shape'][n_pose:]
+    assert pshared and ashared              # views of the full model's network: the weights loaded into it are theirs
 
 
 @pytest.mark.skipif(not os.path.isdir(os.environ.get('DEEPHAR_REFERENCE', '/root/reference')),
@@ -583,3 +584,20 @@ def test_models_as_layers_of_other_models():
         stem.plan                                                    # applied as a layer: compile the outer model
     with pytest.raises(NotImplementedError):
         pe.get_layer('Stem')(f)                                      # once per model
+
+
+def test_a_model_of_some_outputs_shares_the_compiled_network():
+    """Model(full.input, full.outputs[:n]) after the full model exists (spnet.py:443-446): a view, not a second network."""
+    K.clear_session()
+    inp = K.Input(shape=(16, 16, 3))
+    a = K.Conv2D(4, (3, 3), padding='same', use_bias=False, name='a')(inp)
+    b = K.Conv2D(2, (1, 1), use_bias=False, name='b')(K.Activation('relu')(a))
+    full = K.Model(inputs=inp, outputs=[a, b], name='full')
+    table = {n: np.full(s, 0.5, np.float32) for n, s in full.weight_specs}
+    full.set_weights(table)
+    part = K.Model(full.input, full.outputs[1:], name='part')
+    assert part.name == 'part' and part.output_shape == [(None, 16, 16, 2)] and part.input_shape == (None, 16, 16, 3)
+    assert part._compiled().full is full._compiled()
+    assert part._compiled().full.get_weights()['b/kernel'].max() == 0.5
+    other = K.Model(full.input, K.Conv2D(2, (1, 1), use_bias=False, name='c')(a))       # not a subset: its own network
+    assert [n for n, _ in other.weight_specs] == ['a/kernel', 'b/kernel', 'c/kernel'] and other.optional_weights == ['b/kernel']
