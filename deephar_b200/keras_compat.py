@@ -440,7 +440,7 @@ class Model(object):
       action.py:354) but not compiled on their own.
     """
 
-    _OWN = ('_impl', '_applied_to', '_graph', '_inputs', '_outputs', '_single', '_name', 'trainable')
+    _OWN = ('_impl', '_applied_to', '_graph', '_inputs', '_outputs', '_single', '_name', 'trainable', '_fetched_from')
 
     def __init__(self, inputs=None, outputs=None, name=None):
         self._inputs = list(inputs) if isinstance(inputs, (list, tuple)) else [inputs]
@@ -467,7 +467,10 @@ class Model(object):
         """The nested sub-model / parameter-free head model applied in this model under `name`."""
         if name is None or name not in self._graph.layers:
             raise ValueError('No such layer: %s' % (name,))
-        return self._graph.layers[name]
+        layer = self._graph.layers[name]
+        if isinstance(layer, Model):
+            layer._fetched_from = self          # Keras shares the layer objects: weights already loaded here go along
+        return layer
 
     def summary(self, *args, **kwargs):
         pass
@@ -491,6 +494,13 @@ class Model(object):
             g.outputs = outs
             g.name = self._name
             self._impl = _Model(g, name=self._name)
+            mine = set(n for n, _ in self._impl.weight_specs)
+            for src in getattr(self._graph, 'shares_with', []):          # layers fetched with get_layer() from `src`
+                held = getattr(src._impl, '_host_weights', None) if src._impl is not None else None
+                if held:
+                    shared = getattr(self._impl, '_backbone_weights', None) or {}
+                    shared.update({n: w for n, w in held.items() if n in mine})
+                    self._impl._backbone_weights = shared
             if not hasattr(self._graph, 'compiled'):
                 self._graph.compiled = []
             self._graph.compiled.append((list(self._outputs), self._impl))
@@ -527,6 +537,11 @@ class Model(object):
         kind = new[self._inputs[0].id].kind
         self._applied_to.append(tgt)
         tgt.layers.setdefault(self._name, self)
+        if getattr(self, '_fetched_from', None) is not None:
+            if not hasattr(tgt, 'shares_with'):
+                tgt.shares_with = []
+            if all(m is not self._fetched_from for m in tgt.shares_with):
+                tgt.shares_with.append(self._fetched_from)
 
         prefix = tgt.qualify(self._name)
         scoped = lambda n, parts: n if n.count('/') >= parts else prefix + '/' + n      # noqa: E731

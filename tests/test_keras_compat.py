@@ -544,6 +544,8 @@ def test_models_as_layers_of_other_models():
         pe.get_layer('nope')
     assert [n for n, _ in pe.weight_specs] == ['Stem/conv2d_1/kernel', 'Head/conv2d_2/kernel']
 
+    pe.set_weights({n: np.full(sh, 0.25, np.float32) for n, sh in pe.weight_specs})     # "pre-trained" pose network
+
     # a clip model re-using them: Stem under TimeDistributed, Head nested once more inside 'Wrap'
     clips = K.Input(shape=(4, 16, 16, 3))
     f = K.TimeDistributed(pe.get_layer('Stem'), name='td_Stem')(clips)
@@ -580,6 +582,10 @@ def test_models_as_layers_of_other_models():
     kinds = [k.kind for k in m.plan.kops]
     assert kinds.count('conv') == 3 and 'sam2d' in kinds and 'mask_mul' in kinds and kinds[-1] == 'sepconv'
     assert m.output_shape == [(None, 4, 4, 6), (None, 4, 4, 2)]
+    m.init_synthetic_weights(3)                                      # the layers shared with `pe` keep pe's weights
+    got = m.get_weights()
+    assert got['Stem/conv2d_1/kernel'].min() == got['Head/conv2d_2/kernel'].max() == 0.25
+    assert np.unique(got['Two/conv2d_3/kernel']).size > 10
     with pytest.raises(NotImplementedError):
         stem.plan                                                    # applied as a layer: compile the outer model
     with pytest.raises(NotImplementedError):
