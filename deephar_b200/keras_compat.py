@@ -473,7 +473,8 @@ class Model(object):
         return layer
 
     def summary(self, *args, **kwargs):
-        pass
+        if not self._applied_to and len(self._inputs) == 1:
+            self._compiled().summary(*args, **kwargs)
 
     # ---- as a model ---------------------------------------------------------------------------------------------
     def _compiled(self):

@@ -90,6 +90,30 @@ class Model(object):
     def count_params(self):
         return self.graph.num_params()
 
+    def summary(self, line_length=None, positions=None, print_fn=None):
+        """keras.Model.summary (exp/ntu/predict_bboxes.py:45): what this model is on the B200 -- layer scopes with their
+        parameter counts, then the compiled plan."""
+        out = print_fn or print
+        out('Model %r on deephar_b200: input %s, %d outputs' % (self.name, self.input_shape, len(self.graph.outputs)))
+        scopes = {}
+        for name, shape in self.weight_specs:
+            scope = name.split('/')[0]
+            scopes[scope] = scopes.get(scope, 0) + int(np.prod(shape))
+        for scope, n in scopes.items():
+            out('  %-40s %12d' % (scope, n))
+        kinds = {}
+        for k in self.plan.kops:
+            kinds[k.kind] = kinds.get(k.kind, 0) + 1
+        out('Total params: %d in %d weights' % (self.count_params(), len(self.weight_specs)))
+        out('Plan: %d kernel launches per forward (%s); %.2f GFLOP per frame; %d activation buffers in %d slots'
+            % (len(self.plan.kops), ', '.join('%d %s' % (n, kd) for kd, n in sorted(kinds.items(), key=lambda kv: -kv[1])),
+               self.conv_flops_per_frame() / 1e9, self.plan.stats['buffers'], self.plan.stats['phys_slots']))
+
+    def compile(self, *args, **kwargs):
+        raise NotImplementedError('deephar_b200 builds the forward (inference) path; training stays with the reference')
+
+    fit = fit_generator = compile
+
     def conv_flops_per_frame(self):
         """2 x MAC of every Conv2D / SeparableConv2D per input frame; clip-level
         (action head) convs are divided by the frames per clip."""
@@ -629,3 +653,6 @@ class _OutputSubset(object):
 
     def load_weights(self, path, by_name=False):
         return self.full.load_weights(path, by_name=by_name)
+
+    def summary(self, *args, **kwargs):
+        return self.full.summary(*args, **kwargs)

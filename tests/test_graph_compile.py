@@ -194,3 +194,16 @@ def test_roofline_accounting_matches_the_flop_counter_and_the_committed_profile(
     assert all(b >= 4.0 * 256 * np.prod(k.outs[0].shape) for (b, _), k in zip(work, m.plan.kops))
     prof = open(os.path.join(root, 'profiles', 'r2_prof_reception2d.txt')).read()
     assert all(rl.label_of(k) in prof for k in m.plan.kops)
+
+
+def test_summary_and_training_entry_points():
+    """keras.Model.summary (exp/ntu/predict_bboxes.py:45) describes the compiled model; compile / fit are refused."""
+    m = reception.build((64, 64, 3), 16, dim=2, num_blocks=2, num_context_per_joint=2, ksize=(5, 5))
+    lines = []
+    m.summary(print_fn=lines.append)
+    text = '\n'.join(lines)
+    assert 'Stem' in text and 'rBlock2' in text and 'Total params: %d' % m.count_params() in text
+    assert '%d kernel launches' % len(m.plan.kops) in text
+    for call in (m.compile, m.fit, m.fit_generator):
+        with pytest.raises(NotImplementedError):
+            call()
