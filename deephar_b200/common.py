@@ -4,20 +4,19 @@ from .layers import (BatchNormalization, add, appstr, concatenate, conv2d, maxpo
                      sepconv2d, upsampling2d)
 
 
+def _merge_list(merge, tensors):
+    """One tensor passes through; several are merged (common.py:9-22: the reference's two list helpers)."""
+    if not isinstance(tensors, list):
+        raise AssertionError('t should be a list, got ({})'.format(tensors))
+    return merge(tensors) if len(tensors) > 1 else tensors[0]
+
+
 def concat_tensorlist(t):
-    """common.py:9-14."""
-    assert isinstance(t, list), 't should be a list, got ({})'.format(t)
-    if len(t) > 1:
-        return concatenate(t)
-    return t[0]
+    return _merge_list(concatenate, t)
 
 
 def add_tensorlist(t):
-    """common.py:17-22."""
-    assert isinstance(t, list), 't should be a list, got ({})'.format(t)
-    if len(t) > 1:
-        return add(t)
-    return t[0]
+    return _merge_list(add, t)
 
 
 def residual_unit(x, kernel_size, strides=(1, 1), out_size=None,
