@@ -22,97 +22,58 @@ def action_top(x, name=None):
 
 
 def build_act_pred_block(x, num_out, name=None, last=False, include_top=True):
-    """action.py:20-42."""
-    num_features = x.channels
+    """One action prediction stage (action.py:20-42): bottleneck residual (1x1 to half the width, 3x3 back), a 3x3
+    conv whose (max + min)-pooled output carries the `num_out` action maps; unless `last`, the maps are upsampled,
+    widened again and summed with both earlier tensors for the next stage."""
+    width = x.channels
+    trunk = add([x, act_conv_bn(act_conv_bn(x, width // 2, (1, 1)), width, (3, 3))])
+    wide = act_conv_bn(trunk, width, (3, 3))
+    pooled = max_min_pooling(wide, (2, 2))
+    maps = act_conv(pooled, num_out, (3, 3))
+    y = action_top(maps) if include_top else maps
+    if last:
+        return pooled, y
+    back = act_conv_bn(UpSampling2D(maps, (2, 2)), width, (3, 3))
+    return add([trunk, wide, back]), y
 
-    ident = x
-    x = act_conv_bn(x, int(num_features / 2), (1, 1))
-    x = act_conv_bn(x, num_features, (3, 3))
-    x = add([ident, x])
 
-    ident = x
-    x1 = act_conv_bn(x, num_features, (3, 3))
-    x = max_min_pooling(x1, (2, 2))
-    action_hm = act_conv(x, num_out, (3, 3))
-    y = action_hm
-    if include_top:
-        y = action_top(y)
+def _four_stages(x, num_actions, include_top):
+    """y1..y4 of both action nets (action.py:74-81, 101-108): three chained stages and a last one without re-injection."""
+    ys = []
+    for i in range(1, 5):
+        x, y = build_act_pred_block(x, num_actions, name='y%d' % i, include_top=include_top, last=(i == 4))
+        ys.append(y)
+    return ys
 
-    if not last:
-        action_hm = UpSampling2D(action_hm, (2, 2))
-        action_hm = act_conv_bn(action_hm, num_features, (3, 3))
-        x = add([ident, x1, action_hm])
 
-    return x, y
+# widths of the pose net's two multi-branch layers (action.py:55-72): (3x1, 3x3, 3x5 branch), (3x3 / 1x1 -> 3x3 branch, 1x1)
+_POSE_NET_WIDTHS = {'v1': ((8, 16, 24), (56, 32)), 'v2': ((12, 24, 36), (112, 64))}
 
 
 def build_pose_model(y, p, num_actions, name='PoseAR', include_top=True, network_version='v1'):
-    """action.py:45-90 applied to clip tensors y (T,nj,dim), p (T,nj,1)."""
+    """action.py:45-90 applied to clip tensors y (T,nj,dim), p (T,nj,1): confidence-masked coordinates as a (T, nj)
+    image -> three kernel shapes side by side -> two 3x3 branches -> (max + min) pooling -> four stages."""
+    if network_version not in _POSE_NET_WIDTHS:
+        raise Exception('Unkown network version "{}"'.format(network_version))
+    first, (wide, squeeze) = _POSE_NET_WIDTHS[network_version]
     with y.g.scope(name):
         x = mask_multiply(y, p)
-        if network_version == 'v1':
-            a = conv_bn_act(x, 8, (3, 1))
-            b = conv_bn_act(x, 16, (3, 3))
-            c = conv_bn_act(x, 24, (3, 5))
-            x = concatenate([a, b, c])
-            a = conv_bn(x, 56, (3, 3))
-            b = conv_bn(x, 32, (1, 1))
-            b = conv_bn(b, 56, (3, 3))
-            x = concatenate([a, b])
-            x = max_min_pooling(x, (2, 2))
-        elif network_version == 'v2':
-            a = conv_bn_act(x, 12, (3, 1))
-            b = conv_bn_act(x, 24, (3, 3))
-            c = conv_bn_act(x, 36, (3, 5))
-            x = concatenate([a, b, c])
-            a = conv_bn(x, 112, (3, 3))
-            b = conv_bn(x, 64, (1, 1))
-            b = conv_bn(b, 112, (3, 3))
-            x = concatenate([a, b])
-            x = max_min_pooling(x, (2, 2))
-        else:
-            raise Exception('Unkown network version "{}"'.format(network_version))
-
-        x, y1 = build_act_pred_block(x, num_actions, name='y1', include_top=include_top)
-        x, y2 = build_act_pred_block(x, num_actions, name='y2', include_top=include_top)
-        x, y3 = build_act_pred_block(x, num_actions, name='y3', include_top=include_top)
-        _, y4 = build_act_pred_block(x, num_actions, name='y4', include_top=include_top, last=True)
-    return [y1, y2, y3, y4]
+        x = concatenate([conv_bn_act(x, w, (3, kw)) for w, kw in zip(first, (1, 3, 5))])
+        direct = conv_bn(x, wide, (3, 3))
+        x = concatenate([direct, conv_bn(conv_bn(x, squeeze, (1, 1)), wide, (3, 3))])
+        return _four_stages(max_min_pooling(x, (2, 2)), num_actions, include_top)
 
 
 def build_visual_model(f, num_actions, name='GuidedVisAR', include_top=True):
     """action.py:93-109 applied to the clip tensor f (T,nj,F)."""
     with f.g.scope(name):
-        x = conv_bn(f, 256, (1, 1))
-        x = MaxPooling2D(x, (2, 2))
-        x, y1 = build_act_pred_block(x, num_actions, name='y1', include_top=include_top)
-        x, y2 = build_act_pred_block(x, num_actions, name='y2', include_top=include_top)
-        x, y3 = build_act_pred_block(x, num_actions, name='y3', include_top=include_top)
-        _, y4 = build_act_pred_block(x, num_actions, name='y4', include_top=include_top, last=True)
-    return [y1, y2, y3, y4]
+        return _four_stages(MaxPooling2D(conv_bn(f, 256, (1, 1)), (2, 2)), num_actions, include_top)
 
 
 def _get_2d_pose_estimation_from_model(inp, num_joints, num_blocks, num_context_per_joint, ksize):
     """action.py:112-203: the ReceptionNet layers re-wired so that only the last block regresses
     the pose.  Layers are created in reception.build's order so the weight names are identical."""
-    x1 = R._stem(inp)
-    xb1 = R.build_reception_block(x1, name='rBlock1', ksize=ksize)
-    nfilt = xb1.channels
-    num_heatmaps = (num_context_per_joint + 1) * num_joints
-
-    x2 = R.build_sconv_block(xb1, name='SepConv1', ksize=ksize)
-    x3 = R.build_fremap_block(R.build_regmap_block(x2, num_heatmaps, name='RegMap1'), nfilt, name='fReMap1')
-    x = add([xb1, x2, x3])
-    for i in range(2, num_blocks):
-        t1 = R.build_reception_block(x, name='rBlock%d' % i, ksize=ksize)
-        t2 = R.build_sconv_block(t1, name='SepConv%d' % i, ksize=ksize)
-        t3 = R.build_fremap_block(R.build_regmap_block(t2, num_heatmaps, name='RegMap%d' % i), nfilt,
-                                  name='fReMap%d' % i)
-        x = add([t1, t2, t3])
-    x = R.build_reception_block(x, name='rBlock%d' % num_blocks, ksize=ksize)
-    x = R.build_sconv_block(x, name='SepConv%d' % num_blocks, ksize=ksize)
-    h = R.build_regmap_block(x, num_heatmaps, name='RegMap%d' % num_blocks)
-
+    h, xb1 = _backbone_to_heatmaps(inp, (num_context_per_joint + 1) * num_joints, num_blocks, ksize)
     # ys/yc/pc/Agg (alpha 0.8) = the same parameter-free head as reception.py:167-182
     y, vis, _ = R.pose_regression_2d_context(h, num_joints, num_context_per_joint, 0.8)
     # p = sjProb(4 * hs)  (action.py:200): 4 x the raw 2x2-window maximum
