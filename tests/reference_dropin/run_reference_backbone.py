@@ -90,7 +90,7 @@ def full_spnet_case(which):
                                  act._compiled().full is full._compiled()]]}))
 
 
-def merge_model_case(pose_dim):
+def merge_model_case(pose_dim, version='v1'):
     """deephar/models/action.py::build_merge_model (the CVPR'18 clip model, action.py:319-400), unmodified: the
     sub-models of the pose network are fetched with get_layer() and re-applied under TimeDistributed, `PoseReg` nests
     them again, PoseAR is a two-Input model, the heads are TimeDistributed head models, sjProb(4 * hs), the soft-max of
@@ -99,7 +99,7 @@ def merge_model_case(pose_dim):
     keras_compat.clear_session()
     if pose_dim == 2:
         pe = R.build((256, 256, 3), 16, dim=2, num_blocks=4, num_context_per_joint=2, ksize=(5, 5))
-        m = A.build_merge_model(pe, 15, (256, 256, 3), 16, 16, 4, pose_dim=2, pose_net_version='v1', full_trainable=False)
+        m = A.build_merge_model(pe, 15, (256, 256, 3), 16, 16, 4, pose_dim=2, pose_net_version=version, full_trainable=False)
     else:
         pe = R.build((256, 256, 3), 20, dim=3, num_blocks=4, depth_maps=8, ksize=(5, 5))
         m = A.build_merge_model(pe, 60, (256, 256, 3), 16, 20, 4, pose_dim=3, depth_maps=8, output_poses=True)
@@ -108,7 +108,7 @@ def merge_model_case(pose_dim):
 
 def main():
     if sys.argv[1] == 'merge':
-        return merge_model_case(int(sys.argv[2]))
+        return merge_model_case(int(sys.argv[2]), *sys.argv[3:4])
     if sys.argv[1] == 'spnet':
         return spnet_case()
     if sys.argv[1] == 'full3d':

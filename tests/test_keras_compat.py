@@ -301,7 +301,7 @@ def test_reference_full_spnet_build_records_the_c4_c5_models(which):
 
 @pytest.mark.skipif(not os.path.isdir(os.environ.get('DEEPHAR_REFERENCE', '/root/reference')),
                     reason='needs the reference tree (development container only)')
-@pytest.mark.parametrize('pose_dim', [2, 3])
+@pytest.mark.parametrize('pose_dim', [2, 3, 'v2'])
 def test_reference_merge_model_build_records_the_clip_models(pose_dim):
     """deephar/models/action.py::build_merge_model, unmodified, on the recording keras (SURVEY 8 a16 / f2): get_layer()
     of the pose network's sub-models re-applied under TimeDistributed, the nested `PoseReg` model, the two-Input PoseAR
@@ -309,10 +309,13 @@ def test_reference_merge_model_build_records_the_clip_models(pose_dim):
     visibility logit (action.py:291-292) and the set_weights()-initialised 1x1 merge convolutions: the recorded model is
     deephar_b200.action.build_merge_model's -- weights, expressions, launches and their order."""
     from deephar_b200 import action, reception
-    got = _run_reference('merge', str(pose_dim))
+    version = 'v1'
+    if pose_dim == 'v2':                    # the wider PoseAR net (action.py:63-72), 2-D poses
+        pose_dim, version = 2, 'v2'
+    got = _run_reference('merge', str(pose_dim), version)
     if pose_dim == 2:
         pe = reception.build((256, 256, 3), 16, dim=2, num_blocks=4, num_context_per_joint=2, ksize=(5, 5))
-        want = action.build_merge_model(pe, 15, (256, 256, 3), 16, 16, 4, pose_dim=2)
+        want = action.build_merge_model(pe, 15, (256, 256, 3), 16, 16, 4, pose_dim=2, pose_net_version=version)
     else:
         pe = reception.build((256, 256, 3), 20, dim=3, num_blocks=4, depth_maps=8, ksize=(5, 5))
         want = action.build_merge_model(pe, 60, (256, 256, 3), 16, 20, 4, pose_dim=3, depth_maps=8, output_poses=True)
