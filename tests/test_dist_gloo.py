@@ -1,4 +1,4 @@
-"""N > 1 host logic on CPU: world_size-2 gloo processes shard a clip batch, run a deterministic
+"""N > 1 host logic on CPU: world_size-2 and -4 gloo processes shard a clip batch, run a deterministic
 stand-in for the per-rank forward, all-gather the outputs, and must reproduce the unsharded
 result in the original clip order (also with a batch that does not divide evenly)."""
 import os
@@ -15,7 +15,7 @@ from deephar_b200.dist import gather_outputs, shard_range
 
 def _fake_forward(x):
     """stand-in for Model.forward_device: one 'action probability' row per clip"""
-    return torch.softmax(x.reshape(x.shape[0], -1)[:, :15] * 3.0, dim=-1)
+    return torch.softmax(x.reshape(x.shape[0], 4 * 8 * 8 * 3)[:, :15] * 3.0, dim=-1)
 
 
 def _worker(rank, world, port, n_clips, out_path):
@@ -40,10 +40,11 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize('n_clips', [8, 7])
-def test_two_rank_shard_and_gather(tmp_path, n_clips):
+@pytest.mark.parametrize('world,n_clips', [(2, 8), (2, 7), (4, 6), (4, 3)])
+def test_shard_and_gather(tmp_path, world, n_clips):
+    """even shards, ragged shards (padded to the largest, padding dropped) and a rank with NO clip at all"""
     out = str(tmp_path / 'full.npy')
-    mp.spawn(_worker, args=(2, _free_port(), n_clips, out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), n_clips, out), nprocs=world, join=True)
     g = torch.Generator().manual_seed(0)
     x = torch.randn(n_clips, 4, 8, 8, 3, generator=g)
     ref = _fake_forward(x).numpy()
