@@ -63,8 +63,33 @@ class _Inert(object):
         pass
 
 
-def _no_network(*args, **kwargs):
-    raise NotImplementedError('keras.utils.data_utils.get_file: no downloads -- pass the path of a local weight file')
+def get_file(fname, origin=None, untar=False, md5_hash=None, file_hash=None, cache_subdir='datasets',
+             hash_algorithm='auto', extract=False, archive_format='auto', cache_dir=None):
+    """keras.utils.data_utils.get_file for the case the reference's scripts rely on after their first run: the file is
+    already in the Keras cache (`~/.keras/<cache_subdir>/<fname>`, or `fname` itself when it is an absolute path --
+    exp/mpii/eval_mpii_singleperson.py:51-53, datasets/annothelper.py:12-14) and its path is returned.  Nothing is ever
+    downloaded: a missing file is an error that says where to put it.  A hash that differs from the published one is
+    reported, and the local file is used (Keras would download it again)."""
+    import hashlib
+    import os
+    import warnings
+    if untar or extract:
+        raise NotImplementedError('keras.utils.data_utils.get_file: archives are not unpacked here')
+    base = os.path.expanduser(cache_dir or os.environ.get('KERAS_HOME') or os.path.join('~', '.keras'))
+    path = os.path.join(base, cache_subdir, fname)
+    if not os.path.exists(path):
+        raise IOError('keras.utils.data_utils.get_file: %s is not there and nothing is downloaded; fetch %s and place '
+                      'it at that path' % (path, origin))
+    want = file_hash or md5_hash
+    if want:
+        algo = 'md5' if (hash_algorithm == 'md5' or (hash_algorithm == 'auto' and len(want) == 32)) else 'sha256'
+        h = hashlib.new(algo)
+        with open(path, 'rb') as f:
+            for chunk in iter(lambda: f.read(1 << 20), b''):
+                h.update(chunk)
+        if h.hexdigest() != want:
+            warnings.warn('%s: %s %s differs from the published %s; using the local file' % (path, algo, h.hexdigest(), want))
+    return path
 
 
 def install(override_blocks=True):
@@ -93,7 +118,7 @@ def install(override_blocks=True):
     regularizers = _module('keras.regularizers', 'inert', l1=nothing, l2=nothing)
     constraints = _module('keras.constraints', 'inert', unit_norm=nothing)
     losses = _stubbed(_module('keras.losses', 'training only'), 'keras.losses')
-    data_utils = _module('keras.utils.data_utils', 'no network', get_file=_no_network)
+    data_utils = _module('keras.utils.data_utils', 'cache look-up only, no network', get_file=get_file)
     utils = _module('keras.utils', 'inert', data_utils=data_utils, __path__=[], **inert('Sequence', 'OrderedEnqueuer'))
     tensorflow = _stubbed(_module('tensorflow', 'tensorflow stand-in: nothing of it is on the recorded forward path',
                                   __version__='1.6.0'), 'tensorflow')

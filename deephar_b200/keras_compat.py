@@ -495,13 +495,23 @@ class Model(object):
             g.outputs = outs
             g.name = self._name
             self._impl = _Model(g, name=self._name)
+            # Keras models share their layer OBJECTS, so weights already loaded into one model are the weights of every
+            # model made of the same layers: sub-models fetched with get_layer() from `src` (action.py:117-125), and new
+            # outputs built on the tensors of a model that is already loaded (eval_h36m.py:48-59 concatenates pose and
+            # visibility per block AFTER load_weights).  Carried over once, when this model is compiled.
             mine = set(n for n, _ in self._impl.weight_specs)
-            for src in getattr(self._graph, 'shares_with', []):          # layers fetched with get_layer() from `src`
-                held = getattr(src._impl, '_host_weights', None) if src._impl is not None else None
+            donors = [src._impl for src in getattr(self._graph, 'shares_with', []) if src._impl is not None]
+            donors += [impl for _, impl in getattr(self._graph, 'compiled', [])]
+            shared = {}
+            for impl in donors:
+                held = getattr(impl, '_host_weights', None)
                 if held:
-                    shared = getattr(self._impl, '_backbone_weights', None) or {}
-                    shared.update({n: w for n, w in held.items() if n in mine})
-                    self._impl._backbone_weights = shared
+                    shared.update({n: w for n, w in held.items() if n in mine and n not in shared})
+            if shared:
+                self._impl._backbone_weights = shared
+                optional = set(self._impl.optional_weights)
+                if all(n in shared or n in optional for n in mine):      # nothing new to load: the model is ready
+                    self._impl.set_weights(shared)
             if not hasattr(self._graph, 'compiled'):
                 self._graph.compiled = []
             self._graph.compiled.append((list(self._outputs), self._impl))

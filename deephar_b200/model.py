@@ -176,8 +176,9 @@ class Model(object):
             known = set(n for n, _ in self.weight_specs)
             self.unused_file_weights = [k for k in table if k not in known]
             table = {k: v for k, v in table.items() if k in known}
-        if by_name and self._host_weights is not None:
-            merged = dict(self._host_weights)
+        if by_name:                 # layers the file does not name keep what they hold: weights set earlier, or the
+            merged = dict(getattr(self, '_backbone_weights', None) or {})      # ones shared with a model loaded before
+            merged.update(self._host_weights or {})
             merged.update(table)
             table = merged
         self.set_weights(table)
@@ -494,16 +495,27 @@ class Model(object):
             outs.append(o.reshape(self._keras_shape(t, self._items(t.kind, n_frames) if t.kind == 'clip' else n_frames)))
         return outs
 
-    def predict(self, x, batch_size=32, verbose=0):
-        """keras.Model.predict: host numpy in, list of host numpy out.  `batch_size` counts items
-        of the leading axis (frames, or clips for clip models), as in Keras."""
-        torch = self._torch()
+    def _host_input(self, x):
+        """What keras.Model.predict accepts for a single-input model: the array itself or a list holding it
+        (`inputs = [fval]`, exp/common/mpii_tools.py:80-86); returned as contiguous float32 of the model's input shape."""
+        if isinstance(x, (list, tuple)):
+            if len(x) != 1:
+                raise ValueError('model %r has one input, predict() got a list of %d arrays' % (self.name, len(x)))
+            x = x[0]
         x = np.ascontiguousarray(x, dtype=np.float32)
         T = self.graph.frames_per_clip
         lead = 2 if T > 1 else 1
         exp = tuple(self.graph.inputs[0].shape)
         if tuple(x.shape[lead:]) != exp or (T > 1 and x.shape[1] != T):
             raise ValueError('input shape %s does not match model input %s' % (x.shape, self.input_shape))
+        return x
+
+    def predict(self, x, batch_size=32, verbose=0):
+        """keras.Model.predict: host numpy in, list of host numpy out.  `batch_size` counts items
+        of the leading axis (frames, or clips for clip models), as in Keras."""
+        x = self._host_input(x)
+        torch = self._torch()
+        T = self.graph.frames_per_clip
         n = x.shape[0]
         if n == 0:                  # keras returns empty arrays of the right trailing shape
             outs = [np.zeros((0,) + tuple(d for d in self._keras_shape(t, 0)[1:]), np.float32) for t in self.graph.outputs]

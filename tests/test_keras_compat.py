@@ -610,3 +610,53 @@ def test_a_model_of_some_outputs_shares_the_compiled_network():
     assert part._compiled().full.get_weights()['b/kernel'].max() == 0.5
     other = K.Model(full.input, K.Conv2D(2, (1, 1), use_bias=False, name='c')(a))       # not a subset: its own network
     assert [n for n, _ in other.weight_specs] == ['a/kernel', 'b/kernel', 'c/kernel'] and other.optional_weights == ['b/kernel']
+
+
+@pytest.mark.skipif(not os.path.isdir(os.environ.get('DEEPHAR_REFERENCE', '/root/reference')),
+                    reason='needs the reference tree (development container only)')
+@pytest.mark.parametrize('which', ['mpii', 'h36m'])
+def test_reference_entry_scripts_run_unmodified(tmp_path, which):
+    """exp/mpii/eval_mpii_singleperson.py (the headline model's evaluator, BASELINE configs[0]/[1]) and
+    exp/h36m/eval_h36m.py (configs[2]) executed AS THEY ARE (runpy) after dropin.install(): reception.build -> get_file
+    (Keras cache look-up) -> load_weights (Keras HDF5) -> the script's Model(model.input, [concatenate([pose, vis]) ...])
+    re-wrap made after the weights were loaded -> the reference's own evaluator calling model.predict([x]).  Stand-ins:
+    the dataset, the checkpoint contents and (no GPU here) the forward, see tests/reference_dropin/run_reference_script.py."""
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, KERAS_HOME=str(tmp_path / 'keras'))
+    out = subprocess.run([sys.executable, os.path.join(here, 'reference_dropin', 'run_reference_script.py'), which],
+                         capture_output=True, text=True, timeout=900, env=env)
+    assert out.returncode == 0, out.stderr[-3000:]
+    got = json.loads([l for l in out.stdout.splitlines() if l.startswith('{')][-1])
+    assert got['model_class'] == 'deephar_b200.keras_compat.Model' and got['n_outputs'] == 8
+    assert got['output_shape'] == [[None, 16 if which == 'mpii' else 17, 3 if which == 'mpii' else 4]] * 8
+    assert got['weights_are_the_files']            # loaded BEFORE the re-wrap, shared with it as Keras shares layers
+    assert got['scores'] == pytest.approx(got['oracle_scores'], rel=1e-9, abs=1e-12)
+    assert ('r_ankle' if which == 'mpii' else 'Final averaged error') in got['script_printed']     # the script's own report
+
+
+def test_get_file_is_a_cache_lookup(tmp_path, monkeypatch):
+    from deephar_b200 import dropin
+    monkeypatch.setenv('KERAS_HOME', str(tmp_path))
+    with pytest.raises(IOError) as e:
+        dropin.get_file('w.h5', 'https://example.invalid/w.h5', cache_subdir='models')
+    assert str(tmp_path / 'models' / 'w.h5') in str(e.value) and 'example.invalid' in str(e.value)
+    (tmp_path / 'models').mkdir()
+    (tmp_path / 'models' / 'w.h5').write_bytes(b'abc')
+    assert dropin.get_file('w.h5', 'x', cache_subdir='models', md5_hash='900150983cd24fb0d6963f7d28e17f72') == \
+        str(tmp_path / 'models' / 'w.h5')
+    with pytest.warns(UserWarning):
+        assert dropin.get_file('w.h5', 'x', cache_subdir='models', md5_hash='0' * 32).endswith('w.h5')
+    absolute = tmp_path / 'annotations.mat'
+    absolute.write_bytes(b'')
+    assert dropin.get_file(str(absolute), 'x') == str(absolute)     # datasets/annothelper.py passes absolute paths
+
+
+def test_predict_takes_its_input_in_a_list_as_keras_does():
+    from deephar_b200 import reception
+    m = reception.build((64, 64, 3), num_joints=16, dim=2, num_context_per_joint=2, num_blocks=1, ksize=(3, 3))
+    x = np.zeros((2, 64, 64, 3), np.float64)
+    assert m._host_input([x]).shape == (2, 64, 64, 3) and m._host_input([x]).dtype == np.float32   # mpii_tools.py:80-86
+    with pytest.raises(ValueError):
+        m.predict([x, x])
+    with pytest.raises(ValueError):
+        m.predict([x[:, :32]])
