@@ -614,24 +614,39 @@ def test_a_model_of_some_outputs_shares_the_compiled_network():
 
 @pytest.mark.skipif(not os.path.isdir(os.environ.get('DEEPHAR_REFERENCE', '/root/reference')),
                     reason='needs the reference tree (development container only)')
-@pytest.mark.parametrize('which', ['mpii', 'h36m'])
+@pytest.mark.parametrize('which', ['mpii', 'h36m', 'penn_multitask', 'ntu_multitask'])
 def test_reference_entry_scripts_run_unmodified(tmp_path, which):
-    """exp/mpii/eval_mpii_singleperson.py (the headline model's evaluator, BASELINE configs[0]/[1]) and
-    exp/h36m/eval_h36m.py (configs[2]) executed AS THEY ARE (runpy) after dropin.install(): reception.build -> get_file
-    (Keras cache look-up) -> load_weights (Keras HDF5) -> the script's Model(model.input, [concatenate([pose, vis]) ...])
-    re-wrap made after the weights were loaded -> the reference's own evaluator calling model.predict([x]).  Stand-ins:
-    the dataset, the checkpoint contents and (no GPU here) the forward, see tests/reference_dropin/run_reference_script.py."""
+    """The reference's entry scripts of every BASELINE config, executed AS THEY ARE (runpy) after dropin.install():
+    exp/mpii/eval_mpii_singleperson.py (configs[0]/[1], the headline model), exp/h36m/eval_h36m.py (configs[2]),
+    exp/pennaction/eval_penn_multitask.py (configs[3]) and exp/ntu/eval_ntu_multitask.py (configs[4]):
+    reception.build / spnet.build -> get_file (Keras cache look-up) / a local .hdf5 -> load_weights([by_name=True]) ->
+    the scripts' own re-wiring made after the weights were loaded (Model(model.input, [concatenate([pose, vis]) ...]),
+    split_model) -> the reference's own evaluators calling predict([x]) / predict(clip[None]).  The scores the evaluators
+    hand back to the script equal the ones recomputed from the oracle's outputs.  Stand-ins: datasets, checkpoint
+    contents and (no GPU here) the forward -- see tests/reference_dropin/run_reference_script.py."""
     here = os.path.dirname(os.path.abspath(__file__))
     env = dict(os.environ, KERAS_HOME=str(tmp_path / 'keras'))
-    out = subprocess.run([sys.executable, os.path.join(here, 'reference_dropin', 'run_reference_script.py'), which],
+    work = tmp_path / 'checkout'
+    work.mkdir()
+    out = subprocess.run([sys.executable, os.path.join(here, 'reference_dropin', 'run_reference_script.py'), which, str(work)],
                          capture_output=True, text=True, timeout=900, env=env)
     assert out.returncode == 0, out.stderr[-3000:]
+    assert 'exception on sample' not in out.stderr + out.stdout      # the multi-clip evaluators swallow predict() errors
     got = json.loads([l for l in out.stdout.splitlines() if l.startswith('{')][-1])
-    assert got['model_class'] == 'deephar_b200.keras_compat.Model' and got['n_outputs'] == 8
-    assert got['output_shape'] == [[None, 16 if which == 'mpii' else 17, 3 if which == 'mpii' else 4]] * 8
-    assert got['weights_are_the_files']            # loaded BEFORE the re-wrap, shared with it as Keras shares layers
-    assert got['scores'] == pytest.approx(got['oracle_scores'], rel=1e-9, abs=1e-12)
-    assert ('r_ankle' if which == 'mpii' else 'Final averaged error') in got['script_printed']     # the script's own report
+    assert got['model_class'] == 'deephar_b200.keras_compat.Model'
+    assert got['weights_are_the_files']            # loaded BEFORE the re-wiring, shared with it as Keras shares layers
+    expected_calls = {'mpii': ['eval_singleperson_pckh'], 'h36m': ['eval_human36m_sc_error'],
+                      'penn_multitask': ['eval_multiclip_dataset', 'eval_singleclip_generator', 'eval_singleperson_pckh'],
+                      'ntu_multitask': ['eval_multiclip_dataset']}[which]
+    assert sorted(got['returned']) == sorted(got['oracle']) == expected_calls
+    for fn in expected_calls:
+        assert len(got['returned'][fn]) == 1
+        assert got['returned'][fn][0] == pytest.approx(got['oracle'][fn][0], rel=1e-9, abs=1e-12), fn
+    if which in ('mpii', 'h36m'):
+        assert got['output_shape'] == [[None, 16 if which == 'mpii' else 17, 3 if which == 'mpii' else 4]] * 8
+    else:
+        assert got['output_shape'] == [[None, 15 if which == 'penn_multitask' else 60]] * 6      # the 'Action' split
+        assert max(got['returned']['eval_multiclip_dataset'][0]) == 50.0        # labels: one right, one wrong by design
 
 
 def test_get_file_is_a_cache_lookup(tmp_path, monkeypatch):
