@@ -40,18 +40,23 @@ def act_pred_block(c, x, num_out, last=False):
     return x, y
 
 
-def pose_model(c0, y, p, num_actions):
-    """action.py:45-90 (network_version 'v1', include_top=False).  y (B,T,nj,2), p (B,T,nj,1)."""
+POSE_NET_WIDTHS = {'v1': (8, 16, 24, 56, 32), 'v2': (12, 24, 36, 112, 64)}      # action.py:55-72
+
+
+def pose_model(c0, y, p, num_actions, network_version='v1'):
+    """action.py:45-90 (include_top=False).  y (B,T,nj,dim), p (B,T,nj,1); 'v2' (action.py:63-72) is the wider net of
+    exp/ntu/eval_ntu_ar_pe_merge.py."""
     ops = c0.ops
     c = c0.sub('PoseAR')
+    w31, w33, w35, wide, squeeze = POSE_NET_WIDTHS[network_version]
     x = y * p
-    a = c.conv_bn_act(x, 8, (3, 1))
-    b = c.conv_bn_act(x, 16, (3, 3))
-    cc = c.conv_bn_act(x, 24, (3, 5))
+    a = c.conv_bn_act(x, w31, (3, 1))
+    b = c.conv_bn_act(x, w33, (3, 3))
+    cc = c.conv_bn_act(x, w35, (3, 5))
     x = ops.concat([a, b, cc])
-    a = c.conv_bn(x, 56, (3, 3))
-    b = c.conv_bn(x, 32, (1, 1))
-    b = c.conv_bn(b, 56, (3, 3))
+    a = c.conv_bn(x, wide, (3, 3))
+    b = c.conv_bn(x, squeeze, (1, 1))
+    b = c.conv_bn(b, wide, (3, 3))
     x = ops.concat([a, b])
     x = ops.max_min_pooling(x, (2, 2))
     outs = []
@@ -76,7 +81,7 @@ def visual_model(c0, f, num_actions):
 
 def forward(ops, weight_table, x, num_actions, num_joints, num_blocks, num_context_per_joint=2,
             ksize=(5, 5), output_poses=False, weighted_merge=True, return_weights_used=False,
-            pose_dim=2, depth_maps=8):
+            pose_dim=2, depth_maps=8, pose_net_version='v1'):
     """action.py:319-400 on a ReceptionNet built as in eval_penn_ar_pe_merge.py:51-53 (pose_dim=2) or with
     dim=3, depth_maps=`depth_maps` (pose_dim=3, action.py:208-297)."""
     w = Weights(weight_table, ops)
@@ -138,7 +143,7 @@ def forward(ops, weight_table, x, num_actions, num_joints, num_blocks, num_conte
     if output_poses:
         outputs += [y, p]
 
-    out_pose = pose_model(c, y, p, num_actions)
+    out_pose = pose_model(c, y, p, num_actions, pose_net_version)
     f = ops.kronecker_prod(unf(hs_prob), unf(xb1))
     out_vis = visual_model(c, f, num_actions)
 

@@ -47,6 +47,7 @@ import deephar.data  # noqa: E402
 sys.stderr = _stderr
 
 from deephar_b200 import keras_h5  # noqa: E402
+from deephar_b200.compiler import verify_plan  # noqa: E402
 from deephar_b200 import model as product_model  # noqa: E402
 from deephar_b200 import reception as product_reception  # noqa: E402
 from deephar_b200 import spnet as product_spnet  # noqa: E402
@@ -359,7 +360,7 @@ def main():
         'output_shape': [list(s) for s in model.output_shape],
         'weights_are_the_files': set(held) == set(oracle.table) and all(np.array_equal(held[k], oracle.table[k])
                                                                        for k in oracle.table),
-        'launches': len(impl.plan.kops), 'script_printed': printed.getvalue()[-600:],
+        'launches': len(impl.plan.kops), 'plan_checked': verify_plan(impl.plan, impl.graph), 'script_printed': printed.getvalue()[-600:],
         'forward': 'B200' if ON_GPU else 'oracle (CPU stand-in)'}))
 
 

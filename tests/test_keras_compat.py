@@ -635,6 +635,7 @@ def test_reference_entry_scripts_run_unmodified(tmp_path, which):
     got = json.loads([l for l in out.stdout.splitlines() if l.startswith('{')][-1])
     assert got['model_class'] == 'deephar_b200.keras_compat.Model'
     assert got['weights_are_the_files']            # loaded BEFORE the re-wiring, shared with it as Keras shares layers
+    assert got['plan_checked'] > got['launches']   # the re-wired model's buffer plan replays memory-safe
     expected_calls = {'mpii': ['eval_singleperson_pckh'], 'h36m': ['eval_human36m_sc_error'],
                       'penn_multitask': ['eval_multiclip_dataset', 'eval_singleclip_generator', 'eval_singleperson_pckh'],
                       'ntu_multitask': ['eval_multiclip_dataset']}[which]

@@ -23,6 +23,19 @@ def test_merge_weight_specs_match_oracle():
     assert len(outs) == 9 and m.output_shape == [(None, 15)] * 9
 
 
+def test_merge_v2_pose_net_weight_specs_match_oracle():
+    """pose_net_version='v2' with 20 frames and the 3-D head (exp/ntu/eval_ntu_ar_pe_merge.py:51-58)."""
+    pe = reception.build((64, 64, 3), 20, dim=3, num_blocks=2, depth_maps=8, ksize=(5, 5))
+    m = action.build_merge_model(pe, 60, (64, 64, 3), 20, 20, 2, pose_dim=3, depth_maps=8, num_context_per_joint=0,
+                                 pose_net_version='v2')
+    x = synth.synth_frames(20, 64, 64)[None]
+    outs, used = oracle_action.forward(ops_torch, synth.SyntheticTable(3), x, 60, 20, 2, 0, (5, 5), pose_dim=3,
+                                       depth_maps=8, pose_net_version='v2', return_weights_used=True)
+    assert m.weight_specs == used
+    assert any(n.startswith('PoseAR/') and s == (3, 1, 3, 12) for n, s in used)          # 12 filters: the v2 width
+    assert len(outs) == 9 and m.output_shape == [(None, 60)] * 9
+
+
 def test_merge_full_size_config():
     """exp/pennaction/eval_penn_ar_pe_merge.py:42-62: 16 frames, 4 blocks."""
     pe = reception.build((256, 256, 3), 16, dim=2, num_blocks=4, num_context_per_joint=2, ksize=(5, 5),
