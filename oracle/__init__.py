@@ -24,6 +24,11 @@ PARITY -- what is pinned by the reference itself and what is not:
   reference ships no tests or golden tensors and its weights are download-only.  ops_np.py (and the shim,
   written independently with torch kernels) restate SURVEY.md Appendix A; they are checked by closed-form
   known-answer tests (tests/test_oracle_kat.py) and against each other, not against TensorFlow.
+  Third-party referees that ARE in the image (tests/test_oracle_thirdparty.py): the TF-'SAME' padding rule against
+  HuggingFace transformers' TensorFlow-compatible padding (apply_tf_padding of its TF-ported MobileNets), and the
+  arithmetic of Conv2D / the SeparableConv2D stages / MaxPooling2D (-inf padding) / AveragePooling2D /
+  BatchNormalization(eps 1e-3) / UpSampling2D / soft-max against torch's own kernels behind that padding.  That Keras
+  2.1.4 maps its arguments onto exactly these rules remains a documented fact, not an executed one.
 
 Only tests/, __graft_entry__.smoke() and bench.py (cpu_baseline / --impl
 reference) may import this package.  The product (deephar_b200/) never does.
