@@ -514,6 +514,11 @@ class Model(object):
         """keras.Model.predict: host numpy in, list of host numpy out.  `batch_size` counts items
         of the leading axis (frames, or clips for clip models), as in Keras."""
         x = self._host_input(x)
+        if batch_size is None:      # keras: None means the default of 32
+            batch_size = 32
+        if int(batch_size) != batch_size or batch_size < 1:
+            raise ValueError('batch_size must be a positive integer, got %r' % (batch_size,))
+        batch_size = int(batch_size)
         torch = self._torch()
         T = self.graph.frames_per_clip
         n = x.shape[0]

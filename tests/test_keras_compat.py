@@ -682,3 +682,6 @@ def test_predict_takes_its_input_in_a_list_as_keras_does():
         m.predict([x, x])
     with pytest.raises(ValueError):
         m.predict([x[:, :32]])
+    for bad in (0, -1, 2.5):
+        with pytest.raises(ValueError):
+            m.predict(x, batch_size=bad)
