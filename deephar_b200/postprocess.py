@@ -179,3 +179,30 @@ def human36m_mpjpe(preds, afmat, rootz, scam, pose_w, resol_z=2000., map_to_pa17
         dist = np.sqrt(np.sum((y_true - w) ** 2, axis=-1))
         out.append(float((dist * valid).sum() / valid.sum()))
     return out
+
+
+def bbox_from_poses(poses, afmat, scale=1.5, min_confidence=0.25):
+    """exp/common/generic.py:7-28 (`get_bbox_from_poses`, the step after `model.predict` in exp/*/predict_bboxes.py):
+    the person's bounding box in IMAGE coordinates from one frame batch (N, nj, >= 3) or one clip (1, T, nj, >= 3) of
+    predicted poses.  Per frame: the joints whose confidence column -- the second to last one, as the reference slices it
+    (`poses[..., -2:-1]`: the last coordinate for (x, y, v) and (x, y, z, v) rows alike) -- exceeds `min_confidence`,
+    the square box of `scale` x their extent around their centre (deephar/utils/bbox.py:53-76); then the union over the
+    frames, its two corners through the inverse crop affine (transform.py:136-171), re-ordered.  A frame without a joint
+    above the threshold raises ValueError as the reference does.  A few dozen floats: host arithmetic in float64."""
+    poses = np.asarray(poses, np.float64)
+    if poses.ndim == 4:
+        poses = poses[0]
+    elif poses.ndim != 3:
+        raise ValueError('Invalid poses shape {}'.format(poses.shape))
+    xy, keep = poses[:, :, 0:2], poses[:, :, -2] > min_confidence
+    if not keep.any(axis=1).all():
+        raise ValueError('get_valid_bbox: all points are invalid!')
+    lo = np.where(keep[..., None], xy, np.inf).min(axis=1)
+    hi = np.where(keep[..., None], xy, -np.inf).max(axis=1)
+    centre = (lo + hi) / 2.0
+    half = np.max(scale * (hi - lo) / 2.0, axis=1, keepdims=True)          # square=True: the larger half-extent
+    corners = np.array([(centre - half).min(axis=0), (centre + half).max(axis=0)])       # union over the frames
+    A = np.linalg.inv(np.asarray(afmat, np.float64))
+    img = corners @ A[0:2, 0:2].T + A[0:2, 2]
+    return np.concatenate([img.min(axis=0), img.max(axis=0)])
+

@@ -100,3 +100,21 @@ def test_human36m_mpjpe_matches_the_reference_evaluator():
     assert all(abs(a - b) < 5.0 for a, b in zip(nod, want)) and not np.allclose(nod, want, rtol=1e-5)
     with pytest.raises(ValueError):
         pp.human36m_mpjpe([G['preds'][0][:-1]], args[1], args[2], args[3], args[4])
+
+
+def test_bbox_from_poses_matches_the_reference_helper():
+    """tests/golden/ref_bbox_from_poses.npz: boxes returned by the reference's own exp/common/generic.py::get_bbox_from_poses
+    (make_bbox_golden.py) for frame batches, a clip and 3-D rows; two scales."""
+    from deephar_b200 import postprocess as pp
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'ref_bbox_from_poses.npz'))
+    cases = sorted(set(n.split('/')[0] for n in G.files))
+    assert len(cases) == 6
+    for k in cases:
+        got = pp.bbox_from_poses(G[k + '/poses'], G[k + '/afmat'], scale=float(G[k + '/scale']))
+        assert np.abs(got - G[k + '/bbox']).max() <= 1e-9 * np.abs(G[k + '/bbox']).max(), k
+    poses = G['frames_1.5/poses'].copy()
+    poses[2, :, -2] = 0.0                                          # a frame with no joint above the threshold
+    with pytest.raises(ValueError):
+        pp.bbox_from_poses(poses, G['frames_1.5/afmat'])
+    with pytest.raises(ValueError):
+        pp.bbox_from_poses(poses[0], G['frames_1.5/afmat'])
