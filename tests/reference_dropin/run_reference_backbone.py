@@ -106,7 +106,68 @@ def merge_model_case(pose_dim, version='v1'):
     _dump(m)
 
 
+def option_sweep_case():
+    """Builder options off the BASELINE configs: the reference's reception.build / spnet.build (unmodified, recorded) against
+    deephar_b200's builders for the same arguments -- weight lists, output expressions, output shapes, launches.  One JSON
+    line per configuration.  (spnet.py:210-214 keeps a module-level action-block counter across builds in one process --
+    a second model is named act7_..., which breaks by_name loading in the reference itself; reset here per build.)"""
+    from deephar.config import ModelConfig as RefConfig
+    from deephar.models import spnet as S
+    from deephar.utils import pose as ref_pose
+    from deephar_b200 import reception as PR
+    from deephar_b200 import spnet as PS
+    from deephar_b200 import config as pconfig
+
+    def compare(tag, ref_fn, prod_fn):
+        keras_compat.clear_session()
+        S.__dict__.pop('act_cnt', None)
+        res = {'tag': tag}
+        try:
+            ref = ref_fn()
+            ref.weight_specs
+        except Exception as e:                                  # noqa: BLE001
+            ref, res['ref_error'] = None, type(e).__name__
+        try:
+            prod = prod_fn()
+        except Exception as e:                                  # noqa: BLE001
+            prod, res['prod_error'] = None, type(e).__name__
+        if ref is not None and prod is not None:
+            res['weights'] = [(n, tuple(s)) for n, s in ref.weight_specs] == [(n, tuple(s)) for n, s in prod.weight_specs]
+            res['signatures'] = ref.graph.signatures() == prod.graph.signatures()
+            res['shapes'] = [tuple(s) for s in ref.output_shape] == [tuple(s) for s in prod.output_shape]
+            res['launches'] = sorted(k.kind for k in ref.plan.kops) == sorted(k.kind for k in prod.plan.kops)
+            res['n_launches'] = len(prod.plan.kops)
+        print(json.dumps(res))
+
+    for kw in (dict(dim=2, num_context_per_joint=None, num_blocks=1, ksize=(3, 3)),
+               dict(dim=2, num_context_per_joint=1, num_blocks=2, ksize=(5, 5), export_heatmaps=True),
+               dict(dim=2, num_context_per_joint=2, num_blocks=2, ksize=(3, 3), concat_pose_confidence=False, alpha=0.5,
+                    export_vfeat_block=1),
+               dict(dim=3, depth_maps=8, num_blocks=2, ksize=(3, 3)),
+               dict(dim=3, num_blocks=1, ksize=(5, 5), export_heatmaps=True),         # refused by both
+               dict(dim=4, num_blocks=1)):                                            # the reference's own ValueError
+        nj = 17 if kw.get('dim') == 3 else 16
+        compare('reception %r' % (kw,), lambda: R.build((128, 128, 3), nj, **kw), lambda: PR.build((128, 128, 3), nj, **kw))
+    base = dict(num_pyramids=2, num_levels=4, num_actions=[15], action_pyramids=[1, 2])
+    for shape, layout, extra in (
+            ((128, 128, 3), 'pa16j2d', dict(num_actions=[], action_pyramids=[], num_levels=3)),
+            ((128, 128, 3), 'pa17j3d', dict(num_actions=[], action_pyramids=[], predict_rootz=True, growth=64)),
+            ((4, 128, 128, 3), 'pa16j2d', dict(pose_replica=True, kernel_size=(3, 3))),
+            ((4, 128, 128, 3), 'pa20j3d', dict(num_actions=[15, 60], sam_alpha=2)),
+            ((16, 128, 128, 3), 'pa17j3d', dict(action_pyramids=[2], image_div=4)),
+            ((16, 128, 128, 3), 'pa16j2d', dict(num_pyramids=3, action_pyramids=[1, 3], num_pose_features=160,
+                                                num_visual_features=96)),
+            ((4, 128, 128, 3), 'pa16j2d', dict(downsampling_type='conv'))):           # transposed conv: refused by both
+        kw = dict(base)
+        kw.update(extra)
+        compare('spnet %r %s %r' % (shape, layout, extra),
+                lambda: S.build(RefConfig(shape, getattr(ref_pose, layout), **kw)),
+                lambda: PS.build(pconfig.ModelConfig(shape, getattr(pconfig, layout), **kw)))
+
+
 def main():
+    if sys.argv[1] == 'sweep':
+        return option_sweep_case()
     if sys.argv[1] == 'merge':
         return merge_model_case(int(sys.argv[2]), *sys.argv[3:4])
     if sys.argv[1] == 'spnet':

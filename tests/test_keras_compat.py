@@ -323,6 +323,28 @@ def test_reference_merge_model_build_records_the_clip_models(pose_dim):
     assert len(got['weight_specs']) == 421 and len(got['output_shape']) == (9 if pose_dim == 2 else 11)
 
 
+@pytest.mark.skipif(not os.path.isdir(os.environ.get('DEEPHAR_REFERENCE', '/root/reference')),
+                    reason='needs the reference tree (development container only)')
+def test_builder_options_off_the_baseline_configs_match_the_reference_builders():
+    """reception.build / spnet.build arguments the BASELINE configs do not exercise (context maps 0 / 1, alpha, heat-map and
+    feature export, depth_maps, 3 levels, growth, kernel 3x3, predict_rootz, several action sets, sam_alpha, image_div,
+    other action pyramids, pa20j3d): the reference's builder, recorded, and the product's builder give the same model;
+    what one refuses the other refuses."""
+    here = os.path.dirname(os.path.abspath(__file__))
+    out = subprocess.run([sys.executable, os.path.join(here, 'reference_dropin', 'run_reference_backbone.py'), 'sweep'],
+                         capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-2000:]
+    rows = [json.loads(l) for l in out.stdout.splitlines() if l.startswith('{')]
+    assert len(rows) == 13
+    refused = [r for r in rows if 'ref_error' in r or 'prod_error' in r]
+    for r in refused:
+        assert 'ref_error' in r and 'prod_error' in r, r                   # never one side only
+    assert len(refused) == 3 and [r['ref_error'] for r in refused if r['tag'].startswith("reception {'dim': 4")] == ['ValueError']
+    for r in rows:
+        if r not in refused:
+            assert r['weights'] and r['signatures'] and r['shapes'] and r['launches'], r
+
+
 def test_head_models_and_lambda_slices():
     K.clear_session()
     inp = K.Input(shape=(32, 32, 8))
