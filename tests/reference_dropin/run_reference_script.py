@@ -354,13 +354,28 @@ def main():
         model = action_model
     impl = full._compiled()
     held = impl.get_weights()
+    # the plan the script's final model compiled to, executed on the CPU on its own buffer layout (tests/plan_emulator.py),
+    # against the oracle's outputs for one item: pins the re-wired model's launch sequence, not only its scores
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    from plan_emulator import PlanEmulator
+    if name in ('mpii', 'h36m'):
+        x1 = frames[0][0][:1]
+        ref1 = oracle(oracle.table, x1)
+        ref1 = [np.concatenate([ref1[2 * b], ref1[2 * b + 1]], axis=-1) for b in range(len(ref1) // 2)]
+    else:
+        x1 = ds.clip(0, 0, 0)[None]
+        ref1 = oracle(oracle.table, x1)
+    with np.errstate(over='ignore'):
+        emu = PlanEmulator(impl).run(x1)
+    plan_err = max(float(np.abs(o - r).max()) for o, r in zip(emu, ref1))
+    assert len(emu) == len(ref1) and all(o.shape == r.shape for o, r in zip(emu, ref1))
     print(json.dumps({
         'returned': returned, 'oracle': {k: [[float(s) for s in v] for v in vs] for k, vs in want.items()},
         'model_class': type(model).__module__ + '.' + type(model).__name__, 'n_outputs': len(model.outputs),
         'output_shape': [list(s) for s in model.output_shape],
         'weights_are_the_files': set(held) == set(oracle.table) and all(np.array_equal(held[k], oracle.table[k])
                                                                        for k in oracle.table),
-        'launches': len(impl.plan.kops), 'plan_checked': verify_plan(impl.plan, impl.graph), 'script_printed': printed.getvalue()[-600:],
+        'launches': len(impl.plan.kops), 'plan_emulation_max_err': plan_err, 'plan_checked': verify_plan(impl.plan, impl.graph), 'script_printed': printed.getvalue()[-600:],
         'forward': 'B200' if ON_GPU else 'oracle (CPU stand-in)'}))
 
 

@@ -664,6 +664,7 @@ def test_reference_entry_scripts_run_unmodified(tmp_path, which):
     assert got['model_class'] == 'deephar_b200.keras_compat.Model'
     assert got['weights_are_the_files']            # loaded BEFORE the re-wiring, shared with it as Keras shares layers
     assert got['plan_checked'] > got['launches']   # the re-wired model's buffer plan replays memory-safe
+    assert got['plan_emulation_max_err'] < 5e-4    # ... and, executed on the CPU, computes the oracle's outputs (fp32 oracle)
     expected_calls = {'mpii': ['eval_singleperson_pckh'], 'h36m': ['eval_human36m_sc_error'],
                       'penn_multitask': ['eval_multiclip_dataset', 'eval_singleclip_generator', 'eval_singleperson_pckh'],
                       'ntu_multitask': ['eval_multiclip_dataset']}[which]
