@@ -13,6 +13,7 @@ product's synthetic weights (assigned by name).
   * oracle (numpy fp64) vs reference outputs: <= 1e-9 (1e-6 for the merge model) -- pins the oracle's
     restatement of the graph wiring;
   * independent torch-CPU fp32 op set vs reference outputs: <= 2e-4;
+  * the product's compiled plan, executed on the CPU (tests/plan_emulator.py) vs reference outputs: <= 2e-6;
   * product (GPU) vs reference outputs: north-star tolerance 1e-3 (-m gpu).
 """
 import os
@@ -135,6 +136,26 @@ def test_oracle_matches_reference_graph(case):
     for o, r in zip(outs, ref_outs):
         assert o.shape == r.shape
         assert np.abs(np.asarray(o, np.float64) - r).max() <= tol * max(1.0, np.abs(r).max())
+
+
+@pytest.mark.parametrize('case', ALL_CASES)
+def test_compiled_plan_matches_reference_graph(case):
+    """No oracle in between: the product's COMPILED PLAN for the case (fused launches, planned and aliased buffers),
+    executed on the CPU in float64 by tests/plan_emulator.py -- one numpy op per kernel contract of
+    include/deephar_b200.h -- reproduces the outputs of the reference's own builder code, at every BASELINE config's
+    full size (C1 / C3 one frame, C4 / C5 one 16-frame clip).  What the GPU run adds is the kernels' arithmetic."""
+    from plan_emulator import PlanEmulator
+    z, ref_outs = _fixture(case)
+    m, seed = _product(case)
+    _init_weights(case, m, seed)
+    x = _input(case, z).astype(np.float64)
+    with np.errstate(over='ignore'):
+        outs = PlanEmulator(m).run(x)
+    assert len(outs) == len(ref_outs)
+    for i, (o, r) in enumerate(zip(outs, ref_outs)):
+        assert o.shape == r.shape and np.isfinite(o).all(), (case, i)
+        # fixtures stored in float32 bound the agreement at ~1e-7; the float64 ones agree to 1e-14
+        assert np.abs(o - r).max() <= 2e-6 * max(1.0, np.abs(r).max()), (case, i, float(np.abs(o - r).max()))
 
 
 @pytest.mark.gpu
