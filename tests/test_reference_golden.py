@@ -214,3 +214,21 @@ def test_product_matches_reference_graph(cuda, case):
         assert skipped <= max(1, total // 50)
     if maps:
         assert ties <= max(1, maps // 20), '%d of %d heat-maps have an unresolvable top-2 tie' % (ties, maps)
+
+
+@pytest.mark.skipif(not os.path.isdir(os.environ.get('DEEPHAR_REFERENCE', '/root/reference')),
+                    reason='needs the reference tree (development container only)')
+def test_options_off_the_baseline_configs_numerically():
+    """Live, no stored fixture: for builder arguments the BASELINE configs do not use (no / one context map, alpha,
+    heat-map and feature export, depth_maps, 3 pyramid levels, growth, 3x3 kernels, predict_rootz, two action sets,
+    sam_alpha, image_div, pa20j3d, other action pyramids) the reference's own builder code is executed on the eager
+    float64 Keras shim and compared with the product's compiled plan executed by tests/plan_emulator.py."""
+    import json
+    import subprocess
+    out = subprocess.run([sys.executable, os.path.join(HERE, 'golden', 'run_option_sweep_numeric.py')],
+                         capture_output=True, text=True, timeout=1500)
+    assert out.returncode == 0, out.stderr[-3000:]
+    rows = [json.loads(l) for l in out.stdout.splitlines() if l.startswith('{')]
+    assert len(rows) == 10
+    for r in rows:
+        assert r['max_rel_err'] <= 1e-9, r
