@@ -565,6 +565,8 @@ def verify_plan(plan, g):
             checked += 1
         for t in k.outs:
             b, lo, hi = span(t)
+            if k.kind == 'copy':        # a concat input copied into place: only its own channel range is written
+                lo, hi = lo + k.attrs['c_off'], lo + k.attrs['c_off'] + k.attrs['channels']
             for u, (bu, ulo, uhi) in zip(k.ins, reads):
                 if bu.phys != b.phys:
                     continue
