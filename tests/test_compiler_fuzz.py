@@ -1,6 +1,6 @@
 """Compiler fuzzing without a GPU: random layer graphs (Conv2D / SeparableConv2D with strides and 'same' / 'valid' padding,
 BatchNormalization with and without gamma, ReLU, n-ary add, max-pooling, 2x upsampling, concatenation, channel slices,
-zero padding; several outputs, shared sub-expressions, tensors that are both an output and an operand) are compiled, the
+zero padding, fused soft-argmax heads with depth expectation and kronecker product; several outputs, shared sub-expressions, tensors that are both an output and an operand) are compiled, the
 plan is replayed for memory safety (`compiler.verify_plan`) and EXECUTED on the CPU by tests/plan_emulator.py, and the
 result must equal a plain node-by-node evaluation of the un-fused graph.  Whatever fusion, view or buffer-reuse decision
 the compiler takes on a topology the reference models never produce, it may not change the function."""
@@ -46,6 +46,16 @@ def _interpret(g, weights, x):
             y = ins[0][..., a['c0']:a['c1']]
         elif nd.op == 'zeropad':
             y = O.zeropad2d(ins[0], a['pads'])
+        elif nd.op == 'softmax2d':
+            y = O.channel_softmax_2d(ins[0], a['alpha'])
+        elif nd.op == 'softargmax2d':
+            y = O.softargmax2d(ins[0])
+        elif nd.op == 'keypoint_confidence':
+            y = O.keypoint_confidence(ins[0])
+        elif nd.op == 'depth_expect':
+            y = np.sum(O.sigmoid(ins[0]) * ins[1], axis=(1, 2))[..., None]
+        elif nd.op == 'kron':
+            y = np.einsum('nhwj,nhwf->njf', ins[0], ins[1])
         else:
             raise NotImplementedError(nd.op)
         val[t.id] = y
@@ -58,10 +68,11 @@ def _random_graph(seed):
     g = Graph('fuzz%d' % seed)
     side = int(rng.choice([16, 32]))
     pool = [L.conv2d(g.input((side, side, 3)), int(rng.choice([8, 16])), (3, 3), strides=(1, 1))]
+    heads = []
     pick = lambda: pool[int(rng.integers(max(0, len(pool) - 6), len(pool)))]           # noqa: E731  (recent tensors)
     for _ in range(int(rng.integers(10, 26))):
         op = rng.choice(['conv', 'conv', 'sepconv', 'sepconv', 'bn', 'relu', 'relu', 'add', 'add', 'pool', 'up', 'concat',
-                         'slice', 'pad', 'hourglass', 'blockend'])
+                         'slice', 'pad', 'hourglass', 'blockend', 'head'])
         x = pick()
         h, w, c = x.shape
         if op == 'hourglass':
@@ -79,6 +90,21 @@ def _random_graph(seed):
             low = L.sepconv2d(L.relu(L.MaxPooling2D(x, (2, 2))), ch, (3, 3))
             a = L.BatchNormalization(L.sepconv2d(L.relu(x), ch, (int(rng.choice([3, 5])),) * 2), scale=False)
             y = L.add([a, L.UpSampling2D(low)] if rng.random() < 0.7 else [L.UpSampling2D(low), a, x])
+        elif op == 'head':
+            # prediction heads as the compiler fuses them into one launch (spnet.py:178-235): heat-maps -> channel soft-max
+            # -> soft-argmax + joint confidence [+ depth expectation concatenated as z] [+ kronecker product with features]
+            if min(h, w) < 4:
+                continue
+            nj = int(rng.choice([5, 8, 16]))
+            hm = L.conv2d(L.relu(x), nj, (1, 1))
+            prob = L.channel_softmax_2d(hm, alpha=float(rng.choice([1.0, 2.0])))
+            pose, conf = L.softargmax2d(prob), L.keypoint_confidence(prob)
+            if rng.random() < 0.4:
+                pose = L.concatenate([pose, L.depth_expectation(L.conv2d(L.relu(x), nj, (1, 1)), prob)])
+            heads.extend([pose, conf])
+            if rng.random() < 0.5:
+                heads.append(L.kronecker_prod(prob, x))
+            y = L.conv2d(L.relu(L.concatenate([hm, x])), c, (1, 1))                    # re-injection of the heat-maps
         elif op == 'blockend':
             # ... and the block-end: add([x, wide 1x1 conv of a narrow map]) whose 2x2 max-pool becomes the conv kernel's
             # second output on 32-pixel-wide maps (reception.py:108-110, 285-312)
@@ -131,18 +157,22 @@ def _random_graph(seed):
         pool.append(y)
     n_out = int(rng.integers(1, 4))
     outs = [pool[-1]] + [pool[int(i)] for i in rng.choice(len(pool) - 1, size=min(n_out - 1, len(pool) - 1), replace=False)]
-    g.outputs = outs
+    g.outputs = outs + heads
     return g, side
 
 
 def test_the_fuzzer_reaches_the_special_fusions():
-    fused_up = fused_pool = 0
+    fused_up = fused_pool = heads = heads_z = heads_kron = 0
     for seed in range(60):
         g, _ = _random_graph(seed)
         kops = Model(g, name=g.name).plan.kops
         fused_up += sum(1 for k in kops if k.kind == 'sepconv' and k.attrs.get('res_up2x'))
         fused_pool += sum(1 for k in kops if k.kind == 'conv' and k.attrs.get('pool_out'))
-    assert fused_up >= 5 and fused_pool >= 5, (fused_up, fused_pool)
+        heads += sum(1 for k in kops if k.kind == 'sam2d')
+        heads_z += sum(1 for k in kops if k.kind == 'sam2d' and k.attrs['depth'])
+        heads_kron += sum(1 for k in kops if k.kind == 'sam2d' and k.attrs['prob'])
+    assert fused_up >= 5 and fused_pool >= 5 and heads >= 20 and heads_z >= 5 and heads_kron >= 5, \
+        (fused_up, fused_pool, heads, heads_z, heads_kron)
 
 
 @pytest.mark.parametrize('seed', range(60))
