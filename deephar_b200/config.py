@@ -42,73 +42,30 @@ ntu_pe_dataconf = DataConfig(crop_resolution=(256, 256))
 
 
 class ModelConfig(object):
-    """Hyperparameters for models (same constructor as the reference)."""
+    """Hyperparameters of the SPNet models: the reference's constructor (config.py:150-192 -- names, order and defaults
+    are the interface every experiment script uses), every argument kept as an attribute of the same name."""
 
-    def __init__(self, input_shape, poselayout,
-                 num_actions=[],
-                 num_pyramids=8,
-                 action_pyramids=[1, 2],
-                 num_levels=4,
-                 kernel_size=(5, 5),
-                 growth=96,
-                 image_div=8,
-                 predict_rootz=False,
-                 downsampling_type='maxpooling',
-                 pose_replica=False,
-                 num_pose_features=128,
-                 num_visual_features=128,
-                 sam_alpha=1,
-                 dbg_decoupled_pose=False,
-                 dbg_decoupled_h=False):
-        self.input_shape = input_shape
-        self.num_joints = poselayout.num_joints
-        self.dim = poselayout.dim
+    _STORED = ('input_shape', 'num_actions', 'num_pyramids', 'action_pyramids', 'num_levels', 'kernel_size', 'growth',
+               'image_div', 'predict_rootz', 'downsampling_type', 'pose_replica', 'num_pose_features',
+               'num_visual_features', 'sam_alpha', 'dbg_decoupled_pose', 'dbg_decoupled_h')
 
-        assert type(num_actions) == list, 'num_actions should be a list'
-        self.num_actions = num_actions
-
-        self.num_pyramids = num_pyramids
-        self.action_pyramids = action_pyramids
-        self.num_levels = num_levels
-        self.kernel_size = kernel_size
-        self.growth = growth
-        self.image_div = image_div
-        self.predict_rootz = predict_rootz
-        self.downsampling_type = downsampling_type
-        self.pose_replica = pose_replica
-        self.num_pose_features = num_pose_features
-        self.num_visual_features = num_visual_features
-        self.sam_alpha = sam_alpha
-
-        self.dbg_decoupled_pose = dbg_decoupled_pose
-        self.dbg_decoupled_h = dbg_decoupled_h
+    def __init__(self, input_shape, poselayout, num_actions=[], num_pyramids=8, action_pyramids=[1, 2], num_levels=4,
+                 kernel_size=(5, 5), growth=96, image_div=8, predict_rootz=False, downsampling_type='maxpooling',
+                 pose_replica=False, num_pose_features=128, num_visual_features=128, sam_alpha=1,
+                 dbg_decoupled_pose=False, dbg_decoupled_h=False):
+        given = locals()
+        if type(num_actions) != list:
+            raise AssertionError('num_actions should be a list')
+        for name in self._STORED:
+            setattr(self, name, given[name])
+        self.num_joints, self.dim = poselayout.num_joints, poselayout.dim          # all the forward path reads of a layout
 
 
-class pa16j2d(object):
-    num_joints = 16
-    dim = 2
+def _layout(name, num_joints, dim):
+    """deephar/utils/pose.py:127-140: of a pose layout the models only read the joint count and the dimension."""
+    return type(name, (object,), {'num_joints': num_joints, 'dim': dim, '__doc__': '%d joints, %d-D' % (num_joints, dim)})
 
 
-class pa16j3d(object):
-    num_joints = 16
-    dim = 3
-
-
-class pa17j2d(object):
-    num_joints = 17
-    dim = 2
-
-
-class pa17j3d(object):
-    num_joints = 17
-    dim = 3
-
-
-class pa20j3d(object):
-    num_joints = 20
-    dim = 3
-
-
-class pa21j3d(object):
-    num_joints = 21
-    dim = 3
+pa16j2d, pa16j3d = _layout('pa16j2d', 16, 2), _layout('pa16j3d', 16, 3)
+pa17j2d, pa17j3d = _layout('pa17j2d', 17, 2), _layout('pa17j3d', 17, 3)
+pa20j3d, pa21j3d = _layout('pa20j3d', 20, 3), _layout('pa21j3d', 21, 3)
