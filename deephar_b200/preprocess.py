@@ -137,6 +137,111 @@ def clip_window(image_size, dconf=None, bbox=None):
     return objpos, np.array(winsize, np.float64)
 
 
+def _decode_one(path):
+    from PIL import Image
+    with Image.open(path) as im:
+        return np.asarray(im if im.mode == 'RGB' else im.convert('RGB'))
+
+
+_ARENA = None       # shared anonymous mapping the decoder's workers write into (set in the parent before they are forked)
+
+
+def _probe(path):
+    from PIL import Image
+    with Image.open(path) as im:        # header only
+        return im.size[1], im.size[0]
+
+
+def _decode_into(job):
+    path, offset, nbytes = job
+    a = _decode_one(path)
+    if a.size != nbytes:
+        raise ValueError('%s: decoded %d bytes, its header announced %d' % (path, a.size, nbytes))
+    np.frombuffer(_ARENA, dtype=np.uint8, count=nbytes, offset=offset)[:] = a.reshape(-1)
+    return a.shape
+
+
+class ImageDecoder(object):
+    """`Image.open(path)` of the reference's loaders (data/mpii.py:83, data/pennaction.py:152, data/ntu.py:221,
+    data/human36m.py:110) for a whole batch: decoded RGB uint8 (H, W, 3) arrays in the order of the paths, ready for
+    FramePipeline.  Decoding stays on the host and stays Pillow's (the frames must be the reference's, bit for bit), but
+    one core decodes ~300-400 VGA JPEGs per second and the forward consumes thousands: the batch is spread over a pool of
+    worker PROCESSES (Pillow holds the GIL while it decodes, threads do not scale), forked on first use and kept -- as
+    torch's DataLoader forks its workers: they only ever run Pillow and never touch the parent's CUDA state.  The pixels
+    come back through one shared anonymous mapping (`arena_mb`), not through pickles.  Grey-scale / palette files are
+    converted to RGB (the models take 3 channels).
+
+        decode = ImageDecoder(workers=16)
+        frames, afmat = pipe(decode(paths), objpos, winsize)
+    """
+
+    def __init__(self, workers=None, arena_mb=256):
+        import os
+        self.workers = max(1, int(workers or min(32, os.cpu_count() or 1)))
+        self.arena_bytes = int(arena_mb) << 20
+        self._pool = None
+
+    def _start(self):
+        global _ARENA
+        import mmap
+        import multiprocessing
+        self._arena = _ARENA = mmap.mmap(-1, self.arena_bytes)         # MAP_SHARED | MAP_ANONYMOUS: inherited by the fork
+        self._pool = multiprocessing.get_context('fork').Pool(self.workers)
+        _ARENA = None
+
+    def __call__(self, paths):
+        paths = [str(p) for p in paths]
+        if self.workers == 1 or len(paths) < 2:
+            return [_decode_one(p) for p in paths]
+        if self._pool is None:
+            self._start()
+        chunk = max(1, len(paths) // (4 * self.workers))
+        sizes = self._pool.map(_probe, paths, chunksize=chunk)
+        out, i = [None] * len(paths), 0
+        while i < len(paths):
+            jobs, used = [], 0
+            while i + len(jobs) < len(paths):                           # as many images as fit the arena
+                h, w = sizes[i + len(jobs)]
+                if used + h * w * 3 > self.arena_bytes:
+                    break
+                jobs.append((paths[i + len(jobs)], used, h * w * 3))
+                used += h * w * 3
+            if not jobs:                                                # one image larger than the arena
+                out[i] = _decode_one(paths[i])
+                i += 1
+                continue
+            shapes = self._pool.map(_decode_into, jobs, chunksize=max(1, len(jobs) // (4 * self.workers)))
+            for k, ((_, off, n), shp) in enumerate(zip(jobs, shapes)):
+                out[i + k] = np.frombuffer(self._arena, dtype=np.uint8, count=n, offset=off).reshape(shp).copy()
+            i += len(jobs)
+        return out
+
+    def close(self):
+        if self._pool is not None:
+            self._pool.terminate()
+            self._pool.join()
+            self._pool = None
+            self._arena.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:       # interpreter shutdown
+            pass
+
+
+def decode_images(paths, workers=1):
+    """One-shot form of ImageDecoder (in-process by default; a pool started for one call costs more than it saves)."""
+    with ImageDecoder(workers) as dec:
+        return dec(paths)
+
+
 class FramePipeline(object):
     """Batched evaluation input pipeline bound to one device.
 

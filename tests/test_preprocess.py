@@ -184,3 +184,33 @@ def test_clip_sampling_and_windows_match_the_reference_helpers():
         assert np.allclose(objpos, row[9:11], rtol=0, atol=1e-12) and np.allclose(win, row[11:13], rtol=0, atol=1e-12)
     with pytest.raises(ValueError):
         preprocess.clip_frame_index(100, 0, 16)
+
+
+def test_decode_images_keeps_order_and_content(tmp_path):
+    """the batch front of FramePipeline: pooled Pillow decode == one Image.open per file, in the order given"""
+    from PIL import Image
+    from deephar_b200 import preprocess
+    rng = np.random.default_rng(4)
+    paths, want = [], []
+    for i, (h, w) in enumerate([(48, 64), (30, 30), (64, 40), (33, 77), (20, 21)] * 3):
+        arr = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        fmt = 'png' if i % 2 else 'jpg'
+        path = str(tmp_path / ('im%d.%s' % (i, fmt)))
+        Image.fromarray(arr).save(path, quality=95)
+        paths.append(path)
+        want.append(np.asarray(Image.open(path)))
+    grey = str(tmp_path / 'grey.png')
+    Image.fromarray(rng.integers(0, 256, (16, 18), dtype=np.uint8)).save(grey)
+    paths.append(grey)
+    want.append(np.asarray(Image.open(grey).convert('RGB')))
+
+    def same(got):
+        assert len(got) == len(want)
+        for g, w_ in zip(got, want):
+            assert g.dtype == np.uint8 and g.shape == w_.shape and np.array_equal(g, w_)
+    same(preprocess.decode_images(paths))
+    with preprocess.ImageDecoder(workers=3) as dec:
+        same(dec(paths))
+        same(dec(paths[::-1])[::-1])                # the pool is kept between calls
+        assert dec([]) == [] and len(dec(paths[:1])) == 1
+    assert dec._pool is None
