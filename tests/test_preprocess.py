@@ -186,6 +186,8 @@ def test_clip_sampling_and_windows_match_the_reference_helpers():
         preprocess.clip_frame_index(100, 0, 16)
 
 
+@pytest.mark.timeout(180)
+@pytest.mark.filterwarnings('ignore:This process .* is multi-threaded, use of fork')
 def test_decode_images_keeps_order_and_content(tmp_path):
     """the batch front of FramePipeline: pooled Pillow decode == one Image.open per file, in the order given"""
     from PIL import Image
