@@ -151,26 +151,40 @@ def build_workload(name):
     return spnet.build(cfg).init_synthetic_weights(1234), True, label
 
 
+def shard_plan(items_global, item_frames, rank, world, micro_frames, clip_model):
+    """Host arithmetic of one rank's share of a step (no device): the contiguous shard of the global batch
+    (`dist.shard_range`), the leading extent of its input tensor -- clips for clip models, frames otherwise -- and how it
+    is cut into forward calls of at most `micro_frames` frames.  -> dict(first, items_local, frames_local, lead,
+    micro_items, spans)."""
+    from deephar_b200.dist import shard_range
+    a, b = shard_range(items_global, rank, world)
+    items_local = b - a
+    frames_local = items_local * item_frames
+    lead = items_local if clip_model else frames_local
+    per = FRAMES if clip_model else 1
+    micro_items = max(1, min(micro_frames // per, lead)) if lead else 1
+    spans = [(i, min(i + micro_items, lead)) for i in range(0, lead, micro_items)]
+    return {'first': a, 'items_local': items_local, 'frames_local': frames_local, 'lead': lead,
+            'micro_items': micro_items, 'spans': spans}
+
+
 class Runner(object):
     """One workload on this rank's shard of a global batch of `items` (clips, or frames for b32-of-frames configs)."""
 
     def __init__(self, torch, model, clip_model, items_global, item_frames, rank, world, micro_frames, precision=3):
-        from deephar_b200.dist import shard_range
         self.torch, self.model, self.world = torch, model, world
         model.precision = precision
-        a, b = shard_range(items_global, rank, world)
-        self.items_global, self.items_local, self.item_frames = items_global, b - a, item_frames
-        self.frames_local = self.items_local * item_frames
+        plan = shard_plan(items_global, item_frames, rank, world, micro_frames, clip_model)
+        self.items_global, self.items_local, self.item_frames = items_global, plan['items_local'], item_frames
+        self.frames_local = plan['frames_local']
         self.clip_model = clip_model
-        shape = ((self.items_local, FRAMES, 256, 256, 3) if clip_model else (self.frames_local, 256, 256, 3))
-        gen = torch.Generator().manual_seed(1000 + a)
+        shape = ((plan['lead'], FRAMES, 256, 256, 3) if clip_model else (plan['lead'], 256, 256, 3))
+        gen = torch.Generator().manual_seed(1000 + plan['first'])
         self.x_host = torch.empty(*shape, dtype=torch.float32).pin_memory()
         if self.x_host.numel():
             self.x_host.uniform_(-1.0, 1.0, generator=gen)
         self.x_dev = self.x_host.cuda()
-        per = FRAMES if clip_model else 1
-        self.micro_items = max(1, min(micro_frames // per, shape[0])) if shape[0] else 1
-        self.spans = [(i, min(i + self.micro_items, shape[0])) for i in range(0, shape[0], self.micro_items)]
+        self.micro_items, self.spans = plan['micro_items'], plan['spans']
         self.comm = None            # dist.Comm: the all-gather through the C ABI (set by main for world > 1)
 
     def forward_all(self):

@@ -1,0 +1,68 @@
+"""bench.py's host logic without a device: the strong-scaling shard arithmetic of every workload at N = 1, 2, 4, 8, the
+nvidia-smi clock parser, and the contract keys of the reference-arm line (the CPU port itself is stubbed: it is timed for
+real by the driver)."""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+# (global items, frames per item, clip model) of the headline and the secondary configs (bench.py main)
+WORKLOADS = {'headline': (32, 16, False), 'weak x8': (32 * 8, 16, False), 'C3': (32, 1, False), 'C4': (16, 16, True),
+             'C5': (64, 16, True)}
+
+
+@pytest.mark.parametrize('world', [1, 2, 4, 8])
+@pytest.mark.parametrize('name', sorted(WORKLOADS))
+def test_every_rank_gets_a_contiguous_non_empty_shard(name, world):
+    items, per, clip = WORKLOADS[name]
+    plans = [bench.shard_plan(items, per, r, world, 256, clip) for r in range(world)]
+    assert [p['first'] for p in plans] == list(np.cumsum([0] + [p['items_local'] for p in plans[:-1]]))
+    assert sum(p['items_local'] for p in plans) == items and all(p['items_local'] > 0 for p in plans)
+    for p in plans:
+        assert p['frames_local'] == p['items_local'] * per
+        assert p['lead'] == (p['items_local'] if clip else p['frames_local'])
+        frames_per_call = p['micro_items'] * (bench.FRAMES if clip else 1)
+        assert 1 <= frames_per_call <= 256
+        assert p['spans'][0][0] == 0 and p['spans'][-1][1] == p['lead']
+        assert all(a1 == b0 for (_, b0), (a1, _) in zip(p['spans'], p['spans'][1:]))
+    if name == 'headline':                  # 32 / 16 / 8 / 4 clips per GPU
+        assert plans[0]['items_local'] == 32 // world and plans[0]['frames_local'] == 512 // world
+
+
+def test_clock_sampler_parses_nvidia_smi_lines():
+    s = bench.ClockSampler(0)
+    s.proc = type('P', (), {'terminate': lambda self: None, 'wait': lambda self, timeout=None: 0, 'kill': lambda self: None})()
+    s.lines = ['0, 1890, 1965, 830.1, 0x0000000000000004, Not Active, Not Active, Not Active, Active',
+               '0, 1905, 1965, 790.0, 0x0000000000000000, Not Active, Not Active, Not Active, Not Active',
+               '0, 1875, 1965, 845.5, 0x0000000000000004, Not Active, Not Active, Not Active, Active',
+               'garbage', '0, [N/A], 1965, 1, 0, Not Active, Not Active, Not Active, Not Active']
+    got = s.stop()
+    assert got == {'sm_mhz': 1890.0, 'sm_max_mhz': 1965.0, 'reasons': ['sw_power_cap'], 'samples': 3}
+    empty = bench.ClockSampler(0)
+    assert empty.stop()['reasons'] == ['nvidia-smi unavailable']
+
+
+def test_reference_arm_line_has_the_contract_keys(monkeypatch, capsys):
+    monkeypatch.setattr(bench, 'cpu_port', lambda **kw: {'b32_times': [3.0, 3.2, 2.8], 'b1_times': [0.1] * 10, 'cores': 128,
+                                                          'threads': 16, 'chunk': 8, 'calibration': {'16 threads, b8': 11.0}})
+    monkeypatch.setenv('RANK', '0')
+    args = type('A', (), {'steps': 3, 'warmup': 1, 'gpus': 4, 'micro_batch': 256})()
+    bench.run_reference(args)
+    line = json.loads(capsys.readouterr().out.strip())
+    assert line['impl'] == 'reference' and line['metric'] == bench.METRIC and line['unit'] == 'frames/s'
+    assert line['value'] == pytest.approx(32.0 / 3.0) and line['ms_per_step'] == pytest.approx(3000.0)
+    assert line['n_gpus'] == 4 and line['higher_is_better'] is True and line['vs_baseline'] is None
+    assert line['e2e'] == {'value': line['value'], 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+    assert line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['cores'] == 16
+    assert line['cpu_baseline']['value'] == line['value'] and 'predict batch_size=8' in line['cpu_baseline']['sample']
+    # same `config` as the product arm prints for the same N (the driver compares them)
+    assert line['config'] == bench.headline_config(4, 128, 128)
+    monkeypatch.setenv('RANK', '1')             # the other ranks of a torchrun launch print nothing
+    bench.run_reference(args)
+    assert capsys.readouterr().out == ''
