@@ -66,3 +66,48 @@ def test_reference_arm_line_has_the_contract_keys(monkeypatch, capsys):
     monkeypatch.setenv('RANK', '1')             # the other ranks of a torchrun launch print nothing
     bench.run_reference(args)
     assert capsys.readouterr().out == ''
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize('world', [1, 8])
+def test_bench_control_flow_on_the_stand_in_device(world):
+    """bench.py from its first line to its JSON line on tests/fake_cuda.py (host memory as device memory, inert streams /
+    events / graphs, gloo for NCCL, every device entry point of the C library a no-op): model builds, buffer binding,
+    CUDA-graph branch, the copy-pipelined predict of the e2e leg, the per-kernel profile, the exchange step through
+    dist.Comm, the weak-scaling and C3 / C4 / C5 secondary runs with their shards, at N = 1 and N = 8 ranks.  The numbers
+    mean nothing; the contract keys and the shard sizes do."""
+    import socket
+    import subprocess
+    fake = os.path.join(ROOT, 'tests', 'fake_cuda.py')
+    tail = [fake, os.path.join(ROOT, 'bench.py'), '--gpus', str(world), '--steps', '1', '--warmup', '3', '--no-cpu-baseline']
+    if world == 1:
+        cmd = [sys.executable] + tail
+    else:
+        s = socket.socket()
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+        s.close()
+        cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(world),
+               '--master-addr', '127.0.0.1', '--master-port', str(port)] + tail
+    env = {k: v for k, v in os.environ.items() if k not in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK')}
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=580, cwd=ROOT, env=env)
+    assert out.returncode == 0, out.stderr[-3000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith('{')]
+    assert len(lines) == 1, 'exactly one JSON line, from rank 0'
+    d = json.loads(lines[0])
+    assert d['metric'] == bench.METRIC and d['unit'] == 'frames/s' and d['n_gpus'] == world and d['scaling'] == 'strong'
+    assert d['steps'] == 1 and d['warmup'] == 3 and d['higher_is_better'] is True and d['vs_baseline'] is None
+    assert d['value'] > 0 and d['ms_per_step'] > 0 and d['data'] == 'synthetic' and 'bf16x3' in d['dtype']
+    assert d['config'] == bench.headline_config(world, 512 // world, min(256, 512 // world))
+    assert set(d['clocks']) >= {'sm_mhz', 'sm_max_mhz', 'reasons'}
+    assert d['e2e']['value'] > 0 and d['e2e']['h2d_bytes_per_step'] == 512 * 256 * 256 * 3 * 4 and d['e2e']['d2h_bytes_per_step'] > 0
+    assert d['gpu_launches'] >= 127 * world and '127 kernels per forward' in d['launch_mode']
+    assert set(d['roofline']) >= {'kernel', 'bound', 'achieved', 'peak', 'unit', 'frac', 'traffic'}
+    assert len(d['kernel_profile']) == 10 and 'cpu_baseline' not in d
+    sec = d['secondary']
+    assert set(sec) >= {'softargmax3d', 'input_pipeline', 'C1', 'C3', 'C4', 'C5'} and ('weak' in sec) == (world > 1)
+    assert (sec['C3']['frames_per_gpu'], sec['C4']['frames_per_gpu'], sec['C5']['frames_per_gpu']) == \
+        (32 // world, 256 // world, 1024 // world)
+    assert (sec['C3']['launches_per_forward'], sec['C4']['launches_per_forward'], sec['C5']['launches_per_forward']) == (134, 345, 237)
+    if world > 1:
+        assert sec['weak']['frames_per_gpu'] == 512 and sec['weak']['scaling'] == 'weak'
