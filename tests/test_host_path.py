@@ -1,0 +1,35 @@
+"""The `-m gpu` model tests, executed on the CPU through the product's OWN host path.
+
+tests/fake_cuda.py --arithmetic replaces the device by host memory and puts numpy arithmetic (the oracle's primitives)
+behind the C entry points of the model forward, decoding the raw `dh_view` / `dh_conv_desc` / weight-pointer arguments as
+the CUDA side does.  Everything above the kernels is the product's: `Model._bind` (buffer slots, channel offsets, leading
+dimensions, folded BatchNormalization vectors, residual / pooled-output descriptors), `_issue`, the CUDA-graph branch
+(captured calls are re-issued on replay), the copy-pipelined `predict`, `load_weights`, `split_model` views, the
+keras_compat front end.  The unchanged GPU tests then hold at their GPU tolerances: ReceptionNet 2-D / 3-D vs the oracle,
+SPNet and merge-model parity, CUDA-graph replay == plain launches, predict edge cases, Keras-HDF5-driven forward, and the
+reference-builder goldens of every BASELINE config at full size.  Deselected: tests that read kernel-internal counters
+(`dh_fallback_count`), the 64-forward batch-independence test (CPU time), and the direct C-ABI op tests (test_gpu_ops /
+test_gpu_tc / pre- and post-processing: they test the kernels themselves, which only a GPU can)."""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.timeout(900)
+def test_gpu_model_tests_hold_on_the_cpu_through_the_products_host_path():
+    files = ['tests/test_reference_golden.py', 'tests/test_gpu_reception.py', 'tests/test_gpu_spnet.py',
+             'tests/test_merge_model.py', 'tests/test_keras_compat.py', 'tests/test_gpu_model.py']
+    cmd = [sys.executable, os.path.join(ROOT, 'tests', 'fake_cuda.py'), '--arithmetic', '-m', 'pytest'] + files + [
+        '-m', 'gpu', '-q', '-p', 'no:cacheprovider',
+        '--deselect', 'tests/test_gpu_model.py::test_no_unexpected_cuda_core_fallback',
+        '--deselect', 'tests/test_gpu_reception.py::test_c2_batch32_equals_32_single_frame_calls']
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=880, cwd=ROOT)
+    tail = out.stdout[-3000:]
+    assert out.returncode == 0, tail + out.stderr[-2000:]
+    m = re.search(r'(\d+) passed', tail)
+    assert m and int(m.group(1)) >= 27 and 'failed' not in tail and 'skipped' not in tail.split('\n')[-2], tail
