@@ -199,7 +199,46 @@ def _mask_mul(ctx, p, c, rows, dim, out, stream):
     _dense(out, rows, dim)[...] = _dense(p, rows, dim) * _dense(c, rows, 1)
 
 
+def _pose_eval(ctx, pred, ldp, afmat, per_sample, inverse, y_true, head, refp, n, nj, out_pose, hits, valid, dsum, stream):
+    """csrc/postprocess.cu: (inverse) affine of the poses, per-joint hit / valid counters and distance sums accumulated"""
+    import numpy as np
+    P = _dense(pred, n, nj, ldp).astype(np.float64)
+    A = _dense(afmat, n if per_sample else 1, 3, 3).astype(np.float64)
+    M = np.linalg.inv(A) if inverse else A
+    M = np.broadcast_to(M, (n, 3, 3))
+    t = np.einsum('nij,nkj->nki', M[:, :2, :2], P[:, :, :2]) + M[:, None, :2, 2]
+    _dense(out_pose, n, nj, 2)[...] = t
+    if y_true:
+        g = _dense(y_true, n, nj, 2).astype(np.float64)
+        ok = (g[..., 0] > -1e6) & (g[..., 1] > -1e6)
+        d = np.sqrt(((g - t) ** 2).sum(axis=-1))
+        np.ctypeslib.as_array(C.cast(valid, C.POINTER(C.c_int32)), shape=(nj,))[...] += ok.sum(axis=0).astype(np.int32)
+        np.ctypeslib.as_array(C.cast(dsum, C.POINTER(C.c_double)), shape=(nj,))[...] += np.where(ok, d, 0.0).sum(axis=0)
+        if head:
+            d = d / _dense(head, n, 1).astype(np.float64)
+        hit = ok & (d <= np.float64(np.float32(refp)))
+        np.ctypeslib.as_array(C.cast(hits, C.POINTER(C.c_int32)), shape=(nj,))[...] += hit.sum(axis=0).astype(np.int32)
+
+
+def _crop_resize_norm(ctx, table, n, max_ch, bounds, coefs, rh, rw, power, tmp, tmp_stride, out, stream):
+    """csrc/preprocess.cu: per frame crop window (outside the image = 0) -> Pillow's bilinear resize -> flip ->
+    normalize_channels; the resampling tables the host sent are not read here: the oracle derives its own"""
+    import numpy as np
+    from deephar_b200._ffi import dh_frame_src
+    from oracle import preprocess as OP
+    frames = C.cast(table, C.POINTER(dh_frame_src))
+    o = _dense(out, n, rh, rw, 3)
+    pw = 1 if not power else tuple(float(v) for v in _f32(power, 3))
+    for i in range(n):
+        f = frames[i]
+        img = np.ctypeslib.as_array(C.cast(f.data, C.POINTER(C.c_uint8)), shape=(int(f.h), int(f.stride)))[:, :int(f.w) * 3]
+        img = img.reshape(int(f.h), int(f.w), 3)
+        box = (int(f.x0), int(f.y0), int(f.x0) + int(f.cw), int(f.y0) + int(f.ch))
+        o[i] = OP.eval_frame(img, box, (rw, rh), hflip=bool(f.hflip), channel_power=pw)
+
+
 ARITHMETIC = {
+    'dh_pose_eval_f32': _pose_eval, 'dh_crop_resize_norm_u8': _crop_resize_norm,
     'dh_conv2d_f32': _conv(False), 'dh_sepconv2d_f32': _conv(True), 'dh_maxpool2d_f32': _maxpool,
     'dh_upsample2x_add_f32': _upsample_add, 'dh_add_n_f32': _add_n, 'dh_softargmax2d_f32': _softargmax2d,
     'dh_softargmax2d_ctx_f32': _softargmax2d_ctx, 'dh_softargmax3d_f32': _softargmax3d,

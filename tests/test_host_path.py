@@ -9,7 +9,10 @@ keras_compat front end.  The unchanged GPU tests then hold at their GPU toleranc
 SPNet and merge-model parity, CUDA-graph replay == plain launches, predict edge cases, Keras-HDF5-driven forward, and the
 reference-builder goldens of every BASELINE config at full size.  Deselected: tests that read kernel-internal counters
 (`dh_fallback_count`), the 64-forward batch-independence test (CPU time), and the direct C-ABI op tests (test_gpu_ops /
-test_gpu_tc / pre- and post-processing: they test the kernels themselves, which only a GPU can)."""
+test_gpu_tc: they test the kernels themselves, which only a GPU can).  The input-pipeline and evaluator entry points have
+stand-ins too (the oracle's Pillow-exact resampler and PCKh arithmetic behind `dh_crop_resize_norm_u8` / `dh_pose_eval_f32`),
+so their GPU tests and `__graft_entry__.smoke()` -- the first thing the driver runs on the GPU box -- go through
+FramePipeline's planning / packing and postprocess' argument marshalling as well."""
 import os
 import re
 import subprocess
@@ -23,7 +26,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 @pytest.mark.timeout(900)
 def test_gpu_model_tests_hold_on_the_cpu_through_the_products_host_path():
     files = ['tests/test_reference_golden.py', 'tests/test_gpu_reception.py', 'tests/test_gpu_spnet.py',
-             'tests/test_merge_model.py', 'tests/test_keras_compat.py', 'tests/test_gpu_model.py']
+             'tests/test_merge_model.py', 'tests/test_keras_compat.py', 'tests/test_gpu_model.py',
+             'tests/test_postprocess.py', 'tests/test_preprocess.py']
     cmd = [sys.executable, os.path.join(ROOT, 'tests', 'fake_cuda.py'), '--arithmetic', '-m', 'pytest'] + files + [
         '-m', 'gpu', '-q', '-p', 'no:cacheprovider',
         '--deselect', 'tests/test_gpu_model.py::test_no_unexpected_cuda_core_fallback',
@@ -32,4 +36,13 @@ def test_gpu_model_tests_hold_on_the_cpu_through_the_products_host_path():
     tail = out.stdout[-3000:]
     assert out.returncode == 0, tail + out.stderr[-2000:]
     m = re.search(r'(\d+) passed', tail)
-    assert m and int(m.group(1)) >= 27 and 'failed' not in tail and 'skipped' not in tail.split('\n')[-2], tail
+    assert m and int(m.group(1)) >= 32 and 'failed' not in tail and 'skipped' not in tail.split('\n')[-2], tail
+
+
+@pytest.mark.timeout(300)
+def test_smoke_entry_point_through_the_host_path():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'tests', 'fake_cuda.py'), '--arithmetic',
+                          os.path.join(ROOT, '__graft_entry__.py'), 'smoke'], capture_output=True, text=True, timeout=280, cwd=ROOT)
+    assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-1500:]
+    assert 'smoke ok: input pipeline bit-exact' in out.stdout
+
