@@ -63,8 +63,8 @@ def main():
             ((128, 128, 3), 'pa17j3d', dict(num_actions=[], action_pyramids=[], predict_rootz=True, growth=64)),
             ((4, 128, 128, 3), 'pa16j2d', dict(pose_replica=True, kernel_size=(3, 3))),
             ((4, 128, 128, 3), 'pa20j3d', dict(num_actions=[15, 60], sam_alpha=2)),
-            ((16, 128, 128, 3), 'pa17j3d', dict(action_pyramids=[2], image_div=4)),
-            ((8, 128, 128, 3), 'pa16j2d', dict(num_pyramids=3, action_pyramids=[1, 3], num_pose_features=160,
+            ((8, 128, 128, 3), 'pa17j3d', dict(action_pyramids=[2], image_div=4)),
+            ((4, 128, 128, 3), 'pa16j2d', dict(num_pyramids=3, action_pyramids=[1, 3], num_pose_features=160,
                                                num_visual_features=96))):
         kw = dict(base)
         kw.update(extra)
