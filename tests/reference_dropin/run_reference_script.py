@@ -376,7 +376,7 @@ def main():
         'weights_are_the_files': set(held) == set(oracle.table) and all(np.array_equal(held[k], oracle.table[k])
                                                                        for k in oracle.table),
         'launches': len(impl.plan.kops), 'plan_emulation_max_err': plan_err, 'plan_checked': verify_plan(impl.plan, impl.graph), 'script_printed': printed.getvalue()[-600:],
-        'forward': 'B200' if ON_GPU else 'oracle (CPU stand-in)'}))
+        'forward': 'Model.predict' if ON_GPU else 'oracle (CPU stand-in)'}))
 
 
 if __name__ == '__main__':
