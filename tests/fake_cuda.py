@@ -237,8 +237,19 @@ def _crop_resize_norm(ctx, table, n, max_ch, bounds, coefs, rh, rw, power, tmp, 
         o[i] = OP.eval_frame(img, box, (rw, rh), hflip=bool(f.hflip), channel_power=pw)
 
 
+def _allgather(ctx, send, recv, count, stream):
+    """csrc/comm.cu dh_allgather_f32 (ncclAllGather): recv[r * count ...] = rank r's send -- over gloo here"""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size()
+    src = torch.from_numpy(_f32(send, count).copy())
+    dst = torch.empty(world * count, dtype=torch.float32)
+    dist.all_gather_into_tensor(dst, src)
+    _f32(recv, world * count)[...] = dst.numpy()
+
+
 ARITHMETIC = {
-    'dh_pose_eval_f32': _pose_eval, 'dh_crop_resize_norm_u8': _crop_resize_norm,
+    'dh_allgather_f32': _allgather, 'dh_pose_eval_f32': _pose_eval, 'dh_crop_resize_norm_u8': _crop_resize_norm,
     'dh_conv2d_f32': _conv(False), 'dh_sepconv2d_f32': _conv(True), 'dh_maxpool2d_f32': _maxpool,
     'dh_upsample2x_add_f32': _upsample_add, 'dh_add_n_f32': _add_n, 'dh_softargmax2d_f32': _softargmax2d,
     'dh_softargmax2d_ctx_f32': _softargmax2d_ctx, 'dh_softargmax3d_f32': _softargmax3d,

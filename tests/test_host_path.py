@@ -49,3 +49,27 @@ def test_smoke_entry_point_through_the_host_path():
     assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-1500:]
     assert 'smoke ok: input pipeline bit-exact' in out.stdout
 
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize('world,n_clips', [(2, 5), (4, 3)])
+def test_sharded_forward_and_exchange_through_the_c_abi(world, n_clips):
+    """SURVEY 8e on the stand-in device: every rank runs the product's forward on its contiguous shard (ragged shards; with
+    4 ranks and 3 clips one rank holds nothing) and the outputs are exchanged with dist.Comm -- dh_comm_unique_id /
+    dh_comm_init / dh_allgather_f32 through the ctypes binding, gloo standing in for NCCL -- into the whole batch's
+    result, in clip order, equal to the oracle's forward of the unsharded batch."""
+    import json
+    import socket
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    env = {k: v for k, v in os.environ.items() if k not in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK')}
+    out = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(world),
+                          '--master-addr', '127.0.0.1', '--master-port', str(port), os.path.join(ROOT, 'tests', 'fake_cuda.py'),
+                          '--arithmetic', os.path.join(ROOT, 'tests', 'run_sharded_forward.py'), str(n_clips)],
+                         capture_output=True, text=True, timeout=280, cwd=ROOT, env=env)
+    assert out.returncode == 0, out.stderr[-3000:]
+    got = json.loads([l for l in out.stdout.splitlines() if l.startswith('{')][-1])
+    assert got['world'] == world and got['shape'] == [n_clips, 6, 15] and got['pose_shape'] == [n_clips, 4 * 16 * 3]
+    assert got['max_err'] <= 1e-3 and got['pose_max_err'] <= 1e-3 and got['argmax_equal']
+
