@@ -531,11 +531,18 @@ class Model(object):
         if not pinned:
             if getattr(self, '_stage', None) is None or self._stage.numel() < batch_size * item:
                 self._stage = torch.empty(batch_size * item, dtype=torch.float32).pin_memory()
-        # per-output pinned result buffers for the whole call (one D2H copy per output per batch)
-        res = []
-        for t in self.graph.outputs:
-            shp = self._keras_shape(t, n if t.kind == 'clip' or T == 1 else n * T)
-            res.append(torch.empty(shp, dtype=torch.float32).pin_memory())
+        # per-output pinned result buffers for the whole call (one D2H copy per output per batch), kept for the next call
+        # with the same item count: page-locking 2 x (number of outputs) buffers costs more than a small forward, and the
+        # evaluators call predict once per clip (exp/common/penn_tools.py:124).  The caller gets copies.
+        held = getattr(self, '_pinned_results', None)
+        if held is not None and held[0] == n:
+            res = held[1]
+        else:
+            res = []
+            for t in self.graph.outputs:
+                shp = self._keras_shape(t, n if t.kind == 'clip' or T == 1 else n * T)
+                res.append(torch.empty(shp, dtype=torch.float32).pin_memory())
+            self._pinned_results = (n, res)
         # The host->device copy of batch k+1 runs on a side stream while batch k computes
         # (two device staging buffers; events order copy -> compute -> buffer reuse).
         main = torch.cuda.current_stream()
@@ -575,7 +582,7 @@ class Model(object):
             for r, o in zip(res, outs):
                 r[i:j].copy_(o, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        outs = [r.numpy() for r in res]
+        outs = [r.numpy().copy() for r in res]
         return outs[0] if len(outs) == 1 else outs
 
     def output_subset(self, indices, name=None):

@@ -90,6 +90,14 @@ def test_predict_edge_cases(cuda):
     assert len(m._bound) <= m.max_bound
     with pytest.raises(ValueError):
         m.predict(np.zeros((1, 32, 32, 3), np.float32))
+    # results are the caller's: a later call with the same batch size (the pinned result buffers are kept) must not
+    # write into arrays handed out earlier; a one-element input list is the array (keras)
+    y = synth.synth_frames(5, 64, 64, seed=3)
+    first = [o.copy() for o in b]
+    c = m.predict([y], batch_size=5)
+    assert all(np.array_equal(u, v) for u, v in zip(b, first)) and np.abs(c[0] - b[0]).max() > 1e-4
+    d = m.predict(x, batch_size=None)
+    assert all(np.abs(u - v).max() <= 1e-6 for u, v in zip(d, first))
 
 
 def test_keras_h5_weights_drive_the_device_path(cuda, tmp_path):
