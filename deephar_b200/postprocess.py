@@ -79,6 +79,17 @@ def pckh(y_true, y_pred, head_size, refp=0.5, A=None):
     return float(hits[used].sum().item()) / float(valid[used].sum().item())
 
 
+def pckh_per_joint(y_true, y_pred, head_size, refp=0.5, A=None):
+    """deephar/measures.py:108-146 (the table the MPII evaluator prints for its last block, mpii_tools.py:124-127) as an
+    array: per joint, the share of annotated samples whose prediction lies within refp x head size; NaN for a joint no
+    sample annotates.  Same kernel launch as `pckh` (its per-joint counters), `A` as there."""
+    eye = np.eye(3, dtype=np.float32)
+    _, hits, valid, _ = _run(y_pred, A if A is not None else eye, A is not None, y_true, head_size, refp)
+    hits, valid = hits.cpu().numpy().astype(np.float64), valid.cpu().numpy().astype(np.float64)
+    with np.errstate(invalid='ignore', divide='ignore'):
+        return hits / valid
+
+
 def mean_distance_error(y_true, y_pred):
     """deephar/measures.py:18-47 for 2-D poses."""
     _, _, valid, dsum = _run(y_pred, np.eye(3, dtype=np.float32), False, y_true, None, 0.0)

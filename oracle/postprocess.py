@@ -35,6 +35,15 @@ def pckh(y_true, y_pred, head_size, refp=0.5):
     return float(((dist <= refp) * valid).sum() / valid.sum())
 
 
+def pckh_per_joint(y_true, y_pred, head_size, refp=0.5):
+    """measures.py:108-146 without the printing: per joint, the share of valid samples within refp x head size."""
+    y_true, y_pred = np.asarray(y_true, np.float64), np.asarray(y_pred, np.float64)
+    valid = np.stack([_valid(y) for y in y_true]).astype(np.float64)
+    dist = np.sqrt(((y_true - y_pred) ** 2).sum(axis=-1)) / np.asarray(head_size, np.float64).reshape(-1, 1)
+    with np.errstate(invalid='ignore', divide='ignore'):
+        return ((dist <= refp) * valid).sum(axis=0) / valid.sum(axis=0)
+
+
 def mean_distance_error(y_true, y_pred):
     """measures.py:18-47."""
     y_true, y_pred = np.asarray(y_true, np.float64), np.asarray(y_pred, np.float64)

@@ -20,6 +20,24 @@ def test_oracle_matches_reference_postprocessing():
     assert oracle_pp.mean_distance_error(Z['y_true'], Z['y_pred']) == pytest.approx(float(Z['mde']), rel=1e-12)
 
 
+def test_oracle_per_joint_pckh_matches_the_table_the_reference_prints():
+    """tests/golden/ref_pckh_per_joint.npz: the ' %.2f | ' cells of deephar/measures.py::pckh_per_joint's printout"""
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'ref_pckh_per_joint.npz'))
+    for refp in (0.5, 0.2):
+        got = 100.0 * oracle_pp.pckh_per_joint(Z['y_true'], Z['y_pred'], Z['head'], refp)
+        assert got.shape == (16,) and np.abs(got - G['percent_%s' % refp]).max() <= 0.005 + 1e-9
+
+
+@pytest.mark.gpu
+def test_gpu_per_joint_pckh(cuda):
+    from deephar_b200 import postprocess as pp
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'ref_pckh_per_joint.npz'))
+    for refp in (0.5, 0.2):
+        got = 100.0 * pp.pckh_per_joint(Z['y_true'], Z['y_pred_crop'], Z['head'], refp, A=Z['A'])
+        # a joint sitting within fp32 rounding of the threshold may flip one sample of ~33: allow one count per joint
+        assert got.shape == (16,) and np.abs(got - G['percent_%s' % refp]).max() <= 100.0 / 30 + 0.005
+
+
 @pytest.mark.gpu
 def test_gpu_postprocessing_matches_reference(cuda):
     from deephar_b200 import postprocess as pp
